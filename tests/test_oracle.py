@@ -1,0 +1,327 @@
+"""Pins the CPU oracle (oracle/) before anything is compared against it.
+
+Sources of truth, in order of strength:
+  * tests/golden/blake3_vectors.json -- produced by the Python binding of the Rust `blake3` crate the
+    reference hashes with: raw hashes, the leaf rule (lcpc-2d/src/lib.rs:719-735) and the node rule
+    (:770-775);
+  * tests/golden/expander_vectors.npz -- produced by running the reference's own
+    doc/encoding.py: pins lcpc-brakedown-pc/src/encode.rs:36-110 (recursion, layout, orientation);
+  * Python big-int arithmetic + SURVEY.md App. A constants -- pins the field/NTT restatement
+    (the reference holds no known-answer vector for those: "parity unpinned");
+  * the reference's own differential/property tests (lcpc-2d/src/tests.rs:127-236) restated.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+FIELDS = [O.FT63, O.FT127, O.FT191, O.FT255]
+
+# SURVEY.md Appendix A (derived with sympy from lcpc-test-fields/src/lib.rs:19-20,31-32,43-44,55-56)
+CONSTS = {
+    O.FT63: dict(p=0x46d0760000000001, gen=10, s=41, inv=0x46d075ffffffffff),
+    O.FT127: dict(p=0x6e754097ba20e0bf7f2bd90000000001, gen=3, s=40, inv=0x7f2bd8ffffffffff),
+    O.FT191: dict(p=0x453708aa3fbc8dda936888270ceecbcdd246820000000001, gen=5, s=41, inv=0xd24681ffffffffff),
+    O.FT255: dict(p=0x663c799b6e4d2900fda9df04b9575969ef73c79086595f3002a4f20000000001, gen=5, s=41,
+                  inv=0x02a4f1ffffffffff),
+}
+
+
+def pattern(n):
+    return bytes(i % 251 for i in range(n))
+
+
+def rand_ints(rng, p, n):
+    return [int.from_bytes(rng.bytes(40), "little") % p for _ in range(n)]
+
+
+# ------------------------------------------------------------------ fields
+@pytest.mark.parametrize("field", FIELDS)
+def test_field_constants(field):
+    info, c = O.field_info(field), CONSTS[field]
+    L = info["limbs"]
+    R = 1 << (64 * L)
+    assert info["modulus"] == c["p"] and info["s"] == c["s"] and info["inv"] == c["inv"]
+    assert info["num_bits"] == c["p"].bit_length()
+    assert info["r"] == R % c["p"] and info["r2"] == R * R % c["p"]
+    t = (c["p"] - 1) >> c["s"]
+    assert info["rou_mont"] == pow(c["gen"], t, c["p"]) * R % c["p"]
+    assert (c["inv"] * c["p"] + 1) % (1 << 64) == 0
+
+
+@pytest.mark.parametrize("field", FIELDS)
+def test_field_ops_vs_bigint(field):
+    p = CONSTS[field]["p"]
+    L = O.FIELD_LIMBS[field]
+    R = 1 << (64 * L)
+    rng = np.random.default_rng(field)
+    a = rand_ints(rng, p, 300) + [0, 1, p - 1, p - 1, 0]
+    b = rand_ints(rng, p, 300) + [0, p - 1, p - 1, 1, p - 1]
+    am, bm = O.to_mont(field, a), O.to_mont(field, b)
+    assert O.elems_to_ints(am) == [x * R % p for x in a]
+    assert O.from_mont(field, am) == a
+    assert O.from_mont(field, O.field_op(field, "add", am, bm)) == [(x + y) % p for x, y in zip(a, b)]
+    assert O.from_mont(field, O.field_op(field, "sub", am, bm)) == [(x - y) % p for x, y in zip(a, b)]
+    assert O.from_mont(field, O.field_op(field, "mul", am, bm)) == [(x * y) % p for x, y in zip(a, b)]
+    nz = [x for x in a if x]
+    inv = O.from_mont(field, O.field_op(field, "inv", O.to_mont(field, nz)))
+    assert all(x * y % p == 1 for x, y in zip(nz, inv))
+    # to_repr = canonical little-endian bytes (PrimeFieldReprEndianness = "little")
+    rep = O.to_repr(field, am)
+    assert [int.from_bytes(r.tobytes(), "little") for r in rep] == a
+
+
+@pytest.mark.parametrize("field", FIELDS)
+def test_random_elems_in_range(field):
+    x = O.random_elems(field, 500, seed=3, stream=1)
+    assert all(v < CONSTS[field]["p"] for v in O.elems_to_ints(x))
+    assert (O.random_elems(field, 500, seed=3, stream=1) == x).all()
+    assert not (O.random_elems(field, 500, seed=3, stream=2) == x).all()
+
+
+# ------------------------------------------------------------------ hash / rng
+def test_blake3_golden_raw():
+    g = json.load(open(os.path.join(GOLD, "blake3_vectors.json")))
+    for v in g["raw"]:
+        assert O.blake3(pattern(v["len"])).hex() == v["hash"], v["len"]
+    assert O.blake3(bytes(64)).hex() == g["node_zero_zero"]
+    n = g["node_left_right"]
+    assert O.blake3(bytes.fromhex(n["left"]) + bytes.fromhex(n["right"])).hex() == n["hash"]
+
+
+def test_blake3_vs_python_binding():
+    blake3 = pytest.importorskip("blake3")
+    rng = np.random.default_rng(7)
+    for n in [0, 1, 64, 65, 1024, 1025, 2047, 2048, 2049, 3072, 5000, 8224, 40000]:
+        data = rng.bytes(n)
+        assert O.blake3(data) == blake3.blake3(data).digest()
+
+
+def test_leaf_rule_golden():
+    """leaf = D(0^32 || repr(col[0]) || ..), lcpc-2d/src/lib.rs:719-735, through merkleize."""
+    g = json.load(open(os.path.join(GOLD, "blake3_vectors.json")))
+    fld = {8: O.FT63, 16: O.FT127, 24: O.FT191, 32: O.FT255}
+    for v in g["leaf_of_1_to_n"]:
+        field, n_rows = fld[v["elem_bytes"]], v["n_rows"]
+        col = O.to_mont(field, list(range(1, n_rows + 1)))
+        # a 2-column matrix whose columns are both 1..n_rows
+        comm = np.repeat(col[:, None, :], 2, axis=1).reshape(-1, O.FIELD_LIMBS[field])
+        for serial in (False, True):
+            h = O.merkleize(field, comm, n_rows, 2, serial=serial)
+            assert h[0].tobytes().hex() == v["hash"] and h[1].tobytes().hex() == v["hash"]
+            assert h[2].tobytes() == O.blake3(h[0].tobytes() + h[1].tobytes())
+
+
+def test_chacha_rfc8439_block():
+    # RFC 8439 2.3.2 with the IETF nonce folded into (counter, stream) words 12..15
+    key = np.frombuffer(bytes(range(32)), dtype="<u4")
+    counter = 1 | (0x09000000 << 32)
+    stream = 0x4A000000 | (0x00000000 << 32)
+    out = O.chacha_block(key, counter, stream)
+    assert out[0] == 0xE4E7F110 and out[15] == 0x4E3C50A2 and out[4] == 0xC7F4D1C7 and out[7] == 0x4E6CD4C3
+
+
+# ------------------------------------------------------------------ NTT
+def direct_dft_bitrev(x, w, p):
+    n = len(x)
+    lg = n.bit_length() - 1
+    out = [0] * n
+    for i in range(n):
+        k = int(format(i, f"0{lg}b")[::-1], 2) if lg else 0
+        out[i] = sum(xj * pow(w, j * k, p) for j, xj in enumerate(x)) % p
+    return out
+
+
+@pytest.mark.parametrize("field", FIELDS)
+@pytest.mark.parametrize("n", [1, 2, 8, 64])
+def test_fft_io_is_bitreversed_dft(field, n):
+    """fffft fft_io: position i holds X[bitrev(i)], X[k] = sum_j x_j w^(jk), w = rou^(2^(S-log n))."""
+    c = CONSTS[field]
+    p = c["p"]
+    rng = np.random.default_rng(n)
+    x = rand_ints(rng, p, n)
+    w = pow(pow(c["gen"], (p - 1) >> c["s"], p), 1 << (c["s"] - (n.bit_length() - 1)), p)
+    assert O.from_mont(field, O.root_of_unity(field, n).reshape(1, -1))[0] == w
+    got = O.from_mont(field, O.fft_io(field, O.to_mont(field, x)))
+    assert got == direct_dft_bitrev(x, w, p)
+    back = O.from_mont(field, O.ifft_oi(field, O.fft_io(field, O.to_mont(field, x))))
+    assert back == x
+
+
+def test_fft_io_survey_pin():
+    # Ft63 fft_io([1,2,3,4,0,0,0,0]) canonical values
+    got = O.from_mont(O.FT63, O.fft_io(O.FT63, O.to_mont(O.FT63, [1, 2, 3, 4, 0, 0, 0, 0])))
+    assert got == [0xa, 0x46d075ffffffffff, 0x3f1b208b6be814ac, 0x07b555749417eb51, 0x3978407655337b20,
+                   0x247835e7671446dc, 0x1208be327d1cea3e, 0x1da7b76fc69b53cc]
+
+
+def test_fft_errors():
+    with pytest.raises(ValueError):
+        O.fft_io(O.FT63, O.to_mont(O.FT63, [1, 2, 3]))
+
+
+# ------------------------------------------------------------------ dims / parameters
+def test_log2_and_degree_tests():
+    # lcpc-2d/src/tests.rs:127-134 and lib.rs:613-616
+    assert O.n_degree_tests(128, 1 << 17, 254) == 1
+    assert O.n_degree_tests(128, 357699, 126) == 2
+    assert O.n_degree_tests(128, 1 << 10, 62) == 3
+
+
+def test_ligero_dims_survey_table():
+    # SURVEY.md 8 config shapes (restating lcpc-ligero-pc/src/lib.rs:70-112)
+    assert O.ligero_get_dims(O.FT255, 1 << 10) == (2, 512, 1024)
+    assert O.ligero_get_dims(O.FT255, 1 << 20) == (64, 16384, 32768)
+    assert O.ligero_get_dims(O.FT255, 1 << 24) == (256, 65536, 131072)
+    assert O.ligero_get_dims(O.FT255, 1 << 28) == (1024, 262144, 524288)
+    assert O.Encoding.ligero(O.FT255, 1 << 20).get_n_col_opens() == 309
+
+
+def test_ligero_get_dims_property():
+    # lcpc-ligero-pc/src/tests.rs:22-41
+    rng = np.random.default_rng(0)
+    for lgl in range(2, 30, 3):
+        for _ in range(8):
+            length = int(rng.integers(1 << lgl, 2 << lgl))
+            n_rows, n_per_row, n_cols = O.ligero_get_dims(O.FT255, length)
+            assert n_rows * n_per_row >= length and (n_rows - 1) * n_per_row < length
+            assert n_cols & (n_cols - 1) == 0 and n_per_row * 2 == n_cols
+
+
+def test_sdig_dims_survey_table():
+    pre, post = O.sdig_level_dims(O.FT127, 3, 235173)
+    assert [(n, m, d) for n, m, d in pre] == [(235173, 41861, 8), (41861, 7452, 8), (7452, 1327, 8),
+                                              (1327, 237, 9), (237, 43, 14), (43, 8, 7)]
+    assert [(n, m, d) for n, m, d in post][::-1] == [(13, 10, 8), (66, 58, 31), (361, 331, 28),
+                                                     (2019, 1864, 24), (11335, 10475, 23), (63671, 58855, 23)]
+    assert O.lib().lcpc_oracle_sdig_n_col_opens(3) == 6593
+
+
+# ------------------------------------------------------------------ brakedown
+def _npz_case(z, name):
+    field = int(z[name + "_field"][0])
+    nlev = int(z[name + "_n_levels"][0])
+
+    def mats(tag):
+        out = []
+        for i in range(nlev):
+            m, n = (int(v) for v in z[f"{name}_{tag}{i}_shape"])
+            out.append(dict(m=m, n=n, ptrs=z[f"{name}_{tag}{i}_ptrs"], idxs=z[f"{name}_{tag}{i}_idxs"].astype(np.uint64),
+                            data=z[f"{name}_{tag}{i}_data"]))
+        return out
+    return field, mats("pre"), mats("post"), z[name + "_input_mont"], z[name + "_codeword_mont"]
+
+
+@pytest.mark.parametrize("name", ["ft63_n400", "ft127_n150", "ft255_n64"])
+def test_expander_encode_vs_reference_python_spec(name):
+    z = np.load(os.path.join(GOLD, "expander_vectors.npz"))
+    field, pre, post, x, want = _npz_case(z, name)
+    enc = O.Encoding.sdig_from_matrices(field, pre, post)
+    row = np.zeros((enc.n_cols, enc.L), np.uint64)
+    row[:x.shape[0]] = x
+    assert (enc.encode(row) == want).all()
+
+
+def test_matgen_shape_contract():
+    """matgen.rs:114-188: every CSC column has exactly d sorted distinct rows and non-zero values;
+    brakedown tests.rs:77-93: generate + encode run through the offset asserts."""
+    for n, seed in [(256, 0), (1000, 1), (4351, 2)]:
+        enc = O.Encoding.sdig_from_dims(O.FT63, n, seed=seed)
+        pre_d, post_d = O.sdig_level_dims(O.FT63, 3, n)
+        pre, post = enc.matrices()
+        for M, (nn, mm, d) in list(zip(pre, pre_d)) + list(zip(post, post_d)):
+            assert (M["n"], M["m"]) == (nn, mm)
+            assert (np.diff(M["ptrs"].astype(np.int64)) == d).all()
+            idx = M["idxs"].reshape(nn, d).astype(np.int64)
+            assert (np.diff(idx, axis=1) > 0).all() and idx.max() < mm
+            assert M["data"].any(axis=1).all()
+        row = np.zeros((enc.n_cols, 1), np.uint64)
+        row[:n] = O.random_elems(O.FT63, n, seed=9)
+        enc.encode(row)
+        # same seed -> same code; other seed -> other code
+        again = O.Encoding.sdig_from_dims(O.FT63, n, seed=seed).matrices()[0][0]
+        assert (again["idxs"] == pre[0]["idxs"]).all() and (again["data"] == pre[0]["data"]).all()
+
+
+def test_encode_is_linear():
+    # lcpc-2d/src/tests.rs:193-236 pins linearity of encode for the commit check
+    for enc in (O.Encoding.ligero_from_dims(O.FT127, 32, 64), O.Encoding.sdig_from_dims(O.FT127, 300, seed=4)):
+        f, n = enc.field, enc.n_per_row
+        a = np.zeros((enc.n_cols, enc.L), np.uint64)
+        b = a.copy()
+        a[:n], b[:n] = O.random_elems(f, n, seed=1), O.random_elems(f, n, seed=2)
+        s = a.copy()
+        s[:n] = O.field_op(f, "add", a[:n], b[:n])
+        assert (enc.encode(s) == O.field_op(f, "add", enc.encode(a), enc.encode(b))).all()
+
+
+# ------------------------------------------------------------------ commit / prove pieces
+@pytest.mark.parametrize("mk", [lambda: O.Encoding.ligero(O.FT255, 1 << 10),
+                                lambda: O.Encoding.ligero_from_dims(O.FT63, 16, 64, rho=(1, 4)),
+                                lambda: O.Encoding.sdig(O.FT127, 3000, seed=1)])
+def test_commit_structure(mk):
+    enc = mk()
+    f = enc.field
+    length = enc.n_per_row * 3 - 5  # ragged last row
+    x = O.random_elems(f, length, seed=11)
+    c = enc.commit(x)
+    nr, npr, nc = c["n_rows"], c["n_per_row"], c["n_cols"]
+    assert nr == 3
+    coeffs = c["coeffs"].reshape(nr, npr, enc.L)
+    comm = c["comm"].reshape(nr, nc, enc.L)
+    assert (coeffs.reshape(-1, enc.L)[:length] == x).all() and not coeffs.reshape(-1, enc.L)[length:].any()
+    for r in range(nr):
+        row = np.zeros((nc, enc.L), np.uint64)
+        row[:npr] = coeffs[r]
+        assert (enc.encode(row) == comm[r]).all()
+    # merkleize == merkleize_ser (lcpc-2d/src/tests.rs:136-149)
+    assert (O.merkleize(f, c["comm"], nr, nc, serial=True) == c["hashes"]).all()
+    np2 = 1 << (nc - 1).bit_length()
+    assert not c["hashes"][nc:np2].any()
+    # leaf rule straight from the definition
+    col = 5
+    data = bytes(32) + b"".join(O.to_repr(f, comm[:, col]).tobytes()[i * 8 * enc.L:(i + 1) * 8 * enc.L] for i in range(nr))
+    assert c["hashes"][col].tobytes() == O.blake3(data)
+    # open_column verifies against the root (lcpc-2d/src/tests.rs:167-191)
+    for column in [0, 1, nc - 1, nc // 2]:
+        cv, path = O.open_column(f, c["comm"], c["hashes"], nr, nc, column)
+        assert (cv == comm[:, column]).all() and len(path) == (nc - 1).bit_length()
+        assert O.verify_column_path(f, cv, path, column, c["root"])
+        assert not O.verify_column_path(f, cv, path, column ^ 1, c["root"])
+    with pytest.raises(IndexError):
+        O.open_column(f, c["comm"], c["hashes"], nr, nc, nc)
+
+
+def test_collapse_matches_serial_and_bigint():
+    # lcpc-2d/src/tests.rs:151-165 (eval_outer vs eval_outer_ser)
+    f, nr, npr = O.FT127, 7, 100
+    p = CONSTS[f]["p"]
+    coeffs = O.random_elems(f, nr * npr, seed=5)
+    tensor = O.random_elems(f, nr, seed=6)
+    a = O.collapse(f, coeffs, tensor, nr, npr)
+    assert (a == O.collapse(f, coeffs, tensor, nr, npr, serial=True)).all()
+    ci, ti = O.from_mont(f, coeffs), O.from_mont(f, tensor)
+    want = [sum(ti[r] * ci[r * npr + c] for r in range(nr)) % p for c in range(npr)]
+    assert O.from_mont(f, a) == want
+
+
+def test_commit_evaluation_property():
+    """lcpc-2d/src/tests.rs:193-236 (i): sum coeffs*x^i equals <inner, collapse(coeffs, outer)>."""
+    f = O.FT63
+    p = CONSTS[f]["p"]
+    enc = O.Encoding.ligero_from_dims(f, 32, 64)
+    length = 32 * 4
+    x = O.random_elems(f, length, seed=21)
+    c = enc.commit(x)
+    pt = 0x123456789abcdef % p
+    xi = O.from_mont(f, x)
+    direct = sum(v * pow(pt, i, p) for i, v in enumerate(xi)) % p
+    inner = [pow(pt, i, p) for i in range(32)]
+    outer = [pow(pt, 32 * r, p) for r in range(4)]
+    poly = O.from_mont(f, O.collapse(f, c["coeffs"], O.to_mont(f, outer), 4, 32))
+    assert sum(a * b for a, b in zip(poly, inner)) % p == direct
