@@ -1,0 +1,169 @@
+/*
+ * include/lcpc_b200.h -- C ABI of the B200-native commit/prove engine for lcpc-2d's hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  A Rust `lcpc-2d`
+ * built with the shim shown in INTEGRATION.md binds exactly these symbols (bindgen/extern "C").
+ * Each entry point names the reference item it replaces (paths relative to the reference repo).
+ *
+ * Field elements cross the boundary as the in-memory image of the reference's
+ * `struct FtNNN([u64; L])` (lcpc-test-fields/src/lib.rs:22,34,46,58): L little-endian u64 limbs in
+ * Montgomery form, so a Rust `&[F]` can be passed as `*const u64` without conversion.
+ * Digests are 32-byte BLAKE3 outputs (`Output<D>` with D = blake3::Hasher).
+ *
+ * Every function returns LCPC_B200_OK (0) or a negative status; nothing unwinds across the boundary.
+ * `lcpc_b200_last_error(ctx)` returns a human-readable description of the last failure on `ctx`.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ * LCPC_B200_ERR_CUDA.
+ *
+ * Threading: a context serialises its calls internally (one stream, one mutex); use one context per
+ * host thread for concurrency.  `LcEncoding::encode` is called from many rayon workers in the
+ * reference (lcpc-2d/src/lib.rs:648-653); the batched entry points here replace that loop.
+ */
+#ifndef LCPC_B200_H
+#define LCPC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes; the Rust shim maps them onto ProverError (lcpc-2d/src/lib.rs:111-139) */
+#define LCPC_B200_OK 0
+#define LCPC_B200_ERR_BAD_ARG (-1)     /* failed `assert!`s of commit()/prove(); ProverError::Commit (:683-684) */
+#define LCPC_B200_ERR_TOO_BIG (-2)     /* ProverError::TooBig (:656-658); FFTError::TooBig via precomp_fft */
+#define LCPC_B200_ERR_ENCODE (-3)      /* ProverError::Encode(E::Err) (:120-121) */
+#define LCPC_B200_ERR_CUDA (-4)        /* CUDA runtime failure or no device; message in last_error */
+#define LCPC_B200_ERR_OOM (-5)         /* device or pinned-host allocation failed */
+#define LCPC_B200_ERR_COLUMN (-6)      /* ProverError::ColumnNumber (:797-799) */
+#define LCPC_B200_ERR_UNSUPPORTED (-7) /* valid request this build does not implement */
+
+/* field ids: lcpc-test-fields/src/lib.rs:13-59 */
+enum { LCPC_B200_FT63 = 1, LCPC_B200_FT127 = 2, LCPC_B200_FT191 = 3, LCPC_B200_FT255 = 4 };
+/* encoding kinds */
+enum { LCPC_B200_ENC_LIGERO = 1, LCPC_B200_ENC_SDIG = 2 };
+
+typedef struct lcpc_b200_ctx lcpc_b200_ctx;       /* one CUDA device + stream + scratch */
+typedef struct lcpc_b200_enc lcpc_b200_enc;       /* device side of an `impl LcEncoding` */
+typedef struct lcpc_b200_commit lcpc_b200_commit; /* device-resident LcCommit (lcpc-2d/src/lib.rs:172-184) */
+
+/* ---- library / context ---- */
+const char *lcpc_b200_version(void);
+/* number of u64 limbs of a field (1,2,3,4) or -1 */
+int lcpc_b200_field_limbs(int field);
+int lcpc_b200_ctx_create(int device, lcpc_b200_ctx **out);
+void lcpc_b200_ctx_destroy(lcpc_b200_ctx *ctx);
+const char *lcpc_b200_last_error(const lcpc_b200_ctx *ctx);
+int lcpc_b200_ctx_device(const lcpc_b200_ctx *ctx);
+/* the cudaStream_t all work of this context is enqueued on (for event timing by the caller) */
+void *lcpc_b200_ctx_stream(const lcpc_b200_ctx *ctx);
+int lcpc_b200_ctx_synchronize(lcpc_b200_ctx *ctx);
+/* kernels launched by this context since creation (bench.py's `gpu_launches`) */
+uint64_t lcpc_b200_ctx_launch_count(const lcpc_b200_ctx *ctx);
+
+/* ---- encodings (impl LcEncoding, lcpc-2d/src/lib.rs:74-104) ----
+ * Dimension choosing (`_get_dims`, lcpc-ligero-pc/src/lib.rs:70-112; `_new_from_np1`,
+ * lcpc-brakedown-pc/src/lib.rs:69-99) and Brakedown code generation (matgen.rs) stay on the host
+ * side of the boundary; the device object is built from their results. */
+
+/* LigeroEncodingRho::new_from_dims (lcpc-ligero-pc/src/lib.rs:138-148): checks dims_ok (:114-118),
+ * builds the root table precomp_fft(n_cols) would (:140).  ERR_BAD_ARG when !dims_ok, ERR_TOO_BIG when
+ * log2(n_cols) exceeds the field's two-adicity. */
+int lcpc_b200_ligero_new(lcpc_b200_ctx *ctx, int field, size_t n_per_row, size_t n_cols, lcpc_b200_enc **out);
+
+/* One Brakedown code matrix exactly as matgen::gen_code builds it (matgen.rs:114-188, :187):
+ * CsMat::new_csc((m, n), ptrs, idxs, data) -- m outputs, n inputs, column-compressed. */
+typedef struct {
+  size_t m, n;
+  const uint64_t *ptrs; /* n + 1 column starts */
+  const uint64_t *idxs; /* nnz row indices */
+  const uint64_t *data; /* nnz elements, Montgomery limbs */
+} lcpc_b200_csc;
+/* SdigEncodingS from its `precodes` / `postcodes` vectors (lcpc-brakedown-pc/src/lib.rs:40-47);
+ * n_per_row = pre[0].n, n_cols = codeword_length (encode.rs:18-33). */
+int lcpc_b200_sdig_new(lcpc_b200_ctx *ctx, int field, size_t n_levels, const lcpc_b200_csc *pre,
+                       const lcpc_b200_csc *post, lcpc_b200_enc **out);
+void lcpc_b200_enc_free(lcpc_b200_enc *enc);
+int lcpc_b200_enc_kind(const lcpc_b200_enc *enc);
+int lcpc_b200_enc_field(const lcpc_b200_enc *enc);
+/* LcEncoding::get_dims (lcpc-ligero-pc/src/lib.rs:166-169, lcpc-brakedown-pc/src/lib.rs:155-158) */
+int lcpc_b200_enc_get_dims(const lcpc_b200_enc *enc, size_t len, size_t *n_rows, size_t *n_per_row,
+                           size_t *n_cols);
+/* LcEncoding::dims_ok (lcpc-ligero-pc/src/lib.rs:171-177, lcpc-brakedown-pc/src/lib.rs:160-167): 1 / 0 */
+int lcpc_b200_enc_dims_ok(const lcpc_b200_enc *enc, size_t n_per_row, size_t n_cols);
+
+/* LcEncoding::encode (trait :91; lcpc-ligero-pc/src/lib.rs:162-164, lcpc-brakedown-pc/src/lib.rs:150-153),
+ * batched: `rows` holds n_rows rows of n_cols elements (host memory), each encoded in place; like the
+ * reference, the whole row is the input (callers zero the tail, lcpc-2d/src/lib.rs:648-653, :886, :918). */
+int lcpc_b200_encode(lcpc_b200_enc *enc, uint64_t *rows, size_t n_rows);
+/* same on DEVICE memory; `valid` leading elements of each row are read, the rest taken as zero */
+int lcpc_b200_encode_dev(lcpc_b200_enc *enc, uint64_t *d_rows, size_t n_rows, size_t valid);
+
+/* out of place on DEVICE memory: source rows are src_stride elements apart with `valid` leading
+ * elements each; destination rows are n_cols apart (the row-block step of the multi-GPU commit) */
+int lcpc_b200_encode_rows_dev(lcpc_b200_enc *enc, const uint64_t *d_src, size_t src_stride, size_t valid,
+                              uint64_t *d_dst, size_t n_rows);
+
+/* ---- commit (LcCommit::commit, lcpc-2d/src/lib.rs:299-301 -> :622-671) ----
+ * coeffs_in: `len` elements on the host.  Pads to n_rows x n_per_row (:636-645), encodes every row
+ * (:648-653), hashes columns and builds the Merkle tree (:656-668).  The result stays on the device. */
+int lcpc_b200_commit_new(lcpc_b200_enc *enc, const uint64_t *coeffs_in, size_t len, lcpc_b200_commit **out);
+/* same with coeffs_in already in device memory (the roofline-timed region of bench.py) */
+int lcpc_b200_commit_new_dev(lcpc_b200_enc *enc, const uint64_t *d_coeffs_in, size_t len, lcpc_b200_commit **out);
+/* re-run the commit into an existing object of the same shape (no allocation; for timing loops) */
+int lcpc_b200_commit_rerun_dev(lcpc_b200_commit *c, const uint64_t *d_coeffs_in, size_t len);
+int lcpc_b200_commit_rerun(lcpc_b200_commit *c, const uint64_t *coeffs_in, size_t len);
+void lcpc_b200_commit_free(lcpc_b200_commit *c);
+/* n_hashes = 2 * next_power_of_two(n_cols) - 1 (:656-666) */
+int lcpc_b200_commit_dims(const lcpc_b200_commit *c, size_t *n_rows, size_t *n_per_row, size_t *n_cols,
+                          size_t *n_hashes);
+/* LcCommit::get_root (:276-281): the last entry of `hashes` */
+int lcpc_b200_commit_root(lcpc_b200_commit *c, uint8_t root[32]);
+/* copy out the LcCommit fields (:178-183); any pointer may be NULL to skip that field.
+ * comm: n_rows*n_cols elements, coeffs: n_rows*n_per_row elements, hashes: n_hashes*32 bytes. */
+int lcpc_b200_commit_download(lcpc_b200_commit *c, uint64_t *comm, uint64_t *coeffs, uint8_t *hashes);
+/* device time of the phases of the last (re)run on this object, from events recorded on the context's
+ * stream: ms[0] pad/copy, ms[1] row encode, ms[2] column leaf hashing, ms[3] Merkle layers; launches[]
+ * (optional) = kernels launched by the encode / leaf-hash / Merkle phases.  Synchronises. */
+int lcpc_b200_commit_phase_times(lcpc_b200_commit *c, float ms[4], int launches[3]);
+/* device pointers of the same three arrays (owned by the commit) */
+int lcpc_b200_commit_device_ptrs(lcpc_b200_commit *c, uint64_t **d_comm, uint64_t **d_coeffs, uint8_t **d_hashes);
+/* one-shot form with host outputs, the exact shape of commit(): new + download + free */
+int lcpc_b200_commit_to_host(lcpc_b200_enc *enc, const uint64_t *coeffs_in, size_t len, uint64_t *comm,
+                             uint64_t *coeffs, uint8_t *hashes);
+
+/* ---- prove pieces ---- */
+/* collapse_columns (lcpc-2d/src/lib.rs:1095-1123; call sites :1034, :1055):
+ * poly[c] = sum_r tensor[r] * coeffs[r*n_per_row + c]; tensor: n_rows elements, poly: n_per_row (host) */
+int lcpc_b200_commit_collapse(lcpc_b200_commit *c, const uint64_t *tensor, uint64_t *poly);
+/* stateless form on host arrays */
+int lcpc_b200_collapse(lcpc_b200_ctx *ctx, int field, const uint64_t *coeffs, const uint64_t *tensor,
+                       uint64_t *poly, size_t n_rows, size_t n_per_row);
+/* open_column (lcpc-2d/src/lib.rs:788-825) for `n` columns at once (the par_iter at :1081-1084):
+ * cols_out: n * n_rows elements (column i contiguous), paths_out: n * path_len * 32 bytes with
+ * path_len = log2(next_power_of_two(n_cols)).  ERR_COLUMN if any index >= n_cols (:797-799). */
+int lcpc_b200_commit_open_columns(lcpc_b200_commit *c, const uint64_t *cols, size_t n, uint64_t *cols_out,
+                                  uint8_t *paths_out);
+
+/* ---- standalone pieces (tests, verifier-side use, multi-GPU pipeline) ---- */
+/* merkleize (lcpc-2d/src/lib.rs:690-704) of a host row-major comm into host hashes[2*np2-1][32] */
+int lcpc_b200_merkleize(lcpc_b200_ctx *ctx, int field, const uint64_t *comm, size_t n_rows, size_t n_cols,
+                        uint8_t *hashes);
+/* device building blocks: column leaf digests of a device matrix whose element (r,c) is at
+ * d_comm[(r*row_stride + c)*L]; d_leaves: n_cols*32 bytes */
+int lcpc_b200_hash_columns_dev(lcpc_b200_ctx *ctx, int field, const uint64_t *d_comm, size_t n_rows,
+                               size_t n_cols, size_t row_stride, uint8_t *d_leaves);
+/* merkle_tree (lcpc-2d/src/lib.rs:747-760) in place on device: d_hashes[0..np2) given */
+int lcpc_b200_merkle_tree_dev(lcpc_b200_ctx *ctx, uint8_t *d_hashes, size_t np2);
+int lcpc_b200_collapse_dev(lcpc_b200_ctx *ctx, int field, const uint64_t *d_coeffs, size_t row_stride,
+                           const uint64_t *d_tensor, uint64_t *d_poly, size_t n_rows, size_t n_per_row);
+/* element-wise field arithmetic on host arrays (parity tests of the device arithmetic):
+ * op 0 add, 1 sub, 2 mul, 4 from_mont (b ignored) */
+int lcpc_b200_field_op(lcpc_b200_ctx *ctx, int field, int op, uint64_t *r, const uint64_t *a,
+                       const uint64_t *b, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LCPC_B200_H */

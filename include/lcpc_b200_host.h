@@ -1,0 +1,44 @@
+/*
+ * include/lcpc_b200_host.h -- host-side setup helpers that accompany include/lcpc_b200.h.
+ *
+ * In a Rust integration these stay in Rust (they ARE the reference's code: `_get_dims`, `matgen`);
+ * they are exported here so that hosts without the reference crates (this repo's C++/Python host
+ * layer, tests, bench.py) can construct the same encodings.  No device work happens in this header.
+ */
+#ifndef LCPC_B200_HOST_H
+#define LCPC_B200_HOST_H
+
+#include "lcpc_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* n_degree_tests (lcpc-2d/src/lib.rs:613-616) and SizedField::FLOG2 (:61-71) */
+size_t lcpc_b200_n_degree_tests(size_t lambda, size_t len, size_t flog2);
+unsigned lcpc_b200_field_flog2(int field);
+/* LigeroEncodingRho::_n_col_opens / _get_dims (lcpc-ligero-pc/src/lib.rs:61-64, 70-112) */
+size_t lcpc_b200_ligero_n_col_opens(size_t rho_num, size_t rho_den);
+int lcpc_b200_ligero_get_dims(int field, size_t len, size_t rho_num, size_t rho_den, size_t *n_rows,
+                              size_t *n_per_row, size_t *n_cols);
+/* SdigEncodingS::_n_col_opens and the n_per_row choice of ::new (lcpc-brakedown-pc/src/lib.rs:57-61, 69-110);
+ * code = 1..6 selects SdigCode1..6 (codespec.rs:169-232; the default alias is SdigCode3, lib.rs:19) */
+size_t lcpc_b200_sdig_n_col_opens(int code);
+int lcpc_b200_sdig_choose_n_per_row(int field, int code, size_t len, size_t *n_per_row);
+
+/* matgen::generate (lcpc-brakedown-pc/src/matgen.rs:28-52): the seeded precodes/postcodes, host memory */
+typedef struct lcpc_b200_sdig_code lcpc_b200_sdig_code;
+int lcpc_b200_sdig_code_generate(int field, int code, size_t n_per_row, uint64_t seed, lcpc_b200_sdig_code **out);
+void lcpc_b200_sdig_code_free(lcpc_b200_sdig_code *c);
+size_t lcpc_b200_sdig_code_levels(const lcpc_b200_sdig_code *c);
+size_t lcpc_b200_sdig_code_n_per_row(const lcpc_b200_sdig_code *c);
+size_t lcpc_b200_sdig_code_codeword_length(const lcpc_b200_sdig_code *c); /* encode.rs:18-33 */
+/* borrow one matrix; pointers stay valid until lcpc_b200_sdig_code_free */
+int lcpc_b200_sdig_code_matrix(const lcpc_b200_sdig_code *c, size_t level, int is_post, lcpc_b200_csc *out);
+/* convenience: lcpc_b200_sdig_new on every matrix of a generated code */
+int lcpc_b200_sdig_new_from_code(lcpc_b200_ctx *ctx, const lcpc_b200_sdig_code *c, lcpc_b200_enc **out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LCPC_B200_HOST_H */

@@ -1,0 +1,30 @@
+"""lcpc_b200 -- B200-native commit/prove engine for lcpc-2d's data-parallel hot path.
+
+Host-side mirror of the reference's operator interface, over the C ABI in ``include/lcpc_b200.h``:
+
+=====================================  ==========================================================
+reference (Rust)                       here
+=====================================  ==========================================================
+``trait LcEncoding`` (lcpc-2d lib.rs   ``LcEncoding`` base class: ``encode``, ``get_dims``,
+:74-104)                               ``dims_ok``, ``get_n_col_opens``, ``get_n_degree_tests``
+``LigeroEncoding<F>`` (ligero lib.rs   ``LigeroEncoding(field, len)`` / ``.new_from_dims``
+:189)
+``SdigEncoding<F>`` (brakedown lib.rs  ``SdigEncoding(field, len, seed)`` / ``.new_from_dims``
+:179)
+``LcCommit::commit / get_root /        ``LcCommit.commit(coeffs, enc)``, ``.get_root()``,
+prove`` (lib.rs:276-311)               ``.collapse(tensor)``, ``.open_columns(cols)``
+``LcRoot`` (lib.rs:315-323)            ``LcRoot`` (32-byte digest)
+=====================================  ==========================================================
+
+Field elements are ``numpy.uint64`` arrays of shape ``(n, L)``: the in-memory image of the reference's
+``struct FtNNN([u64; L])`` (Montgomery limbs, little-endian).  All compute happens on the GPU through
+the C ABI; there is no CPU implementation in this package.
+"""
+from .host import (FT63, FT127, FT191, FT255, FIELD_LIMBS, Context, LcCommit, LcEncoding, LcRoot,  # noqa: F401
+                   LigeroEncoding, SdigEncoding, default_context, field_op, merkleize, collapse_columns,
+                   ligero_get_dims, n_degree_tests)
+from ._cabi import LcpcError, LIB_PATH  # noqa: F401
+
+__all__ = ["FT63", "FT127", "FT191", "FT255", "FIELD_LIMBS", "Context", "LcCommit", "LcEncoding", "LcRoot",
+           "LigeroEncoding", "SdigEncoding", "LcpcError", "default_context", "field_op", "merkleize",
+           "collapse_columns", "ligero_get_dims", "n_degree_tests"]

@@ -1,0 +1,108 @@
+"""ctypes binding of lcpc_b200/lib/liblcpc_b200.so (the C ABI of include/lcpc_b200.h).
+
+Loads the in-tree CUDA library and nothing else: there is no fallback implementation.  Importing this
+module works without a GPU (the library only needs the CUDA runtime it links statically); creating
+a context without one raises ``LcpcError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "liblcpc_b200.so")
+
+OK = 0
+ERR_BAD_ARG, ERR_TOO_BIG, ERR_ENCODE, ERR_CUDA, ERR_OOM, ERR_COLUMN, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6, -7
+_ERR_NAMES = {ERR_BAD_ARG: "BAD_ARG", ERR_TOO_BIG: "TOO_BIG", ERR_ENCODE: "ENCODE", ERR_CUDA: "CUDA",
+              ERR_OOM: "OOM", ERR_COLUMN: "COLUMN", ERR_UNSUPPORTED: "UNSUPPORTED"}
+
+
+class LcpcError(RuntimeError):
+    """A non-zero status from the C ABI (the Rust shim maps these onto ProverError)."""
+
+    def __init__(self, code, message=""):
+        self.code = code
+        super().__init__(f"lcpc_b200: {_ERR_NAMES.get(code, code)} {message}".rstrip())
+
+
+class Csc(C.Structure):
+    _fields_ = [("m", C.c_size_t), ("n", C.c_size_t), ("ptrs", C.c_void_p), ("idxs", C.c_void_p),
+                ("data", C.c_void_p)]
+
+
+_vp, _sz, _i, _u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64
+_pvp, _psz = C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)
+
+# name -> (restype, argtypes); mirrors include/lcpc_b200.h and include/lcpc_b200_host.h one to one
+SIGNATURES = {
+    "lcpc_b200_version": (C.c_char_p, []),
+    "lcpc_b200_field_limbs": (_i, [_i]),
+    "lcpc_b200_ctx_create": (_i, [_i, _pvp]),
+    "lcpc_b200_ctx_destroy": (None, [_vp]),
+    "lcpc_b200_last_error": (C.c_char_p, [_vp]),
+    "lcpc_b200_ctx_device": (_i, [_vp]),
+    "lcpc_b200_ctx_stream": (_vp, [_vp]),
+    "lcpc_b200_ctx_synchronize": (_i, [_vp]),
+    "lcpc_b200_ctx_launch_count": (_u64, [_vp]),
+    "lcpc_b200_ligero_new": (_i, [_vp, _i, _sz, _sz, _pvp]),
+    "lcpc_b200_sdig_new": (_i, [_vp, _i, _sz, C.POINTER(Csc), C.POINTER(Csc), _pvp]),
+    "lcpc_b200_enc_free": (None, [_vp]),
+    "lcpc_b200_enc_kind": (_i, [_vp]),
+    "lcpc_b200_enc_field": (_i, [_vp]),
+    "lcpc_b200_enc_get_dims": (_i, [_vp, _sz, _psz, _psz, _psz]),
+    "lcpc_b200_enc_dims_ok": (_i, [_vp, _sz, _sz]),
+    "lcpc_b200_encode": (_i, [_vp, _vp, _sz]),
+    "lcpc_b200_encode_dev": (_i, [_vp, _vp, _sz, _sz]),
+    "lcpc_b200_commit_new": (_i, [_vp, _vp, _sz, _pvp]),
+    "lcpc_b200_commit_new_dev": (_i, [_vp, _vp, _sz, _pvp]),
+    "lcpc_b200_commit_rerun_dev": (_i, [_vp, _vp, _sz]),
+    "lcpc_b200_commit_rerun": (_i, [_vp, _vp, _sz]),
+    "lcpc_b200_commit_free": (None, [_vp]),
+    "lcpc_b200_commit_dims": (_i, [_vp, _psz, _psz, _psz, _psz]),
+    "lcpc_b200_commit_root": (_i, [_vp, _vp]),
+    "lcpc_b200_commit_download": (_i, [_vp, _vp, _vp, _vp]),
+    "lcpc_b200_commit_phase_times": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "lcpc_b200_encode_rows_dev": (_i, [_vp, _vp, _sz, _sz, _vp, _sz]),
+    "lcpc_b200_commit_device_ptrs": (_i, [_vp, _pvp, _pvp, _pvp]),
+    "lcpc_b200_commit_to_host": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
+    "lcpc_b200_commit_collapse": (_i, [_vp, _vp, _vp]),
+    "lcpc_b200_collapse": (_i, [_vp, _i, _vp, _vp, _vp, _sz, _sz]),
+    "lcpc_b200_commit_open_columns": (_i, [_vp, _vp, _sz, _vp, _vp]),
+    "lcpc_b200_merkleize": (_i, [_vp, _i, _vp, _sz, _sz, _vp]),
+    "lcpc_b200_hash_columns_dev": (_i, [_vp, _i, _vp, _sz, _sz, _sz, _vp]),
+    "lcpc_b200_merkle_tree_dev": (_i, [_vp, _vp, _sz]),
+    "lcpc_b200_collapse_dev": (_i, [_vp, _i, _vp, _sz, _vp, _vp, _sz, _sz]),
+    "lcpc_b200_field_op": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz]),
+    # host-side setup (include/lcpc_b200_host.h)
+    "lcpc_b200_n_degree_tests": (_sz, [_sz, _sz, _sz]),
+    "lcpc_b200_field_flog2": (C.c_uint, [_i]),
+    "lcpc_b200_ligero_n_col_opens": (_sz, [_sz, _sz]),
+    "lcpc_b200_ligero_get_dims": (_i, [_i, _sz, _sz, _sz, _psz, _psz, _psz]),
+    "lcpc_b200_sdig_n_col_opens": (_sz, [_i]),
+    "lcpc_b200_sdig_choose_n_per_row": (_i, [_i, _i, _sz, _psz]),
+    "lcpc_b200_sdig_code_generate": (_i, [_i, _i, _sz, _u64, _pvp]),
+    "lcpc_b200_sdig_code_free": (None, [_vp]),
+    "lcpc_b200_sdig_code_levels": (_sz, [_vp]),
+    "lcpc_b200_sdig_code_n_per_row": (_sz, [_vp]),
+    "lcpc_b200_sdig_code_codeword_length": (_sz, [_vp]),
+    "lcpc_b200_sdig_code_matrix": (_i, [_vp, _sz, _i, C.POINTER(Csc)]),
+    "lcpc_b200_sdig_new_from_code": (_i, [_vp, _vp, _pvp]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library; raises if it has not been built (run __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LcpcError(ERR_CUDA, f"{LIB_PATH} is missing: build it with `make -C lcpc_b200/csrc` "
+                                      "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib

@@ -1,0 +1,733 @@
+// lcpc_b200/csrc/api.cu -- the extern "C" boundary declared in include/lcpc_b200.h.
+// Owns contexts, encodings and device-resident commits; all compute is in the kernels_*.cu files.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/lcpc_b200.h"
+#include "expander.h"
+#include "field.cuh"
+#include "kernels.h"
+
+using namespace lcpc;
+
+// ------------------------------------------------------------------------------------------------
+struct lcpc_b200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  std::string err;
+  uint64_t launches = 0;
+  // grow-only device scratch shared by the stateless entry points
+  void *scratch = nullptr;
+  size_t scratch_bytes = 0;
+};
+
+static int fail(lcpc_b200_ctx *ctx, int code, const char *fmt, ...) {
+  if (ctx) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    ctx->err = buf;
+  }
+  return code;
+}
+
+static int cuda_fail(lcpc_b200_ctx *ctx, cudaError_t e, const char *what) {
+  int code = (e == cudaErrorMemoryAllocation) ? LCPC_B200_ERR_OOM : LCPC_B200_ERR_CUDA;
+  return fail(ctx, code, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define CU(ctx, call)                                        \
+  do {                                                       \
+    cudaError_t e_ = (call);                                 \
+    if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call); \
+  } while (0)
+
+static int bind_device(lcpc_b200_ctx *ctx) {
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
+  return LCPC_B200_OK;
+}
+
+static int ensure_scratch(lcpc_b200_ctx *ctx, size_t bytes) {
+  if (bytes <= ctx->scratch_bytes) return LCPC_B200_OK;
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  ctx->scratch = nullptr, ctx->scratch_bytes = 0;
+  CU(ctx, cudaMalloc(&ctx->scratch, bytes));
+  ctx->scratch_bytes = bytes;
+  return LCPC_B200_OK;
+}
+
+static bool is_pow2(size_t v) { return v && !(v & (v - 1)); }
+static unsigned log2_ceil(size_t v) {  // lcpc-2d/src/lib.rs:827-829
+  unsigned l = 0;
+  while (((size_t)1 << l) < v) l++;
+  return l;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side setup scalars (one = R mod p, w = the n_cols-th root of unity).  These few values are
+// computed once per encoding with field.cuh's host build of the same algorithms.
+struct FieldHostInfo { unsigned two_adicity; uint32_t generator; };
+static bool field_host_info(int field, FieldHostInfo *out) {
+  switch (field) {  // lcpc-test-fields/src/lib.rs:20,32,44,56 (PrimeFieldGenerator) and 2-adicity of p-1
+    case FT63: *out = {41, 10}; return true;
+    case FT127: *out = {40, 3}; return true;
+    case FT191: *out = {41, 5}; return true;
+    case FT255: *out = {41, 5}; return true;
+  }
+  return false;
+}
+
+template <int FID>
+static void host_root_of_unity(unsigned log_len, unsigned two_adicity, uint32_t gen, uint32_t *w_out, uint32_t *one_out) {
+  using F = Field<FID>;
+  constexpr int N = F::N;
+  typename F::Elem one = F::zero();
+  one.v[0] = 1;
+  for (int i = 0; i < 32 * N; i++) one = F::add(one, one);  // R mod p
+  typename F::Elem g = one;
+  for (uint32_t i = 1; i < gen; i++) g = F::add(g, one);  // generator in Montgomery form
+  // t = (p - 1) >> two_adicity
+  uint32_t t[N];
+  for (int i = 0; i < N; i++) t[i] = FieldP<FID>::P(i);
+  t[0] -= 1;
+  for (unsigned s = 0; s < two_adicity; s++) {
+    for (int i = 0; i < N; i++) t[i] = (t[i] >> 1) | (i + 1 < N ? t[i + 1] << 31 : 0);
+  }
+  typename F::Elem acc = one, base = g;
+  for (int i = 0; i < N; i++)
+    for (int k = 0; k < 32; k++) {
+      if ((t[i] >> k) & 1) acc = F::mul(acc, base);
+      base = F::mul(base, base);
+    }
+  // PrimeField::root_of_unity() = acc; fffft squares it down to order 2^log_len
+  for (unsigned i = log_len; i < two_adicity; i++) acc = F::mul(acc, acc);
+  memcpy(w_out, acc.v, sizeof acc.v);
+  memcpy(one_out, one.v, sizeof one.v);
+}
+
+static void host_root(int field, unsigned log_len, uint32_t *w, uint32_t *one) {
+  FieldHostInfo fi;
+  field_host_info(field, &fi);
+  switch (field) {
+    case FT63: host_root_of_unity<FT63>(log_len, fi.two_adicity, fi.generator, w, one); break;
+    case FT127: host_root_of_unity<FT127>(log_len, fi.two_adicity, fi.generator, w, one); break;
+    case FT191: host_root_of_unity<FT191>(log_len, fi.two_adicity, fi.generator, w, one); break;
+    default: host_root_of_unity<FT255>(log_len, fi.two_adicity, fi.generator, w, one); break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct lcpc_b200_enc {
+  lcpc_b200_ctx *ctx = nullptr;
+  int kind = 0, field = 0;
+  size_t n_per_row = 0, n_cols = 0;
+  // ligero
+  unsigned log_n = 0;
+  uint32_t *d_roots = nullptr;
+  // sdig
+  ExpanderCode *code = nullptr;
+};
+
+struct lcpc_b200_commit {
+  lcpc_b200_enc *enc = nullptr;
+  size_t n_rows = 0, n_per_row = 0, n_cols = 0, np2 = 0;
+  uint32_t *d_coeffs = nullptr, *d_comm = nullptr;
+  uint8_t *d_hashes = nullptr;
+  void *d_hash_scratch = nullptr;
+  void *d_enc_scratch = nullptr;
+  // prove-side staging
+  uint32_t *d_tensor = nullptr, *d_poly = nullptr;
+  // phase boundaries of the last run: start | copy+pad | encode | leaf hash | merkle
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  int encode_launches = 0, hash_launches = 0, merkle_launches = 0;
+};
+
+extern "C" {
+
+const char *lcpc_b200_version(void) { return "lcpc_b200 0.1 (sm_100a)"; }
+
+int lcpc_b200_field_limbs(int field) {
+  int n = field_limbs32(field);
+  return n < 0 ? -1 : n / 2;
+}
+
+int lcpc_b200_ctx_create(int device, lcpc_b200_ctx **out) {
+  if (!out) return LCPC_B200_ERR_BAD_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0 || device < 0 || device >= count) return LCPC_B200_ERR_CUDA;
+  lcpc_b200_ctx *ctx = new (std::nothrow) lcpc_b200_ctx;
+  if (!ctx) return LCPC_B200_ERR_OOM;
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return LCPC_B200_ERR_CUDA;
+  }
+  *out = ctx;
+  return LCPC_B200_OK;
+}
+
+void lcpc_b200_ctx_destroy(lcpc_b200_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->stream);
+  }
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  delete ctx;
+}
+
+const char *lcpc_b200_last_error(const lcpc_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int lcpc_b200_ctx_device(const lcpc_b200_ctx *ctx) { return ctx ? ctx->device : -1; }
+void *lcpc_b200_ctx_stream(const lcpc_b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+uint64_t lcpc_b200_ctx_launch_count(const lcpc_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int lcpc_b200_ctx_synchronize(lcpc_b200_ctx *ctx) {
+  if (!ctx) return LCPC_B200_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (int rc = bind_device(ctx)) return rc;
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return LCPC_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------- encodings
+int lcpc_b200_ligero_new(lcpc_b200_ctx *ctx, int field, size_t n_per_row, size_t n_cols, lcpc_b200_enc **out) {
+  if (!ctx || !out) return LCPC_B200_ERR_BAD_ARG;
+  *out = nullptr;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  FieldHostInfo fi;
+  if (!field_host_info(field, &fi)) return fail(ctx, LCPC_B200_ERR_BAD_ARG, "unknown field %d", field);
+  // dims_ok: lcpc-ligero-pc/src/lib.rs:114-118
+  if (!(n_per_row < n_cols && is_pow2(n_cols)))
+    return fail(ctx, LCPC_B200_ERR_BAD_ARG, "ligero dims not ok: n_per_row=%zu n_cols=%zu", n_per_row, n_cols);
+  unsigned log_n = log2_ceil(n_cols);
+  if (log_n > fi.two_adicity) return fail(ctx, LCPC_B200_ERR_TOO_BIG, "FFTError::TooBig: 2^%u points", log_n);
+  if (int rc = bind_device(ctx)) return rc;
+  lcpc_b200_enc *e = new (std::nothrow) lcpc_b200_enc;
+  if (!e) return LCPC_B200_ERR_OOM;
+  e->ctx = ctx, e->kind = LCPC_B200_ENC_LIGERO, e->field = field;
+  e->n_per_row = n_per_row, e->n_cols = n_cols, e->log_n = log_n;
+  const int N = field_limbs32(field);
+  const size_t half = n_cols / 2;
+  uint32_t seed[16];  // [w, one]
+  host_root(field, log_n, seed, seed + N);
+  uint32_t *d_seed = nullptr;
+  cudaError_t ce = cudaMalloc(&e->d_roots, (half ? half : 1) * N * 4);
+  if (ce == cudaSuccess) ce = cudaMalloc(&d_seed, 2 * N * 4);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_seed, seed, 2 * N * 4, cudaMemcpyHostToDevice, ctx->stream);
+  if (ce == cudaSuccess) ce = launch_root_table(field, e->d_roots, d_seed, half, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+  if (d_seed) cudaFree(d_seed);
+  if (ce != cudaSuccess) {
+    if (e->d_roots) cudaFree(e->d_roots);
+    delete e;
+    return cuda_fail(ctx, ce, "ligero_new");
+  }
+  ctx->launches += half ? 1 : 0;
+  *out = e;
+  return LCPC_B200_OK;
+}
+
+int lcpc_b200_sdig_new(lcpc_b200_ctx *ctx, int field, size_t n_levels, const lcpc_b200_csc *pre,
+                       const lcpc_b200_csc *post, lcpc_b200_enc **out) {
+  if (!ctx || !out || !pre || !post) return LCPC_B200_ERR_BAD_ARG;
+  *out = nullptr;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (field_limbs32(field) < 0) return fail(ctx, LCPC_B200_ERR_BAD_ARG, "unknown field %d", field);
+  if (n_levels == 0 || n_levels > 64) return fail(ctx, LCPC_B200_ERR_BAD_ARG, "bad level count %zu", n_levels);
+  if (int rc = bind_device(ctx)) return rc;
+  std::vector<CscView> vpre(n_levels), vpost(n_levels);
+  for (size_t i = 0; i < n_levels; i++) {
+    vpre[i] = {pre[i].m, pre[i].n, pre[i].ptrs, pre[i].idxs, pre[i].data};
+    vpost[i] = {post[i].m, post[i].n, post[i].ptrs, post[i].idxs, post[i].data};
+  }
+  std::string err;
+  ExpanderCode *code = nullptr;
+  int rc = expander_build(field, n_levels, vpre.data(), vpost.data(), ctx->stream, &code, &err);
+  if (rc != LCPC_B200_OK) return fail(ctx, rc, "sdig_new: %s", err.c_str());
+  lcpc_b200_enc *e = new (std::nothrow) lcpc_b200_enc;
+  if (!e) {
+    expander_free(code);
+    return LCPC_B200_ERR_OOM;
+  }
+  e->ctx = ctx, e->kind = LCPC_B200_ENC_SDIG, e->field = field;
+  e->n_per_row = expander_n_in(code), e->n_cols = expander_codeword_length(code);
+  e->code = code;
+  *out = e;
+  return LCPC_B200_OK;
+}
+
+void lcpc_b200_enc_free(lcpc_b200_enc *enc) {
+  if (!enc) return;
+  std::lock_guard<std::mutex> g(enc->ctx->mu);
+  cudaSetDevice(enc->ctx->device);
+  cudaStreamSynchronize(enc->ctx->stream);
+  if (enc->d_roots) cudaFree(enc->d_roots);
+  if (enc->code) expander_free(enc->code);
+  delete enc;
+}
+
+int lcpc_b200_enc_kind(const lcpc_b200_enc *enc) { return enc ? enc->kind : LCPC_B200_ERR_BAD_ARG; }
+int lcpc_b200_enc_field(const lcpc_b200_enc *enc) { return enc ? enc->field : LCPC_B200_ERR_BAD_ARG; }
+
+int lcpc_b200_enc_get_dims(const lcpc_b200_enc *enc, size_t len, size_t *n_rows, size_t *n_per_row, size_t *n_cols) {
+  if (!enc) return LCPC_B200_ERR_BAD_ARG;
+  if (n_rows) *n_rows = (len + enc->n_per_row - 1) / enc->n_per_row;
+  if (n_per_row) *n_per_row = enc->n_per_row;
+  if (n_cols) *n_cols = enc->n_cols;
+  return LCPC_B200_OK;
+}
+
+int lcpc_b200_enc_dims_ok(const lcpc_b200_enc *enc, size_t n_per_row, size_t n_cols) {
+  if (!enc) return 0;
+  bool ok = n_per_row < n_cols && n_per_row == enc->n_per_row && n_cols == enc->n_cols;
+  if (enc->kind == LCPC_B200_ENC_LIGERO) ok = ok && is_pow2(n_cols);
+  return ok ? 1 : 0;
+}
+
+// encode n_rows rows: src (stride/valid) -> dst (stride n_cols); enqueues only
+static int encode_rows(lcpc_b200_enc *enc, const uint32_t *src, size_t src_stride, size_t valid, uint32_t *dst,
+                       size_t n_rows, void *enc_scratch) {
+  lcpc_b200_ctx *ctx = enc->ctx;
+  int nl = 0;
+  cudaError_t ce;
+  if (enc->kind == LCPC_B200_ENC_LIGERO) {
+    ce = launch_ntt_rows(enc->field, src, src_stride, valid, dst, enc->n_cols, enc->d_roots, enc->log_n, n_rows,
+                         ctx->stream, &nl);
+  } else {
+    ce = expander_encode_rows(enc->code, src, src_stride, valid, dst, enc->n_cols, n_rows, enc_scratch, ctx->stream, &nl);
+  }
+  ctx->launches += nl;
+  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "encode");
+  return LCPC_B200_OK;
+}
+
+static size_t enc_scratch_bytes(const lcpc_b200_enc *enc, size_t n_rows) {
+  return enc->kind == LCPC_B200_ENC_SDIG ? expander_scratch_bytes(enc->code, n_rows) : 0;
+}
+
+int lcpc_b200_encode_dev(lcpc_b200_enc *enc, uint64_t *d_rows, size_t n_rows, size_t valid) {
+  if (!enc || (!d_rows && n_rows)) return LCPC_B200_ERR_BAD_ARG;
+  lcpc_b200_ctx *ctx = enc->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (valid > enc->n_cols) return fail(ctx, LCPC_B200_ERR_BAD_ARG, "valid %zu > n_cols %zu", valid, enc->n_cols);
+  if (int rc = bind_device(ctx)) return rc;
+  if (int rc = ensure_scratch(ctx, enc_scratch_bytes(enc, n_rows))) return rc;
+  return encode_rows(enc, (const uint32_t *)d_rows, enc->n_cols, valid, (uint32_t *)d_rows, n_rows, ctx->scratch);
+}
+
+int lcpc_b200_encode_rows_dev(lcpc_b200_enc *enc, const uint64_t *d_src, size_t src_stride, size_t valid,
+                              uint64_t *d_dst, size_t n_rows) {
+  if (!enc || ((!d_src || !d_dst) && n_rows)) return LCPC_B200_ERR_BAD_ARG;
+  lcpc_b200_ctx *ctx = enc->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (valid > enc->n_cols || valid > src_stride)
+    return fail(ctx, LCPC_B200_ERR_BAD_ARG, "valid %zu exceeds row (stride %zu, n_cols %zu)", valid, src_stride, enc->n_cols);
+  if (int rc = bind_device(ctx)) return rc;
+  if (int rc = ensure_scratch(ctx, enc_scratch_bytes(enc, n_rows))) return rc;
+  return encode_rows(enc, (const uint32_t *)d_src, src_stride, valid, (uint32_t *)d_dst, n_rows, ctx->scratch);
+}
+
+int lcpc_b200_encode(lcpc_b200_enc *enc, uint64_t *rows, size_t n_rows) {
+  if (!enc || (!rows && n_rows)) return LCPC_B200_ERR_BAD_ARG;
+  if (n_rows == 0) return LCPC_B200_OK;
+  lcpc_b200_ctx *ctx = enc->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (int rc = bind_device(ctx)) return rc;
+  const size_t bytes = n_rows * enc->n_cols * field_bytes(enc->field);
+  uint32_t *d = nullptr;
+  CU(ctx, cudaMalloc(&d, bytes));
+  int rc = ensure_scratch(ctx, enc_scratch_bytes(enc, n_rows));
+  cudaError_t ce = cudaSuccess;
+  if (rc == LCPC_B200_OK) {
+    ce = cudaMemcpyAsync(d, rows, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    // the reference transforms the whole row: Ligero reads all n_cols entries, Brakedown the first n_per_row
+    size_t valid = enc->kind == LCPC_B200_ENC_LIGERO ? enc->n_cols : enc->n_per_row;
+    if (ce == cudaSuccess) rc = encode_rows(enc, d, enc->n_cols, valid, d, n_rows, ctx->scratch);
+    if (ce == cudaSuccess && rc == LCPC_B200_OK) ce = cudaMemcpyAsync(rows, d, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+  }
+  cudaFree(d);
+  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "encode");
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------ commit
+static void commit_release(lcpc_b200_commit *c) {
+  cudaFree(c->d_coeffs);
+  cudaFree(c->d_comm);
+  cudaFree(c->d_hashes);
+  cudaFree(c->d_hash_scratch);
+  cudaFree(c->d_enc_scratch);
+  cudaFree(c->d_tensor);
+  cudaFree(c->d_poly);
+  for (auto &e : c->ev)
+    if (e) cudaEventDestroy(e);
+  delete c;
+}
+
+static int commit_alloc(lcpc_b200_enc *enc, size_t len, lcpc_b200_commit **out) {
+  lcpc_b200_ctx *ctx = enc->ctx;
+  if (len == 0) return fail(ctx, LCPC_B200_ERR_BAD_ARG, "commit: empty coefficient vector");
+  size_t n_rows = (len + enc->n_per_row - 1) / enc->n_per_row, n_per_row = enc->n_per_row, n_cols = enc->n_cols;
+  // asserts at lcpc-2d/src/lib.rs:630-632
+  if (!(n_rows * n_per_row >= len && (n_rows - 1) * n_per_row < len && lcpc_b200_enc_dims_ok(enc, n_per_row, n_cols)))
+    return fail(ctx, LCPC_B200_ERR_BAD_ARG, "commit: inconsistent dims");
+  // n_cols.checked_next_power_of_two() (:656-658)
+  unsigned lg = log2_ceil(n_cols);
+  if (lg >= 8 * sizeof(size_t) - 2) return fail(ctx, LCPC_B200_ERR_TOO_BIG, "commit: n_cols too big");
+  lcpc_b200_commit *c = new (std::nothrow) lcpc_b200_commit;
+  if (!c) return LCPC_B200_ERR_OOM;
+  c->enc = enc, c->n_rows = n_rows, c->n_per_row = n_per_row, c->n_cols = n_cols, c->np2 = (size_t)1 << lg;
+  const size_t B = field_bytes(enc->field);
+  size_t hs = hash_scratch_bytes(enc->field, n_rows, n_cols);
+  size_t es = enc_scratch_bytes(enc, n_rows);
+  cudaError_t ce = cudaMalloc(&c->d_coeffs, n_rows * n_per_row * B);
+  if (ce == cudaSuccess) ce = cudaMalloc(&c->d_comm, n_rows * n_cols * B);
+  if (ce == cudaSuccess) ce = cudaMalloc(&c->d_hashes, (2 * c->np2 - 1) * 32);
+  if (ce == cudaSuccess && hs) ce = cudaMalloc(&c->d_hash_scratch, hs);
+  if (ce == cudaSuccess && es) ce = cudaMalloc(&c->d_enc_scratch, es);
+  if (ce == cudaSuccess) ce = cudaMalloc(&c->d_tensor, n_rows * B);
+  if (ce == cudaSuccess) ce = cudaMalloc(&c->d_poly, n_per_row * B);
+  for (auto &e : c->ev)
+    if (ce == cudaSuccess) ce = cudaEventCreate(&e);
+  if (ce != cudaSuccess) {
+    commit_release(c);
+    return cuda_fail(ctx, ce, "commit: cudaMalloc");
+  }
+  *out = c;
+  return LCPC_B200_OK;
+}
+
+// enqueue the whole commit pipeline; src is host or device memory holding `len` elements
+static int commit_run(lcpc_b200_commit *c, const void *src, size_t len, cudaMemcpyKind kind) {
+  lcpc_b200_enc *enc = c->enc;
+  lcpc_b200_ctx *ctx = enc->ctx;
+  const size_t B = field_bytes(enc->field);
+  if ((len + c->n_per_row - 1) / c->n_per_row != c->n_rows)
+    return fail(ctx, LCPC_B200_ERR_BAD_ARG, "commit: length %zu does not give %zu rows", len, c->n_rows);
+  cudaStream_t st = ctx->stream;
+  CU(ctx, cudaEventRecord(c->ev[0], st));
+  // pad + copy (lcpc-2d/src/lib.rs:636-645): coeffs = coeffs_in || zeros
+  CU(ctx, cudaMemcpyAsync(c->d_coeffs, src, len * B, kind, st));
+  size_t padded = c->n_rows * c->n_per_row;
+  if (padded > len) CU(ctx, cudaMemsetAsync((uint8_t *)c->d_coeffs + len * B, 0, (padded - len) * B, st));
+  CU(ctx, cudaEventRecord(c->ev[1], st));
+  // per-row encode (:648-653); reads the padded coefficient rows, writes comm
+  uint64_t l0 = ctx->launches;
+  if (int rc = encode_rows(enc, c->d_coeffs, c->n_per_row, c->n_per_row, c->d_comm, c->n_rows, c->d_enc_scratch)) return rc;
+  c->encode_launches = (int)(ctx->launches - l0);
+  CU(ctx, cudaEventRecord(c->ev[2], st));
+  // leaves beyond n_cols stay Output::default() = zeros (:665, :696)
+  if (c->np2 > c->n_cols) CU(ctx, cudaMemsetAsync(c->d_hashes + c->n_cols * 32, 0, (c->np2 - c->n_cols) * 32, st));
+  int nl = 0;
+  cudaError_t ce = launch_hash_columns(enc->field, c->d_comm, c->n_rows, c->n_cols, c->n_cols, c->d_hashes,
+                                       c->d_hash_scratch, st, &nl);
+  ctx->launches += nl;
+  c->hash_launches = nl;
+  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "hash_columns");
+  CU(ctx, cudaEventRecord(c->ev[3], st));
+  ce = launch_merkle_tree(c->d_hashes, c->np2, st, &nl);
+  ctx->launches += nl;
+  c->merkle_launches = nl;
+  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "merkle_tree");
+  CU(ctx, cudaEventRecord(c->ev[4], st));
+  return LCPC_B200_OK;
+}
+
+static int commit_new_impl(lcpc_b200_enc *enc, const void *src, size_t len, cudaMemcpyKind kind, lcpc_b200_commit **out) {
+  if (!enc || !out || (!src && len)) return LCPC_B200_ERR_BAD_ARG;
+  *out = nullptr;
+  lcpc_b200_ctx *ctx = enc->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (int rc = bind_device(ctx)) return rc;
+  lcpc_b200_commit *c = nullptr;
+  if (int rc = commit_alloc(enc, len, &c)) return rc;
+  int rc = commit_run(c, src, len, kind);
+  if (rc == LCPC_B200_OK) {
+    cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+    if (ce != cudaSuccess) rc = cuda_fail(ctx, ce, "commit: synchronize");
+  }
+  if (rc != LCPC_B200_OK) {
+    commit_release(c);
+    return rc;
+  }
+  *out = c;
+  return LCPC_B200_OK;
+}
+
+int lcpc_b200_commit_new(lcpc_b200_enc *enc, const uint64_t *coeffs_in, size_t len, lcpc_b200_commit **out) {
+  return commit_new_impl(enc, coeffs_in, len, cudaMemcpyHostToDevice, out);
+}
+int lcpc_b200_commit_new_dev(lcpc_b200_enc *enc, const uint64_t *d_coeffs_in, size_t len, lcpc_b200_commit **out) {
+  return commit_new_impl(enc, d_coeffs_in, len, cudaMemcpyDeviceToDevice, out);
+}
+
+static int commit_rerun_impl(lcpc_b200_commit *c, const void *src, size_t len, cudaMemcpyKind kind, bool sync) {
+  if (!c || !src) return LCPC_B200_ERR_BAD_ARG;
+  lcpc_b200_ctx *ctx = c->enc->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (int rc = bind_device(ctx)) return rc;
+  int rc = commit_run(c, src, len, kind);
+  if (rc == LCPC_B200_OK && sync) CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return rc;
+}
+// device input: enqueue only (the caller times with events on lcpc_b200_ctx_stream and synchronises)
+int lcpc_b200_commit_rerun_dev(lcpc_b200_commit *c, const uint64_t *d_coeffs_in, size_t len) {
+  return commit_rerun_impl(c, d_coeffs_in, len, cudaMemcpyDeviceToDevice, false);
+}
+int lcpc_b200_commit_rerun(lcpc_b200_commit *c, const uint64_t *coeffs_in, size_t len) {
+  return commit_rerun_impl(c, coeffs_in, len, cudaMemcpyHostToDevice, true);
+}
+
+void lcpc_b200_commit_free(lcpc_b200_commit *c) {
+  if (!c) return;
+  lcpc_b200_ctx *ctx = c->enc->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  commit_release(c);
+}
+
+int lcpc_b200_commit_dims(const lcpc_b200_commit *c, size_t *n_rows, size_t *n_per_row, size_t *n_cols, size_t *n_hashes) {
+  if (!c) return LCPC_B200_ERR_BAD_ARG;
+  if (n_rows) *n_rows = c->n_rows;
+  if (n_per_row) *n_per_row = c->n_per_row;
+  if (n_cols) *n_cols = c->n_cols;
+  if (n_hashes) *n_hashes = 2 * c->np2 - 1;
+  return LCPC_B200_OK;
+}
+
+int lcpc_b200_commit_root(lcpc_b200_commit *c, uint8_t root[32]) {
+  if (!c || !root) return LCPC_B200_ERR_BAD_ARG;
+  lcpc_b200_ctx *ctx = c->enc->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (int rc = bind_device(ctx)) return rc;
+  CU(ctx, cudaMemcpyAsync(root, c->d_hashes + (2 * c->np2 - 2) * 32, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return LCPC_B200_OK;
+}
+
+int lcpc_b200_commit_download(lcpc_b200_commit *c, uint64_t *comm, uint64_t *coeffs, uint8_t *hashes) {
+  if (!c) return LCPC_B200_ERR_BAD_ARG;
+  lcpc_b200_ctx *ctx = c->enc->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (int rc = bind_device(ctx)) return rc;
+  const size_t B = field_bytes(c->enc->field);
+  if (comm) CU(ctx, cudaMemcpyAsync(comm, c->d_comm, c->n_rows * c->n_cols * B, cudaMemcpyDeviceToHost, ctx->stream));
+  if (coeffs) CU(ctx, cudaMemcpyAsync(coeffs, c->d_coeffs, c->n_rows * c->n_per_row * B, cudaMemcpyDeviceToHost, ctx->stream));
+  if (hashes) CU(ctx, cudaMemcpyAsync(hashes, c->d_hashes, (2 * c->np2 - 1) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return LCPC_B200_OK;
+}
+
+int lcpc_b200_commit_phase_times(lcpc_b200_commit *c, float ms[4], int launches[3]) {
+  if (!c || !ms) return LCPC_B200_ERR_BAD_ARG;
+  lcpc_b200_ctx *ctx = c->enc->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (int rc = bind_device(ctx)) return rc;
+  CU(ctx, cudaEventSynchronize(c->ev[4]));
+  for (int i = 0; i < 4; i++) CU(ctx, cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
+  if (launches) launches[0] = c->encode_launches, launches[1] = c->hash_launches, launches[2] = c->merkle_launches;
+  return LCPC_B200_OK;
+}
+
+int lcpc_b200_commit_device_ptrs(lcpc_b200_commit *c, uint64_t **d_comm, uint64_t **d_coeffs, uint8_t **d_hashes) {
+  if (!c) return LCPC_B200_ERR_BAD_ARG;
+  if (d_comm) *d_comm = (uint64_t *)c->d_comm;
+  if (d_coeffs) *d_coeffs = (uint64_t *)c->d_coeffs;
+  if (d_hashes) *d_hashes = c->d_hashes;
+  return LCPC_B200_OK;
+}
+
+int lcpc_b200_commit_to_host(lcpc_b200_enc *enc, const uint64_t *coeffs_in, size_t len, uint64_t *comm, uint64_t *coeffs,
+                     uint8_t *hashes) {
+  lcpc_b200_commit *c = nullptr;
+  int rc = lcpc_b200_commit_new(enc, coeffs_in, len, &c);
+  if (rc != LCPC_B200_OK) return rc;
+  rc = lcpc_b200_commit_download(c, comm, coeffs, hashes);
+  lcpc_b200_commit_free(c);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------- prove
+int lcpc_b200_commit_collapse(lcpc_b200_commit *c, const uint64_t *tensor, uint64_t *poly) {
+  if (!c || !tensor || !poly) return LCPC_B200_ERR_BAD_ARG;
+  lcpc_b200_ctx *ctx = c->enc->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (int rc = bind_device(ctx)) return rc;
+  const int field = c->enc->field;
+  const size_t B = field_bytes(field);
+  CU(ctx, cudaMemcpyAsync(c->d_tensor, tensor, c->n_rows * B, cudaMemcpyHostToDevice, ctx->stream));
+  int nl = 0;
+  cudaError_t ce = launch_collapse(field, c->d_coeffs, c->n_per_row, c->d_tensor, c->d_poly, c->n_rows, c->n_per_row,
+                                   nullptr, ctx->stream, &nl);
+  ctx->launches += nl;
+  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "collapse");
+  CU(ctx, cudaMemcpyAsync(poly, c->d_poly, c->n_per_row * B, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return LCPC_B200_OK;
+}
+
+int lcpc_b200_collapse_dev(lcpc_b200_ctx *ctx, int field, const uint64_t *d_coeffs, size_t row_stride,
+                           const uint64_t *d_tensor, uint64_t *d_poly, size_t n_rows, size_t n_per_row) {
+  if (!ctx) return LCPC_B200_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (field_limbs32(field) < 0) return fail(ctx, LCPC_B200_ERR_BAD_ARG, "unknown field %d", field);
+  if (int rc = bind_device(ctx)) return rc;
+  int nl = 0;
+  cudaError_t ce = launch_collapse(field, (const uint32_t *)d_coeffs, row_stride, (const uint32_t *)d_tensor,
+                                   (uint32_t *)d_poly, n_rows, n_per_row, nullptr, ctx->stream, &nl);
+  ctx->launches += nl;
+  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "collapse");
+  return LCPC_B200_OK;
+}
+
+int lcpc_b200_collapse(lcpc_b200_ctx *ctx, int field, const uint64_t *coeffs, const uint64_t *tensor, uint64_t *poly,
+                       size_t n_rows, size_t n_per_row) {
+  if (!ctx || !coeffs || !tensor || !poly) return LCPC_B200_ERR_BAD_ARG;
+  if (field_limbs32(field) < 0) return fail(ctx, LCPC_B200_ERR_BAD_ARG, "unknown field %d", field);
+  const size_t B = field_bytes(field);
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (int rc = bind_device(ctx)) return rc;
+    size_t cb = n_rows * n_per_row * B, tb = n_rows * B, pb = n_per_row * B;
+    size_t tb_al = (tb + 255) & ~(size_t)255, cb_al = (cb + 255) & ~(size_t)255;
+    if (int rc = ensure_scratch(ctx, cb_al + tb_al + pb)) return rc;
+    uint8_t *base = (uint8_t *)ctx->scratch;
+    uint32_t *d_c = (uint32_t *)base, *d_t = (uint32_t *)(base + cb_al), *d_p = (uint32_t *)(base + cb_al + tb_al);
+    CU(ctx, cudaMemcpyAsync(d_c, coeffs, cb, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_t, tensor, tb, cudaMemcpyHostToDevice, ctx->stream));
+    int nl = 0;
+    cudaError_t ce = launch_collapse(field, d_c, n_per_row, d_t, d_p, n_rows, n_per_row, nullptr, ctx->stream, &nl);
+    ctx->launches += nl;
+    if (ce != cudaSuccess) return cuda_fail(ctx, ce, "collapse");
+    CU(ctx, cudaMemcpyAsync(poly, d_p, pb, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return LCPC_B200_OK;
+}
+
+int lcpc_b200_commit_open_columns(lcpc_b200_commit *c, const uint64_t *cols, size_t n, uint64_t *cols_out,
+                                  uint8_t *paths_out) {
+  if (!c || (n && (!cols || !cols_out || !paths_out))) return LCPC_B200_ERR_BAD_ARG;
+  lcpc_b200_ctx *ctx = c->enc->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  for (size_t i = 0; i < n; i++)
+    if (cols[i] >= c->n_cols) return fail(ctx, LCPC_B200_ERR_COLUMN, "column %llu >= n_cols %zu", (unsigned long long)cols[i], c->n_cols);
+  if (n == 0) return LCPC_B200_OK;
+  if (int rc = bind_device(ctx)) return rc;
+  const int field = c->enc->field;
+  const size_t B = field_bytes(field);
+  const unsigned path_len = log2_ceil(c->n_cols);
+  // device staging: [cols (8n) | column values (n*n_rows*B) | paths (n*path_len*32)]
+  size_t off_vals = (n * 8 + 255) & ~(size_t)255;
+  size_t off_paths = (off_vals + n * c->n_rows * B + 255) & ~(size_t)255;
+  size_t total = off_paths + n * (size_t)path_len * 32;
+  if (int rc = ensure_scratch(ctx, total)) return rc;
+  uint8_t *base = (uint8_t *)ctx->scratch;
+  CU(ctx, cudaMemcpyAsync(base, cols, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  cudaError_t ce = launch_gather_columns(field, c->d_comm, c->n_rows, c->n_cols, (const uint64_t *)base, n,
+                                         (uint32_t *)(base + off_vals), ctx->stream);
+  if (ce == cudaSuccess && path_len)
+    ce = launch_gather_paths(c->d_hashes, c->np2, (const uint64_t *)base, n, path_len, base + off_paths, ctx->stream);
+  ctx->launches += path_len ? 2 : 1;
+  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "open_columns");
+  CU(ctx, cudaMemcpyAsync(cols_out, base + off_vals, n * c->n_rows * B, cudaMemcpyDeviceToHost, ctx->stream));
+  if (path_len) CU(ctx, cudaMemcpyAsync(paths_out, base + off_paths, n * (size_t)path_len * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return LCPC_B200_OK;
+}
+
+// --------------------------------------------------------------------------------- standalone pieces
+int lcpc_b200_hash_columns_dev(lcpc_b200_ctx *ctx, int field, const uint64_t *d_comm, size_t n_rows, size_t n_cols,
+                               size_t row_stride, uint8_t *d_leaves) {
+  if (!ctx) return LCPC_B200_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (field_limbs32(field) < 0) return fail(ctx, LCPC_B200_ERR_BAD_ARG, "unknown field %d", field);
+  if (int rc = bind_device(ctx)) return rc;
+  if (int rc = ensure_scratch(ctx, hash_scratch_bytes(field, n_rows, n_cols))) return rc;
+  int nl = 0;
+  cudaError_t ce = launch_hash_columns(field, (const uint32_t *)d_comm, n_rows, n_cols, row_stride, d_leaves,
+                                       ctx->scratch, ctx->stream, &nl);
+  ctx->launches += nl;
+  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "hash_columns");
+  return LCPC_B200_OK;
+}
+
+int lcpc_b200_merkle_tree_dev(lcpc_b200_ctx *ctx, uint8_t *d_hashes, size_t np2) {
+  if (!ctx || !d_hashes || !is_pow2(np2)) return LCPC_B200_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (int rc = bind_device(ctx)) return rc;
+  int nl = 0;
+  cudaError_t ce = launch_merkle_tree(d_hashes, np2, ctx->stream, &nl);
+  ctx->launches += nl;
+  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "merkle_tree");
+  return LCPC_B200_OK;
+}
+
+int lcpc_b200_merkleize(lcpc_b200_ctx *ctx, int field, const uint64_t *comm, size_t n_rows, size_t n_cols,
+                        uint8_t *hashes) {
+  if (!ctx || !comm || !hashes || n_cols == 0) return LCPC_B200_ERR_BAD_ARG;
+  if (field_limbs32(field) < 0) return fail(ctx, LCPC_B200_ERR_BAD_ARG, "unknown field %d", field);
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (int rc = bind_device(ctx)) return rc;
+  const size_t B = field_bytes(field);
+  const size_t np2 = (size_t)1 << log2_ceil(n_cols);
+  const size_t cb = (n_rows * n_cols * B + 255) & ~(size_t)255, hb = ((2 * np2 - 1) * 32 + 255) & ~(size_t)255;
+  const size_t sb = hash_scratch_bytes(field, n_rows, n_cols);
+  if (int rc = ensure_scratch(ctx, cb + hb + sb)) return rc;
+  uint8_t *base = (uint8_t *)ctx->scratch;
+  uint8_t *d_h = base + cb;
+  CU(ctx, cudaMemcpyAsync(base, comm, n_rows * n_cols * B, cudaMemcpyHostToDevice, ctx->stream));
+  if (np2 > n_cols) CU(ctx, cudaMemsetAsync(d_h + n_cols * 32, 0, (np2 - n_cols) * 32, ctx->stream));
+  int nl = 0;
+  cudaError_t ce = launch_hash_columns(field, (const uint32_t *)base, n_rows, n_cols, n_cols, d_h, base + cb + hb, ctx->stream, &nl);
+  ctx->launches += nl;
+  if (ce == cudaSuccess) {
+    ce = launch_merkle_tree(d_h, np2, ctx->stream, &nl);
+    ctx->launches += nl;
+  }
+  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "merkleize");
+  CU(ctx, cudaMemcpyAsync(hashes, d_h, (2 * np2 - 1) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return LCPC_B200_OK;
+}
+
+int lcpc_b200_field_op(lcpc_b200_ctx *ctx, int field, int op, uint64_t *r, const uint64_t *a, const uint64_t *b, size_t n) {
+  if (!ctx || !r || !a) return LCPC_B200_ERR_BAD_ARG;
+  if (field_limbs32(field) < 0 || !(op == 0 || op == 1 || op == 2 || op == 4))
+    return fail(ctx, LCPC_B200_ERR_BAD_ARG, "bad field/op %d/%d", field, op);
+  if ((op <= 2) && !b) return LCPC_B200_ERR_BAD_ARG;
+  if (n == 0) return LCPC_B200_OK;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (int rc = bind_device(ctx)) return rc;
+  const size_t bytes = n * field_bytes(field), al = (bytes + 255) & ~(size_t)255;
+  if (int rc = ensure_scratch(ctx, 3 * al)) return rc;
+  uint8_t *base = (uint8_t *)ctx->scratch;
+  CU(ctx, cudaMemcpyAsync(base, a, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (op <= 2) CU(ctx, cudaMemcpyAsync(base + al, b, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  cudaError_t ce = launch_field_op(field, op, (uint32_t *)(base + 2 * al), (const uint32_t *)base,
+                                   op <= 2 ? (const uint32_t *)(base + al) : nullptr, n, ctx->stream);
+  ctx->launches += 1;
+  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "field_op");
+  CU(ctx, cudaMemcpyAsync(r, base + 2 * al, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return LCPC_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,33 @@
+// lcpc_b200/csrc/expander.h -- device side of the Brakedown ("SDIG") expander code (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace lcpc {
+
+// borrowed view of one CsMat::new_csc((m, n), ptrs, idxs, data) (matgen.rs:187), host memory
+struct CscView {
+  size_t m, n;
+  const uint64_t *ptrs, *idxs, *data;
+};
+
+struct ExpanderCode;
+
+// uploads the code in gather (row-compressed) form; returns an LCPC_B200_* status
+int expander_build(int field, size_t n_levels, const CscView *pre, const CscView *post, cudaStream_t stream,
+                   ExpanderCode **out, std::string *err);
+void expander_free(ExpanderCode *code);
+size_t expander_n_in(const ExpanderCode *code);
+size_t expander_codeword_length(const ExpanderCode *code);  // encode.rs:18-33
+size_t expander_nnz(const ExpanderCode *code);
+size_t expander_scratch_bytes(const ExpanderCode *code, size_t n_rows);
+// encode n_rows rows: src row r holds `valid` >= n_in leading elements at src + r*src_stride; dst rows
+// are dst_stride apart and receive the full codeword.  src may equal dst.
+cudaError_t expander_encode_rows(const ExpanderCode *code, const uint32_t *src, size_t src_stride, size_t valid,
+                                 uint32_t *dst, size_t dst_stride, size_t n_rows, void *scratch, cudaStream_t stream,
+                                 int *n_launches);
+
+}  // namespace lcpc

@@ -1,0 +1,284 @@
+// lcpc_b200/csrc/field.cuh -- prime-field arithmetic for the lcpc test fields on sm_100a.
+//
+// Replaces, for the device path, the arithmetic `#[derive(PrimeField)]` generates for
+//   Ft63 / Ft127 / Ft191 / Ft255   (reference: lcpc-test-fields/src/lib.rs:18-22, 30-34, 42-46, 54-58).
+// An element is the in-memory image of the reference's `struct FtNNN([u64; L])`: L little-endian
+// u64 limbs holding the MONTGOMERY image x*R mod p, R = 2^(64 L).  On the device the same bytes are
+// read as N = 2L little-endian 32-bit limbs, which keeps R unchanged, so results are bit-identical
+// to the 64-bit-limb CPU arithmetic (all operations are exact mod p and results are canonical).
+//
+// Design notes (B200): the SM has no 64-bit integer multiplier; the unit of work is IMAD.WIDE.U32
+// (32x32+64) on the FMA pipe, with adds/logic on the ALU pipe.  Montgomery multiplication is
+// written as an interleaved (CIOS) product/reduction over two accumulator arrays that always hold
+// 64-bit-aligned register pairs ("even"/"odd" alignment), so every multiply-add is one wide IMAD
+// fed by a carry flag rather than a 3-instruction mul/add/add-carry group.  All four moduli are
+// = 1 mod 2^32, hence -p^{-1} mod 2^32 = 0xffffffff: the Montgomery quotient digit is just the
+// negated low limb and the p[0] column of every reduction step costs two adds instead of an IMAD.
+#pragma once
+#include <stdint.h>
+
+namespace lcpc {
+
+enum FieldId : int { FT63 = 1, FT127 = 2, FT191 = 3, FT255 = 4 };
+
+// ---- moduli as 32-bit limbs (lcpc-test-fields/src/lib.rs:19,31,43,55 give them in decimal) ----
+template <int FID> struct FieldP;
+template <> struct FieldP<FT63> {
+  static constexpr int N = 2;
+  __host__ __device__ static constexpr uint32_t P(int i) {
+    constexpr uint32_t p[N] = {0x00000001u, 0x46d07600u};
+    return p[i];
+  }
+};
+template <> struct FieldP<FT127> {
+  static constexpr int N = 4;
+  __host__ __device__ static constexpr uint32_t P(int i) {
+    constexpr uint32_t p[N] = {0x00000001u, 0x7f2bd900u, 0xba20e0bfu, 0x6e754097u};
+    return p[i];
+  }
+};
+template <> struct FieldP<FT191> {
+  static constexpr int N = 6;
+  __host__ __device__ static constexpr uint32_t P(int i) {
+    constexpr uint32_t p[N] = {0x00000001u, 0xd2468200u, 0x0ceecbcdu, 0x93688827u, 0x3fbc8ddau, 0x453708aau};
+    return p[i];
+  }
+};
+template <> struct FieldP<FT255> {
+  static constexpr int N = 8;
+  __host__ __device__ static constexpr uint32_t P(int i) {
+    constexpr uint32_t p[N] = {0x00000001u, 0x02a4f200u, 0x86595f30u, 0xef73c790u,
+                               0xb9575969u, 0xfda9df04u, 0x6e4d2900u, 0x663c799bu};
+    return p[i];
+  }
+};
+
+// The same limbs in the constant bank: ptxas fuses mad.lo.cc/madc.hi.cc into one IMAD.WIDE.U32.X only
+// when the multiplier is a register or a c[bank][offset] operand, not a 32-bit immediate.
+__device__ __constant__ uint32_t kModulusLimbs[5][8] = {
+    {0, 0, 0, 0, 0, 0, 0, 0},
+    {0x00000001u, 0x46d07600u, 0, 0, 0, 0, 0, 0},
+    {0x00000001u, 0x7f2bd900u, 0xba20e0bfu, 0x6e754097u, 0, 0, 0, 0},
+    {0x00000001u, 0xd2468200u, 0x0ceecbcdu, 0x93688827u, 0x3fbc8ddau, 0x453708aau, 0, 0},
+    {0x00000001u, 0x02a4f200u, 0x86595f30u, 0xef73c790u, 0xb9575969u, 0xfda9df04u, 0x6e4d2900u, 0x663c799bu},
+};
+
+// -p^{-1} mod 2^32 (= 0xffffffff for every modulus here) kept opaque in the constant bank: when the
+// quotient digit is produced by an ALU negate, ptxas 12.9 splits every dependent IMAD.WIDE.U32.X into
+// IMAD.X + IMAD.HI.U32.X (twice the FMA-pipe work); produced by an IMAD it keeps them fused.
+__device__ __constant__ uint32_t kMontInv32 = 0xffffffffu;
+
+// ---- carry-flag primitives (PTX extended-precision integer arithmetic) ----
+// Each statement is `asm volatile` so NVVM keeps them in program order; ptxas tracks CC itself.
+#define LCPC_DEV __host__ __device__ __forceinline__
+
+#ifdef __CUDA_ARCH__
+LCPC_DEV void add_cc(uint32_t &d, uint32_t a, uint32_t b) { asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+LCPC_DEV void addc_cc(uint32_t &d, uint32_t a, uint32_t b) { asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+LCPC_DEV void addc(uint32_t &d, uint32_t a, uint32_t b) { asm volatile("addc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+LCPC_DEV void sub_cc(uint32_t &d, uint32_t a, uint32_t b) { asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+LCPC_DEV void subc_cc(uint32_t &d, uint32_t a, uint32_t b) { asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+LCPC_DEV void subc(uint32_t &d, uint32_t a, uint32_t b) { asm volatile("subc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+// (lo,hi) = a*b + (clo,chi) [+ carry], as a lo/hi pair that ptxas fuses into one IMAD.WIDE.U32
+LCPC_DEV void mad_wide_cc(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi) {
+  asm volatile("mad.lo.cc.u32 %0, %2, %3, %4;\n\tmadc.hi.cc.u32 %1, %2, %3, %5;"
+               : "=r"(lo), "=r"(hi) : "r"(a), "r"(b), "r"(clo), "r"(chi));
+}
+LCPC_DEV void madc_wide_cc(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi) {
+  asm volatile("madc.lo.cc.u32 %0, %2, %3, %4;\n\tmadc.hi.cc.u32 %1, %2, %3, %5;"
+               : "=r"(lo), "=r"(hi) : "r"(a), "r"(b), "r"(clo), "r"(chi));
+}
+LCPC_DEV void madc_wide(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi) {
+  asm volatile("madc.lo.cc.u32 %0, %2, %3, %4;\n\tmadc.hi.u32 %1, %2, %3, %5;"
+               : "=r"(lo), "=r"(hi) : "r"(a), "r"(b), "r"(clo), "r"(chi));
+}
+LCPC_DEV void mul_wide(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b) {
+  asm volatile("mul.lo.u32 %0, %2, %3;\n\tmul.hi.u32 %1, %2, %3;" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
+#else
+// Host emulation of the same primitives with an explicit carry flag.  It exists so the carry-chain
+// LOGIC of this header can be unit-tested on a machine without a GPU (tests/host_field_check.cu);
+// no product entry point computes on the host.
+namespace hostcc { inline thread_local uint32_t cf = 0; }
+inline void add_cc(uint32_t &d, uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b; d = (uint32_t)s; hostcc::cf = (uint32_t)(s >> 32); }
+inline void addc_cc(uint32_t &d, uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b + hostcc::cf; d = (uint32_t)s; hostcc::cf = (uint32_t)(s >> 32); }
+inline void addc(uint32_t &d, uint32_t a, uint32_t b) { d = a + b + hostcc::cf; }
+inline void sub_cc(uint32_t &d, uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a - b; d = (uint32_t)s; hostcc::cf = (uint32_t)(s >> 63); }
+inline void subc_cc(uint32_t &d, uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a - b - hostcc::cf; d = (uint32_t)s; hostcc::cf = (uint32_t)(s >> 63); }
+inline void subc(uint32_t &d, uint32_t a, uint32_t b) { d = a - b - hostcc::cf; }
+inline void mad_wide_cc(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi) {
+  uint64_t pr = (uint64_t)a * b;
+  uint64_t s = (pr & 0xffffffffu) + clo; lo = (uint32_t)s;
+  uint64_t t = (pr >> 32) + chi + (s >> 32); hi = (uint32_t)t; hostcc::cf = (uint32_t)(t >> 32);
+}
+inline void madc_wide_cc(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi) {
+  uint64_t pr = (uint64_t)a * b;
+  uint64_t s = (pr & 0xffffffffu) + clo + hostcc::cf; lo = (uint32_t)s;
+  uint64_t t = (pr >> 32) + chi + (s >> 32); hi = (uint32_t)t; hostcc::cf = (uint32_t)(t >> 32);
+}
+inline void madc_wide(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi) {
+  madc_wide_cc(lo, hi, a, b, clo, chi);
+}
+inline void mul_wide(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b) {
+  uint64_t pr = (uint64_t)a * b; lo = (uint32_t)pr; hi = (uint32_t)(pr >> 32);
+}
+#endif
+
+template <int FID> struct Field {
+  using FP = FieldP<FID>;
+  static constexpr int N = FP::N;  // 32-bit limbs
+  static constexpr int BYTES = 4 * N;
+
+  struct Elem { uint32_t v[N]; };
+
+  // modulus limb as a multiplier operand (constant bank on the device, see kModulusLimbs)
+  LCPC_DEV static uint32_t PM(int i) {
+#ifdef __CUDA_ARCH__
+    return kModulusLimbs[FID][i];
+#else
+    return FP::P(i);
+#endif
+  }
+
+  LCPC_DEV static Elem zero() {
+    Elem r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = 0;
+    return r;
+  }
+
+  LCPC_DEV static bool is_zero(const Elem &a) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) acc |= a.v[i];
+    return acc == 0;
+  }
+
+  // r = t - p if t >= p else t   (t < 2p)
+  LCPC_DEV static Elem cond_sub_p(const Elem &t) {
+    Elem u;
+    uint32_t borrow;
+    sub_cc(u.v[0], t.v[0], FP::P(0));
+#pragma unroll
+    for (int i = 1; i < N; i++) subc_cc(u.v[i], t.v[i], FP::P(i));
+    subc(borrow, 0u, 0u);  // 0xffffffff if t < p
+    Elem r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = borrow ? t.v[i] : u.v[i];
+    return r;
+  }
+
+  LCPC_DEV static Elem add(const Elem &a, const Elem &b) {
+    Elem t;
+    add_cc(t.v[0], a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) addc_cc(t.v[i], a.v[i], b.v[i]);
+    addc(t.v[N - 1], a.v[N - 1], b.v[N - 1]);  // 2p < 2^(32N): no carry out
+    return cond_sub_p(t);
+  }
+
+  LCPC_DEV static Elem sub(const Elem &a, const Elem &b) {
+    Elem d;
+    uint32_t mask;
+    sub_cc(d.v[0], a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) subc_cc(d.v[i], a.v[i], b.v[i]);
+    subc(mask, 0u, 0u);  // all ones iff a < b
+    add_cc(d.v[0], d.v[0], FP::P(0) & mask);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) addc_cc(d.v[i], d.v[i], FP::P(i) & mask);
+    addc(d.v[N - 1], d.v[N - 1], FP::P(N - 1) & mask);
+    return d;
+  }
+
+  // ---- Montgomery product, interleaved, two aligned accumulator arrays ----
+  // Invariant at the top of step i: X holds limbs at positions 0..N-1, Y at positions 1..N of the
+  // running value V = X + 2^32 Y.  A step adds a*b_i and m*p (m = -V mod 2^32), which clears
+  // position 0, then positions shift down by one: the array that was Y becomes X, and the old X,
+  // minus its two low limbs, becomes the new Y (the "rshift" below); old X[1] folds into new X[0]
+  // and its carry feeds the chain that starts one position higher.
+  template <bool FIRST, bool WITH_AB>
+  LCPC_DEV static void step(uint32_t (&X)[N], uint32_t (&O)[N], const uint32_t (&a)[N], uint32_t bi) {
+    // entry: X = array now at position 0, O = previous step's X (to be shifted into Y), unless FIRST
+    if (FIRST) {
+      if (WITH_AB) {
+#pragma unroll
+        for (int j = 0; j < N; j += 2) mul_wide(O[j], O[j + 1], a[j + 1], bi);   // Y = a_odd * b_i
+#pragma unroll
+        for (int j = 0; j < N; j += 2) mul_wide(X[j], X[j + 1], a[j], bi);       // X = a_even * b_i
+      }
+    } else {
+      add_cc(X[0], X[0], O[1]);
+      if (WITH_AB) {
+#pragma unroll
+        for (int j = 0; j < N - 2; j += 2) madc_wide_cc(O[j], O[j + 1], a[j + 1], bi, O[j + 2], O[j + 3]);
+        madc_wide(O[N - 2], O[N - 1], a[N - 1], bi, 0u, 0u);
+        mad_wide_cc(X[0], X[1], a[0], bi, X[0], X[1]);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) madc_wide_cc(X[j], X[j + 1], a[j], bi, X[j], X[j + 1]);
+        addc(O[N - 1], O[N - 1], 0u);
+      } else {
+#pragma unroll
+        for (int j = 0; j < N - 2; j++) addc_cc(O[j], O[j + 2], 0u);
+        addc(O[N - 2], 0u, 0u);
+        O[N - 1] = 0;
+      }
+    }
+    // reduction digit; p = 1 mod 2^32 so m = -X[0] and the p[0] column is X[0] + m = 2^32 [X[0] != 0]
+#ifdef __CUDA_ARCH__
+    uint32_t m = X[0] * kMontInv32;
+#else
+    uint32_t m = 0u - X[0];
+#endif
+    // Y += m * p_odd
+    mad_wide_cc(O[0], O[1], m, PM(1), O[0], O[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) madc_wide_cc(O[j], O[j + 1], m, PM(j + 1), O[j], O[j + 1]);
+    // X += m * p_even   (carry out of position N-1 lands in Y[N-1])
+    add_cc(X[0], X[0], m);
+    addc_cc(X[1], X[1], 0u);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) madc_wide_cc(X[j], X[j + 1], m, PM(j), X[j], X[j + 1]);
+    addc(O[N - 1], O[N - 1], 0u);
+  }
+
+  // merge the two arrays after the last step and bring the result into [0, p)
+  LCPC_DEV static Elem finish(const uint32_t (&Y)[N], const uint32_t (&Xold)[N]) {
+    // positions after the final shift: Y -> 0..N-1, Xold[1..N-1] -> 0..N-2
+    Elem t;
+    add_cc(t.v[0], Y[0], Xold[1]);
+#pragma unroll
+    for (int j = 1; j < N - 1; j++) addc_cc(t.v[j], Y[j], Xold[j + 1]);
+    addc(t.v[N - 1], Y[N - 1], 0u);
+    return cond_sub_p(t);
+  }
+
+  LCPC_DEV static Elem mul(const Elem &a, const Elem &b) {
+    uint32_t E[N], O[N];
+    step<true, true>(E, O, a.v, b.v[0]);
+#pragma unroll
+    for (int i = 1; i < N; i += 2) {
+      step<false, true>(O, E, a.v, b.v[i]);
+      if (i + 1 < N) step<false, true>(E, O, a.v, b.v[i + 1]);
+    }
+    // N is even: the last step ran with X = O, so Y = E
+    return finish(E, O);
+  }
+
+  // canonical integer of a Montgomery-form element: a * R^{-1} mod p  (what to_repr serialises,
+  // reference: FieldHash::digest_update, lcpc-2d/src/lib.rs:42-57)
+  LCPC_DEV static Elem from_mont(const Elem &a) {
+    uint32_t E[N], O[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) { E[j] = a.v[j]; O[j] = 0; }
+    step<true, false>(E, O, a.v, 0u);
+#pragma unroll
+    for (int i = 1; i < N; i += 2) {
+      step<false, false>(O, E, a.v, 0u);
+      if (i + 1 < N) step<false, false>(E, O, a.v, 0u);
+    }
+    return finish(E, O);
+  }
+};
+
+}  // namespace lcpc

@@ -1,0 +1,54 @@
+// lcpc_b200/csrc/kernels.h -- host-side launchers of the device kernels (internal; the public
+// boundary is include/lcpc_b200.h).  All pointers are DEVICE pointers; elements are N 32-bit limbs
+// in Montgomery form (see field.cuh).  Every launcher enqueues on `stream` and returns the CUDA
+// status of the launch; nothing here synchronises.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace lcpc {
+
+int field_limbs32(int field);  // 2/4/6/8, or -1
+inline size_t field_bytes(int field) { return 4 * (size_t)field_limbs32(field); }
+
+// element-wise field ops (test hook): op 0 add, 1 sub, 2 mul, 4 from_mont
+cudaError_t launch_field_op(int field, int op, uint32_t *r, const uint32_t *a, const uint32_t *b, size_t n,
+                            cudaStream_t stream);
+
+// ---- Ligero: radix-2 DIF NTT, in-order in / bit-reversed out (fffft `fft_io_pc`) ----
+// roots: w^0 .. w^(n_cols/2-1), w = root_of_unity()^(2^(S-log2 n_cols))  (FFTPrecomp)
+// src rows hold `src_valid` leading elements (the rest of the n_cols-long row is implicit zeros) and
+// are `src_stride` elements apart; dst rows are `dst_stride` apart.  src == dst (in place) is allowed
+// when src_stride == dst_stride.  Returns the number of kernels launched through *n_launches.
+cudaError_t launch_ntt_rows(int field, const uint32_t *src, size_t src_stride, size_t src_valid, uint32_t *dst,
+                            size_t dst_stride, const uint32_t *roots, unsigned log_n, size_t n_rows,
+                            cudaStream_t stream, int *n_launches);
+// powers of w into roots[0..half): roots[i] = w^i (Montgomery); `w` points at 2N limbs: [w | R mod p]
+cudaError_t launch_root_table(int field, uint32_t *roots, const uint32_t *w, size_t half, cudaStream_t stream);
+
+// ---- column hashing + Merkle (lcpc-2d/src/lib.rs:706-785) ----
+// leaves[c] = BLAKE3(0^32 || repr(comm[0][c]) || ... || repr(comm[n_rows-1][c])) for c < n_cols;
+// comm element (r, c) lives at comm + (r * row_stride + c) * N.  scratch must hold
+// hash_scratch_bytes(field, n_rows, n_cols) bytes (0 if the leaf input fits one BLAKE3 chunk).
+size_t hash_scratch_bytes(int field, size_t n_rows, size_t n_cols);
+cudaError_t launch_hash_columns(int field, const uint32_t *comm, size_t n_rows, size_t n_cols, size_t row_stride,
+                                uint8_t *leaves, void *scratch, cudaStream_t stream, int *n_launches);
+// hashes = [leaves(np2) | layer 1 | ... | root]; leaves given, upper layers computed
+cudaError_t launch_merkle_tree(uint8_t *hashes, size_t np2, cudaStream_t stream, int *n_launches);
+
+// ---- collapse_columns (lcpc-2d/src/lib.rs:1095-1123): poly[c] = sum_r tensor[r] * coeffs[r][c] ----
+size_t collapse_scratch_bytes(int field, size_t n_rows, size_t n_per_row);
+cudaError_t launch_collapse(int field, const uint32_t *coeffs, size_t row_stride, const uint32_t *tensor,
+                            uint32_t *poly, size_t n_rows, size_t n_per_row, void *scratch, cudaStream_t stream,
+                            int *n_launches);
+
+// ---- open_column gather (lcpc-2d/src/lib.rs:802-808): out[i][r] = comm[r][cols[i]] ----
+cudaError_t launch_gather_columns(int field, const uint32_t *comm, size_t n_rows, size_t row_stride,
+                                  const uint64_t *cols, size_t n_open, uint32_t *out, cudaStream_t stream);
+
+// Merkle paths (lcpc-2d/src/lib.rs:811-821): out[i][l] = sibling of column cols[i]'s ancestor on layer l
+cudaError_t launch_gather_paths(const uint8_t *hashes, size_t np2, const uint64_t *cols, size_t n_open,
+                                unsigned path_len, uint8_t *out, cudaStream_t stream);
+
+}  // namespace lcpc

@@ -1,0 +1,354 @@
+// lcpc_b200/csrc/kernels_expander.cu -- Brakedown row encoding as a chain of batched sparse products.
+//
+// Replaces SdigEncodingS::encode -> encode() (reference: lcpc-brakedown-pc/src/lib.rs:150-153,
+// lcpc-brakedown-pc/src/encode.rs:36-94) with reed_solomon (:97-110) as the base case.  The flat
+// codeword of one row is
+//     x_0 | x_1 | ... | x_{t-1} | RS(x_t) | v_{t-1} | ... | v_0
+//   x_{i+1} = P_i x_i (precodes, :46-58; x_t goes to a temporary, :61-67)
+//   RS(x_t)[k] = sum_j x_t[j] (k+1)^j  (Horner, :101-109)
+//   v_i = Q_i (x_{i+1} | ... | v_{i+1})  (postcodes, reading one contiguous slice, :76-90)
+// `M.dot(x)` is y[i] = sum_j M[i,j] x[j] (sprs CsMat::dot); arithmetic is exact so the summation
+// order is free.
+//
+// All rows of the commit share the matrices, so each level is one SpMM.  The reference's CSC
+// (scatter) form is turned into row-compressed (gather) form once at construction.  During the
+// chain the batch lives TRANSPOSED in a work buffer W[position][row]: the gather of input position j
+// then moves n_rows*B contiguous bytes for the whole batch, and the (index, value) pair of a non-zero
+// is one broadcast load per warp instead of one load per row.  Two tiled transposes connect W to the
+// row-major coefficient / commitment matrices of the C ABI.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "../../include/lcpc_b200.h"
+#include "expander.h"
+#include "field.cuh"
+#include "kernels.h"
+
+namespace lcpc {
+
+struct DeviceCsr {
+  size_t m = 0, n = 0, nnz = 0;
+  uint32_t *rowptr = nullptr;  // m + 1
+  uint32_t *colidx = nullptr;  // nnz
+  uint32_t *vals = nullptr;    // nnz * N limbs
+};
+
+struct ExpanderOp {
+  int kind;  // 0 = sparse product, 1 = reed-solomon
+  int mat;   // index into mats (kind 0)
+  size_t in_off, in_len, out_off, out_len;
+  bool out_tmp, in_tmp;  // x_t lives in the temporary
+};
+
+struct ExpanderCode {
+  int field = 0;
+  size_t n_levels = 0, n_in = 0, n_cols = 0, nnz = 0, tmp_len = 0;
+  std::vector<DeviceCsr> mats;
+  std::vector<ExpanderOp> ops;
+};
+
+size_t expander_n_in(const ExpanderCode *c) { return c->n_in; }
+size_t expander_codeword_length(const ExpanderCode *c) { return c->n_cols; }
+size_t expander_nnz(const ExpanderCode *c) { return c->nnz; }
+
+void expander_free(ExpanderCode *c) {
+  if (!c) return;
+  for (auto &m : c->mats) {
+    cudaFree(m.rowptr);
+    cudaFree(m.colidx);
+    cudaFree(m.vals);
+  }
+  delete c;
+}
+
+static int upload_csr(int field, const CscView &M, cudaStream_t stream, DeviceCsr *out, std::string *err) {
+  const size_t L = field_bytes(field) / 8;  // u64 limbs per element
+  if (!M.ptrs || (M.n && M.ptrs[0] != 0)) {
+    *err = "bad column pointers";
+    return LCPC_B200_ERR_BAD_ARG;
+  }
+  const size_t nnz = M.n ? M.ptrs[M.n] : 0;
+  if (M.m >= 0xffffffffull || M.n >= 0xffffffffull || nnz >= 0xffffffffull) {
+    *err = "matrix too large for 32-bit indices";
+    return LCPC_B200_ERR_TOO_BIG;
+  }
+  std::vector<uint32_t> rowptr(M.m + 1, 0), colidx(nnz);
+  std::vector<uint64_t> vals(nnz * L);
+  for (size_t j = 0; j < M.n; j++) {
+    if (M.ptrs[j + 1] < M.ptrs[j] || M.ptrs[j + 1] > nnz) {
+      *err = "column pointers not monotone";
+      return LCPC_B200_ERR_BAD_ARG;
+    }
+    for (uint64_t k = M.ptrs[j]; k < M.ptrs[j + 1]; k++) {
+      if (M.idxs[k] >= M.m) {
+        *err = "row index out of range";
+        return LCPC_B200_ERR_BAD_ARG;
+      }
+      rowptr[M.idxs[k] + 1]++;
+    }
+  }
+  for (size_t i = 0; i < M.m; i++) rowptr[i + 1] += rowptr[i];
+  std::vector<uint32_t> fill(rowptr.begin(), rowptr.end() - 1);
+  for (size_t j = 0; j < M.n; j++)
+    for (uint64_t k = M.ptrs[j]; k < M.ptrs[j + 1]; k++) {
+      uint32_t pos = fill[M.idxs[k]]++;
+      colidx[pos] = (uint32_t)j;
+      memcpy(&vals[(size_t)pos * L], M.data + k * L, L * 8);
+    }
+  out->m = M.m, out->n = M.n, out->nnz = nnz;
+  cudaError_t e = cudaMalloc(&out->rowptr, (M.m + 1) * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&out->colidx, std::max<size_t>(nnz, 1) * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&out->vals, std::max<size_t>(nnz, 1) * L * 8);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out->rowptr, rowptr.data(), (M.m + 1) * 4, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(out->colidx, colidx.data(), nnz * 4, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(out->vals, vals.data(), nnz * L * 8, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);  // host vectors die at return
+  if (e != cudaSuccess) {
+    *err = cudaGetErrorString(e);
+    return e == cudaErrorMemoryAllocation ? LCPC_B200_ERR_OOM : LCPC_B200_ERR_CUDA;
+  }
+  return LCPC_B200_OK;
+}
+
+int expander_build(int field, size_t t, const CscView *pre, const CscView *post, cudaStream_t stream,
+                   ExpanderCode **out, std::string *err) {
+  ExpanderCode *c = new ExpanderCode;
+  c->field = field, c->n_levels = t;
+  // offsets exactly as encode.rs:36-94 walks them
+  c->n_in = pre[0].n;
+  size_t len = pre[0].n + post[t - 1].n;  // codeword_length, encode.rs:18-33
+  for (size_t i = 0; i + 1 < t; i++) len += pre[i].m;
+  for (size_t i = 0; i < t; i++) len += post[i].m;
+  c->n_cols = len;
+  c->mats.resize(2 * t);
+  int rc = LCPC_B200_OK;
+  size_t in_start = 0;
+  for (size_t i = 0; i < t && rc == LCPC_B200_OK; i++) {
+    if (i + 1 < t && pre[i + 1].n != pre[i].m) {
+      *err = "precode dimensions do not chain";
+      rc = LCPC_B200_ERR_BAD_ARG;
+      break;
+    }
+    rc = upload_csr(field, pre[i], stream, &c->mats[i], err);
+    if (rc != LCPC_B200_OK) break;
+    size_t in_end = in_start + pre[i].n;
+    ExpanderOp op{0, (int)i, in_start, pre[i].n, in_end, pre[i].m, i + 1 == t, false};
+    c->ops.push_back(op);
+    in_start = in_end;
+  }
+  size_t out_start = 0;
+  if (rc == LCPC_B200_OK) {
+    // base case: in_start is now the end of x_{t-1}; RS(x_t) fills [in_start, in_start + post[t-1].n)
+    c->tmp_len = pre[t - 1].m;
+    ExpanderOp rs{1, -1, 0, pre[t - 1].m, in_start, post[t - 1].n, false, true};
+    c->ops.push_back(rs);
+    out_start = in_start + post[t - 1].n;
+    in_start = in_start + pre[t - 1].m;
+    for (size_t i = t; i-- > 0 && rc == LCPC_B200_OK;) {
+      in_start -= pre[i].m;
+      if (out_start - in_start != post[i].n) {
+        *err = "postcode dimensions do not match the codeword slice";
+        rc = LCPC_B200_ERR_BAD_ARG;
+        break;
+      }
+      rc = upload_csr(field, post[i], stream, &c->mats[t + i], err);
+      if (rc != LCPC_B200_OK) break;
+      ExpanderOp op{0, (int)(t + i), in_start, post[i].n, out_start, post[i].m, false, false};
+      c->ops.push_back(op);
+      out_start += post[i].m;
+    }
+  }
+  if (rc == LCPC_B200_OK && (in_start != pre[0].n || out_start != len)) {  // asserts at encode.rs:92-93
+    *err = "codeword offsets do not close";
+    rc = LCPC_B200_ERR_BAD_ARG;
+  }
+  if (rc != LCPC_B200_OK) {
+    expander_free(c);
+    return rc;
+  }
+  for (auto &m : c->mats) c->nnz += m.nnz;
+  *out = c;
+  return LCPC_B200_OK;
+}
+
+size_t expander_scratch_bytes(const ExpanderCode *c, size_t n_rows) {
+  // W[n_cols][n_rows] | T[tmp_len][n_rows] | one
+  return ((c->n_cols + c->tmp_len) * n_rows + 1) * field_bytes(c->field);
+}
+
+// ---- kernels ------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void ldv(uint32_t (&v)[N], const uint32_t *p) {
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 4; i++) {
+      uint4 t = reinterpret_cast<const uint4 *>(p)[i];
+      v[4 * i] = t.x, v[4 * i + 1] = t.y, v[4 * i + 2] = t.z, v[4 * i + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N / 2; i++) {
+      uint2 t = reinterpret_cast<const uint2 *>(p)[i];
+      v[2 * i] = t.x, v[2 * i + 1] = t.y;
+    }
+  }
+}
+template <int N>
+__device__ __forceinline__ void stv(uint32_t *p, const uint32_t (&v)[N]) {
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 4; i++)
+      reinterpret_cast<uint4 *>(p)[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N / 2; i++) reinterpret_cast<uint2 *>(p)[i] = make_uint2(v[2 * i], v[2 * i + 1]);
+  }
+}
+
+// tiled transpose of elements: dst[c * dst_ld + r] = src[r * src_ld + c], r < n_r, c < n_c
+constexpr int TT = 32;
+template <int N>
+__global__ void __launch_bounds__(256)
+transpose_kernel(const uint32_t *__restrict__ src, size_t src_ld, uint32_t *__restrict__ dst, size_t dst_ld,
+                 size_t n_r, size_t n_c) {
+  __shared__ uint32_t tile[N][TT][TT + 1];
+  const size_t c0 = (size_t)blockIdx.x * TT, r0 = (size_t)blockIdx.y * TT;
+  const unsigned tx = threadIdx.x % TT, ty = threadIdx.x / TT;  // 32 x 8
+  for (unsigned rr = ty; rr < TT; rr += 8) {
+    size_t r = r0 + rr, cidx = c0 + tx;
+    if (r < n_r && cidx < n_c) {
+      uint32_t v[N];
+      ldv<N>(v, src + (r * src_ld + cidx) * N);
+#pragma unroll
+      for (int l = 0; l < N; l++) tile[l][rr][tx] = v[l];
+    }
+  }
+  __syncthreads();
+  for (unsigned cc = ty; cc < TT; cc += 8) {
+    size_t cidx = c0 + cc, r = r0 + tx;
+    if (r < n_r && cidx < n_c) {
+      uint32_t v[N];
+#pragma unroll
+      for (int l = 0; l < N; l++) v[l] = tile[l][tx][cc];
+      stv<N>(dst + (cidx * dst_ld + r) * N, v);
+    }
+  }
+}
+
+// y[i][r] = sum_k vals[k] * x[colidx[k]][r]; one thread per (output i, batch row r), r fastest
+template <int FID>
+__global__ void __launch_bounds__(256)
+spmm_kernel(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ colidx, const uint32_t *__restrict__ vals,
+            const uint32_t *__restrict__ x, uint32_t *__restrict__ y, size_t m, size_t n_rows) {
+  using F = Field<FID>;
+  constexpr int N = F::N;
+  const size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= m * n_rows) return;
+  const size_t i = item / n_rows, r = item % n_rows;
+  const uint32_t k0 = __ldg(rowptr + i), k1 = __ldg(rowptr + i + 1);
+  typename F::Elem acc = F::zero();
+  for (uint32_t k = k0; k < k1; k++) {
+    const size_t j = __ldg(colidx + k);
+    typename F::Elem a, xv;
+    ldv<N>(a.v, vals + (size_t)k * N);
+    ldv<N>(xv.v, x + (j * n_rows + r) * N);
+    acc = F::add(acc, F::mul(a, xv));
+  }
+  stv<N>(y + (i * n_rows + r) * N, acc.v);
+}
+
+// reed_solomon (encode.rs:97-110): out[k][r] = Horner of in[.][r] at the point k+1
+template <int FID>
+__global__ void __launch_bounds__(128)
+reed_solomon_kernel(const uint32_t *__restrict__ xin, size_t n_in, uint32_t *__restrict__ out, size_t n_out,
+                    size_t n_rows, const uint32_t *__restrict__ one_mont) {
+  using F = Field<FID>;
+  constexpr int N = F::N;
+  const size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= n_out * n_rows) return;
+  const size_t k = item / n_rows, r = item % n_rows;
+  typename F::Elem one, pt;
+  ldv<N>(one.v, one_mont);
+  pt = one;
+  for (size_t q = 0; q < k; q++) pt = F::add(pt, one);  // the field element k+1
+  typename F::Elem acc = F::zero();
+  for (size_t j = n_in; j-- > 0;) {
+    typename F::Elem c;
+    ldv<N>(c.v, xin + (j * n_rows + r) * N);
+    acc = F::add(F::mul(acc, pt), c);
+  }
+  stv<N>(out + (k * n_rows + r) * N, acc.v);
+}
+
+template <int FID> __global__ void one_mont_kernel(uint32_t *out) {
+  using F = Field<FID>;
+  typename F::Elem one = F::zero();
+  one.v[0] = 1;
+  for (int i = 0; i < 32 * F::N; i++) one = F::add(one, one);  // 2^(32N) mod p
+  for (int l = 0; l < F::N; l++) out[l] = one.v[l];
+}
+
+template <int FID>
+static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_t src_stride, size_t valid,
+                               uint32_t *dst, size_t dst_stride, size_t n_rows, void *scratch, cudaStream_t st,
+                               int *n_launches) {
+  using F = Field<FID>;
+  constexpr int N = F::N;
+  if (n_launches) *n_launches = 0;
+  if (n_rows == 0) return cudaSuccess;
+  if (valid < c->n_in || !scratch) return cudaErrorInvalidValue;
+  uint32_t *W = (uint32_t *)scratch;                       // [n_cols][n_rows]
+  uint32_t *T = W + c->n_cols * n_rows * N;                // [tmp_len][n_rows]
+  int launches = 0;
+  // coefficients -> W[0 .. n_in)
+  {
+    dim3 grid((unsigned)((c->n_in + TT - 1) / TT), (unsigned)((n_rows + TT - 1) / TT));
+    transpose_kernel<N><<<grid, 256, 0, st>>>(src, src_stride, W, n_rows, n_rows, c->n_in);
+    launches++;
+  }
+  for (const ExpanderOp &op : c->ops) {
+    if (op.kind == 0) {
+      const DeviceCsr &M = c->mats[op.mat];
+      const uint32_t *x = W + op.in_off * n_rows * N;
+      uint32_t *y = op.out_tmp ? T : W + op.out_off * n_rows * N;
+      size_t items = M.m * n_rows;
+      if (items) {
+        spmm_kernel<FID><<<(unsigned)((items + 255) / 256), 256, 0, st>>>(M.rowptr, M.colidx, M.vals, x, y, M.m, n_rows);
+        launches++;
+      }
+    } else {
+      size_t items = op.out_len * n_rows;
+      // R mod p (the field's `one`) sits in a dedicated slot right after T (see expander_scratch_bytes)
+      uint32_t *one_slot = T + c->tmp_len * n_rows * N;
+      one_mont_kernel<FID><<<1, 1, 0, st>>>(one_slot);
+      reed_solomon_kernel<FID><<<(unsigned)((items + 127) / 128), 128, 0, st>>>(T, op.in_len, W + op.out_off * n_rows * N,
+                                                                               op.out_len, n_rows, one_slot);
+      launches += 2;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  // W -> row-major codewords
+  {
+    dim3 grid((unsigned)((n_rows + TT - 1) / TT), (unsigned)((c->n_cols + TT - 1) / TT));
+    transpose_kernel<N><<<grid, 256, 0, st>>>(W, n_rows, dst, dst_stride, c->n_cols, n_rows);
+    launches++;
+  }
+  if (n_launches) *n_launches = launches;
+  return cudaGetLastError();
+}
+
+cudaError_t expander_encode_rows(const ExpanderCode *c, const uint32_t *src, size_t src_stride, size_t valid,
+                                 uint32_t *dst, size_t dst_stride, size_t n_rows, void *scratch, cudaStream_t st,
+                                 int *n_launches) {
+  switch (c->field) {
+    case FT63: return encode_impl<FT63>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches);
+    case FT127: return encode_impl<FT127>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches);
+    case FT191: return encode_impl<FT191>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches);
+    case FT255: return encode_impl<FT255>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace lcpc

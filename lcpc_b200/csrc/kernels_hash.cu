@@ -1,0 +1,315 @@
+// lcpc_b200/csrc/kernels_hash.cu -- per-column BLAKE3 leaf digests and the Merkle layers.
+//
+// Replaces hash_columns / merkle_tree / merkle_layer (reference: lcpc-2d/src/lib.rs:706-785):
+//   leaf[c] = D( 0x00*32 || to_repr(comm[0][c]) || ... || to_repr(comm[n_rows-1][c]) )   (:719-735)
+//   node    = D( left || right )                                                          (:768-775)
+// with D = BLAKE3 and to_repr = canonical little-endian bytes (FieldHash::digest_update, :42-57), so
+// every element is taken out of Montgomery form on the fly, in registers, right after its load.
+//
+// Layout / parallelism: the leaf input of one column is Ltot = 32 + B*n_rows bytes = ceil(Ltot/1024)
+// BLAKE3 chunks.  Chunks are independent until the tree merge, so the grid is (columns x chunks):
+// adjacent lanes own adjacent columns, which makes every row read a fully coalesced run of
+// 32*B bytes per warp; a second small kernel merges the chunk chaining values per column.
+#include "blake3.cuh"
+#include "field.cuh"
+#include "kernels.h"
+
+namespace lcpc {
+
+constexpr int HASH_THREADS = 128;
+
+template <int N>
+__device__ __forceinline__ void gload_elem(uint32_t (&v)[N], const uint32_t *p) {
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 4; i++) {
+      uint4 t = __ldg(reinterpret_cast<const uint4 *>(p) + i);
+      v[4 * i] = t.x, v[4 * i + 1] = t.y, v[4 * i + 2] = t.z, v[4 * i + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N / 2; i++) {
+      uint2 t = __ldg(reinterpret_cast<const uint2 *>(p) + i);
+      v[2 * i] = t.x, v[2 * i + 1] = t.y;
+    }
+  }
+}
+
+// Chunk `k` of column `col`.  Works in "slots" of one element (B bytes): slot s of the leaf input is
+// zero for s < 32/B (the 32-byte zero prefix, lib.rs:722-723) and row s - 32/B after that.
+// Requires B | 64 (Ft63, Ft127, Ft255).
+template <int FID>
+__global__ void __launch_bounds__(HASH_THREADS)
+leaf_chunk_kernel(const uint32_t *__restrict__ comm, size_t n_rows, size_t n_cols, size_t row_stride,
+                  uint32_t *__restrict__ out, unsigned n_chunks) {
+  using F = Field<FID>;
+  constexpr int N = F::N;
+  constexpr int B = F::BYTES;
+  static_assert(64 % B == 0, "element must divide the BLAKE3 block");
+  constexpr int SPB = 64 / B;        // slots per block
+  constexpr int PRE = 32 / B;        // zero-prefix slots
+  const size_t col = (size_t)blockIdx.x * HASH_THREADS + threadIdx.x;
+  const unsigned k = blockIdx.y;
+  if (col >= n_cols) return;
+  const size_t total = 32 + (size_t)B * n_rows;
+  const size_t chunk_off = (size_t)k * b3::CHUNK_LEN;
+  const size_t chunk_len = (total - chunk_off < (size_t)b3::CHUNK_LEN) ? total - chunk_off : (size_t)b3::CHUNK_LEN;
+  const unsigned n_blocks = (unsigned)((chunk_len + 63) / 64);
+  uint32_t cv[8];
+  b3::set_iv(cv);
+  const uint32_t *cp = comm + col * N;
+  for (unsigned b = 0; b < n_blocks; b++) {
+    uint32_t m[16];
+    const size_t slot0 = (chunk_off + (size_t)b * 64) / B;
+#pragma unroll
+    for (int i = 0; i < SPB; i++) {
+      const size_t slot = slot0 + i;
+      typename F::Elem x = F::zero();
+      if (slot >= PRE && slot - PRE < n_rows) {
+        typename F::Elem raw;
+        gload_elem<N>(raw.v, cp + (slot - PRE) * row_stride * N);
+        x = F::from_mont(raw);
+      }
+#pragma unroll
+      for (int l = 0; l < N; l++) m[i * N + l] = x.v[l];
+    }
+    const bool lastb = (b + 1 == n_blocks);
+    const uint32_t block_len = lastb ? (uint32_t)(chunk_len - (size_t)b * 64) : 64u;
+    uint32_t flags = (b == 0 ? b3::CHUNK_START : 0u) | (lastb ? b3::CHUNK_END : 0u);
+    if (lastb && n_chunks == 1) flags |= b3::ROOT;
+    b3::compress(cv, m, k, block_len, flags);
+  }
+  // single chunk: this is the digest; else the chunk chaining value for the merge kernel
+  uint32_t *o = out + ((size_t)k * n_cols + col) * 8;
+  reinterpret_cast<uint4 *>(o)[0] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+  reinterpret_cast<uint4 *>(o)[1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+}
+
+// Ft191 (B = 24 does not divide 64): one generic word-granular walk; each block converts the <= 4
+// elements it overlaps.  Kept simple: no reference test or bench uses this field with a commit.
+template <int FID>
+__global__ void __launch_bounds__(HASH_THREADS)
+leaf_chunk_kernel_generic(const uint32_t *__restrict__ comm, size_t n_rows, size_t n_cols, size_t row_stride,
+                          uint32_t *__restrict__ out, unsigned n_chunks) {
+  using F = Field<FID>;
+  constexpr int N = F::N;
+  constexpr int B = F::BYTES;
+  const size_t col = (size_t)blockIdx.x * HASH_THREADS + threadIdx.x;
+  const unsigned k = blockIdx.y;
+  if (col >= n_cols) return;
+  const size_t total = 32 + (size_t)B * n_rows;
+  const size_t chunk_off = (size_t)k * b3::CHUNK_LEN;
+  const size_t chunk_len = (total - chunk_off < (size_t)b3::CHUNK_LEN) ? total - chunk_off : (size_t)b3::CHUNK_LEN;
+  const unsigned n_blocks = (unsigned)((chunk_len + 63) / 64);
+  uint32_t cv[8];
+  b3::set_iv(cv);
+  const uint32_t *cp = comm + col * N;
+  size_t cached_row = (size_t)-1;
+  uint32_t canon[N];
+  for (unsigned b = 0; b < n_blocks; b++) {
+    uint32_t m[16];
+    for (int w = 0; w < 16; w++) {
+      const size_t off = chunk_off + (size_t)b * 64 + 4 * (size_t)w;
+      uint32_t word = 0;
+      if (off >= 32 && off < total) {
+        const size_t row = (off - 32) / B;
+        const unsigned limb = (unsigned)(((off - 32) % B) / 4);
+        if (row != cached_row) {
+          typename F::Elem raw;
+          gload_elem<N>(raw.v, cp + row * row_stride * N);
+          typename F::Elem c = F::from_mont(raw);
+#pragma unroll
+          for (int l = 0; l < N; l++) canon[l] = c.v[l];
+          cached_row = row;
+        }
+#pragma unroll
+        for (int l = 0; l < N; l++)
+          if (l == (int)limb) word = canon[l];
+      }
+#pragma unroll
+      for (int i = 0; i < 16; i++)
+        if (i == w) m[i] = word;
+    }
+    const bool lastb = (b + 1 == n_blocks);
+    const uint32_t block_len = lastb ? (uint32_t)(chunk_len - (size_t)b * 64) : 64u;
+    uint32_t flags = (b == 0 ? b3::CHUNK_START : 0u) | (lastb ? b3::CHUNK_END : 0u);
+    if (lastb && n_chunks == 1) flags |= b3::ROOT;
+    b3::compress(cv, m, k, block_len, flags);
+  }
+  uint32_t *o = out + ((size_t)k * n_cols + col) * 8;
+  reinterpret_cast<uint4 *>(o)[0] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+  reinterpret_cast<uint4 *>(o)[1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+}
+
+__device__ __forceinline__ void parent_cv(uint32_t (&out)[8], const uint32_t (&l)[8], const uint32_t (&r)[8],
+                                          uint32_t extra_flags) {
+  uint32_t m[16];
+#pragma unroll
+  for (int i = 0; i < 8; i++) m[i] = l[i], m[8 + i] = r[i];
+  b3::set_iv(out);
+  b3::compress(out, m, 0, 64, b3::PARENT | extra_flags);
+}
+
+// BLAKE3 tree over the n_chunks chaining values of each column (chunk-major scratch [k][col][8]).
+constexpr int MAX_STACK = 24;
+__global__ void __launch_bounds__(HASH_THREADS)
+leaf_merge_kernel(const uint32_t *__restrict__ cvs, size_t n_cols, unsigned n_chunks, uint32_t *__restrict__ leaves) {
+  const size_t col = (size_t)blockIdx.x * HASH_THREADS + threadIdx.x;
+  if (col >= n_cols) return;
+  uint32_t stack[MAX_STACK][8];
+  int depth = 0;
+  uint32_t cur[8];
+  for (unsigned k = 0; k < n_chunks; k++) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(cvs + ((size_t)k * n_cols + col) * 8);
+    uint4 a = __ldg(p), b = __ldg(p + 1);
+    cur[0] = a.x, cur[1] = a.y, cur[2] = a.z, cur[3] = a.w, cur[4] = b.x, cur[5] = b.y, cur[6] = b.z, cur[7] = b.w;
+    if (k + 1 == n_chunks) break;
+    // add_chunk_chaining_value: merge completed subtrees (one per trailing zero bit of the count)
+    unsigned total = k + 1;
+    while ((total & 1u) == 0) {
+      uint32_t merged[8];
+      depth--;
+      parent_cv(merged, stack[depth], cur, 0);
+#pragma unroll
+      for (int i = 0; i < 8; i++) cur[i] = merged[i];
+      total >>= 1;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) stack[depth][i] = cur[i];
+    depth++;
+  }
+  // finalize: fold the stack from the top, ROOT on the last parent
+  while (depth > 0) {
+    uint32_t merged[8];
+    depth--;
+    parent_cv(merged, stack[depth], cur, depth == 0 ? b3::ROOT : 0u);
+#pragma unroll
+    for (int i = 0; i < 8; i++) cur[i] = merged[i];
+  }
+  uint32_t *o = leaves + col * 8;
+  reinterpret_cast<uint4 *>(o)[0] = make_uint4(cur[0], cur[1], cur[2], cur[3]);
+  reinterpret_cast<uint4 *>(o)[1] = make_uint4(cur[4], cur[5], cur[6], cur[7]);
+}
+
+static unsigned leaf_chunks(int field, size_t n_rows) {
+  size_t total = 32 + field_bytes(field) * n_rows;
+  return (unsigned)((total + b3::CHUNK_LEN - 1) / b3::CHUNK_LEN);
+}
+
+size_t hash_scratch_bytes(int field, size_t n_rows, size_t n_cols) {
+  unsigned k = leaf_chunks(field, n_rows);
+  return k > 1 ? (size_t)k * n_cols * 32 : 0;
+}
+
+cudaError_t launch_hash_columns(int field, const uint32_t *comm, size_t n_rows, size_t n_cols, size_t row_stride,
+                                uint8_t *leaves, void *scratch, cudaStream_t stream, int *n_launches) {
+  if (n_launches) *n_launches = 0;
+  if (n_cols == 0) return cudaSuccess;
+  const unsigned n_chunks = leaf_chunks(field, n_rows);
+  if (n_chunks > 65535u) return cudaErrorInvalidValue;
+  uint32_t *out = n_chunks > 1 ? (uint32_t *)scratch : (uint32_t *)leaves;
+  if (n_chunks > 1 && !scratch) return cudaErrorInvalidValue;
+  dim3 grid((unsigned)((n_cols + HASH_THREADS - 1) / HASH_THREADS), n_chunks);
+  switch (field) {
+    case FT63: leaf_chunk_kernel<FT63><<<grid, HASH_THREADS, 0, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks); break;
+    case FT127: leaf_chunk_kernel<FT127><<<grid, HASH_THREADS, 0, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks); break;
+    case FT191: leaf_chunk_kernel_generic<FT191><<<grid, HASH_THREADS, 0, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks); break;
+    case FT255: leaf_chunk_kernel<FT255><<<grid, HASH_THREADS, 0, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks); break;
+    default: return cudaErrorInvalidValue;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (n_launches) ++*n_launches;
+  if (n_chunks > 1) {
+    leaf_merge_kernel<<<grid.x, HASH_THREADS, 0, stream>>>((const uint32_t *)scratch, n_cols, n_chunks, (uint32_t *)leaves);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (n_launches) ++*n_launches;
+  }
+  return cudaSuccess;
+}
+
+// ---- Merkle layers: node = BLAKE3(left || right), a single 64-byte block (lib.rs:768-775) ----
+__global__ void __launch_bounds__(HASH_THREADS)
+merkle_layer_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t n_out) {
+  const size_t i = (size_t)blockIdx.x * HASH_THREADS + threadIdx.x;
+  if (i >= n_out) return;
+  const uint4 *p = reinterpret_cast<const uint4 *>(in + i * 16);
+  uint32_t m[16];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    uint4 t = p[q];
+    m[4 * q] = t.x, m[4 * q + 1] = t.y, m[4 * q + 2] = t.z, m[4 * q + 3] = t.w;
+  }
+  uint32_t cv[8];
+  b3::set_iv(cv);
+  b3::compress(cv, m, 0, 64, b3::CHUNK_START | b3::CHUNK_END | b3::ROOT);
+  uint32_t *o = out + i * 8;
+  reinterpret_cast<uint4 *>(o)[0] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+  reinterpret_cast<uint4 *>(o)[1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+}
+
+// Many layers in one launch: a CTA reduces a subtree of 2^LOG_SUB nodes in shared memory and writes
+// every intermediate layer to its place in the flat `hashes` array.
+constexpr int MERKLE_LOG_SUB = 8;  // 256 input nodes (8 KiB) per CTA -> 8 layers per launch
+__global__ void __launch_bounds__(128)
+merkle_subtree_kernel(uint32_t *hashes, size_t layer_off, size_t layer_len, unsigned n_layers) {
+  __shared__ uint32_t buf[(1 << MERKLE_LOG_SUB) * 8];
+  const unsigned sub = 1u << n_layers;  // input nodes per CTA
+  const size_t first = (size_t)blockIdx.x * sub;
+  for (unsigned i = threadIdx.x; i < sub * 2; i += blockDim.x)
+    reinterpret_cast<uint4 *>(buf)[i] = reinterpret_cast<const uint4 *>(hashes + (layer_off + first) * 8)[i];
+  __syncthreads();
+  size_t in_off = layer_off, in_len = layer_len;
+  unsigned width = sub;
+  for (unsigned l = 0; l < n_layers; l++) {
+    const size_t out_off = in_off + in_len, out_len = in_len >> 1;
+    const unsigned n_out = width >> 1;
+    uint32_t cv[8];
+    const bool act = threadIdx.x < n_out;
+    if (act) {
+      uint32_t m[16];
+#pragma unroll
+      for (int q = 0; q < 16; q++) m[q] = buf[threadIdx.x * 16 + q];
+      b3::set_iv(cv);
+      b3::compress(cv, m, 0, 64, b3::CHUNK_START | b3::CHUNK_END | b3::ROOT);
+    }
+    __syncthreads();
+    if (act) {
+#pragma unroll
+      for (int q = 0; q < 8; q++) buf[threadIdx.x * 8 + q] = cv[q];
+      uint32_t *o = hashes + (out_off + ((size_t)blockIdx.x * n_out) + threadIdx.x) * 8;
+      reinterpret_cast<uint4 *>(o)[0] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+      reinterpret_cast<uint4 *>(o)[1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+    }
+    __syncthreads();
+    in_off = out_off, in_len = out_len, width = n_out;
+  }
+}
+
+cudaError_t launch_merkle_tree(uint8_t *hashes, size_t np2, cudaStream_t stream, int *n_launches) {
+  if (n_launches) *n_launches = 0;
+  uint32_t *h = (uint32_t *)hashes;
+  size_t off = 0, len = np2;
+  while (len > 1) {
+    unsigned log_len = 0;
+    while (((size_t)1 << log_len) < len) log_len++;
+    if (len >= 2 * HASH_THREADS * 148u) {
+      // wide layer: one thread per node keeps every SM busy
+      size_t n_out = len >> 1;
+      merkle_layer_kernel<<<(unsigned)((n_out + HASH_THREADS - 1) / HASH_THREADS), HASH_THREADS, 0, stream>>>(
+          h + off * 8, h + (off + len) * 8, n_out);
+      off += len, len = n_out;
+    } else {
+      unsigned nl = log_len < (unsigned)MERKLE_LOG_SUB ? log_len : (unsigned)MERKLE_LOG_SUB;
+      merkle_subtree_kernel<<<(unsigned)(len >> nl), 128, 0, stream>>>(h, off, len, nl);
+      for (unsigned l = 0; l < nl; l++) off += len, len >>= 1;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (n_launches) ++*n_launches;
+  }
+  return cudaSuccess;
+}
+
+}  // namespace lcpc

@@ -1,0 +1,40 @@
+// tests/host/field_host_check.cu -- TEST ONLY.
+// Runs lcpc_b200/csrc/field.cuh's carry-chain algorithms on the HOST (through the header's flag
+// emulation) so their logic can be compared with the oracle in the CPU-only container.  The CUDA
+// build of the very same header is compared with the oracle on the GPU in tests/test_gpu_parity.py.
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+
+#include "../../lcpc_b200/csrc/field.cuh"
+
+using namespace lcpc;
+
+template <int FID>
+static int run(int op, uint64_t *r, const uint64_t *a, const uint64_t *b, size_t n) {
+  using F = Field<FID>;
+  typename F::Elem x, y, z;
+  for (size_t i = 0; i < n; i++) {
+    memcpy(x.v, a + i * (F::N / 2), F::BYTES);
+    if (b) memcpy(y.v, b + i * (F::N / 2), F::BYTES);
+    switch (op) {
+      case 0: z = F::add(x, y); break;
+      case 1: z = F::sub(x, y); break;
+      case 2: z = F::mul(x, y); break;
+      case 4: z = F::from_mont(x); break;
+      default: return -1;
+    }
+    memcpy(r + i * (F::N / 2), z.v, F::BYTES);
+  }
+  return 0;
+}
+
+extern "C" int hostcheck_field_op(int field, int op, uint64_t *r, const uint64_t *a, const uint64_t *b, size_t n) {
+  switch (field) {
+    case FT63: return run<FT63>(op, r, a, b, n);
+    case FT127: return run<FT127>(op, r, a, b, n);
+    case FT191: return run<FT191>(op, r, a, b, n);
+    case FT255: return run<FT255>(op, r, a, b, n);
+  }
+  return -2;
+}

@@ -1,0 +1,85 @@
+"""Full-size parity (BASELINE.json configs 2-4) through checks whose cost does not grow with the
+whole matrix: complete rows against the oracle's single-row encode, sampled columns against the leaf
+rule, the whole Merkle tree rebuilt by the oracle from the GPU's leaves, linearity of the encoding,
+and collapse against the oracle on the padded coefficient matrix.
+"""
+import numpy as np
+import pytest
+
+import oracle as O
+import lcpc_b200 as P
+
+pytestmark = pytest.mark.gpu
+
+
+def check_commit_samples(c, oenc, x, field, rows, cols, full_oracle=False):
+    L = c.enc.L
+    comm = c.comm.reshape(c.n_rows, c.n_cols, L)
+    coeffs = c.coeffs.reshape(c.n_rows, c.n_per_row, L)
+    flat = coeffs.reshape(-1, L)
+    assert (flat[:x.shape[0]] == x).all() and not flat[x.shape[0]:].any()
+    for r in rows:  # whole rows: encode parity at the real transform length
+        row = np.zeros((c.n_cols, L), np.uint64)
+        row[:c.n_per_row] = coeffs[r]
+        assert (oenc.encode(row) == comm[r]).all(), r
+    hashes = c.hashes
+    for col in cols:  # leaf rule on sampled columns
+        data = bytes(32) + O.to_repr(field, comm[:, col]).tobytes()
+        assert hashes[col].tobytes() == O.blake3(data), col
+    np2 = 1 << (c.n_cols - 1).bit_length()
+    assert not hashes[c.n_cols:np2].any()
+    assert (O.merkle_tree(hashes[:np2]) == hashes).all()  # every inner node and the root
+    assert c.get_root().root == hashes[-1].tobytes()
+    if full_oracle:
+        oc = oenc.commit(x)
+        assert oc["root"] == c.get_root().root and (oc["hashes"] == hashes).all() and (oc["comm"] == c.comm).all()
+
+
+def test_ligero_ft255_2_20_full_oracle():
+    """config 2: lcpc-ligero-pc commit, Ft255, 2^20 coefficients -- complete comparison."""
+    field, length = P.FT255, 1 << 20
+    enc, oenc = P.LigeroEncoding(field, length), O.Encoding.ligero(field, length)
+    assert (enc.n_per_row, enc.n_cols) == (16384, 32768)
+    x = O.random_elems(field, length, seed=20)
+    c = P.LcCommit.commit(x, enc)
+    assert c.n_rows == 64
+    check_commit_samples(c, oenc, x, field, rows=[0, 63], cols=[0, 1, 32767, 12345], full_oracle=True)
+
+
+def test_ligero_ft255_2_24_sampled():
+    """config 4 on one GPU: 256 x 65536 -> 131072, 2^17-point transforms, 9-chunk leaves."""
+    field, length = P.FT255, 1 << 24
+    enc, oenc = P.LigeroEncoding(field, length), O.Encoding.ligero(field, length)
+    assert (enc.n_per_row, enc.n_cols) == (65536, 131072)
+    x = O.random_elems(field, length, seed=24)
+    c = P.LcCommit.commit(x, enc)
+    assert c.n_rows == 256
+    check_commit_samples(c, oenc, x, field, rows=[0, 1, 128, 255], cols=[0, 1, 2, 65535, 65536, 131071, 99999, 31337])
+    # linearity of the committed encoding (lcpc-2d/src/tests.rs:193-236): enc(a)+enc(b) == enc(a+b)
+    comm = c.comm.reshape(c.n_rows, c.n_cols, 4)
+    coeffs = c.coeffs.reshape(c.n_rows, c.n_per_row, 4)
+    s = np.zeros((c.n_cols, 4), np.uint64)
+    s[:c.n_per_row] = O.field_op(field, "add", coeffs[3], coeffs[200])
+    assert (enc.encode(s) == O.field_op(field, "add", comm[3], comm[200])).all()
+    # collapse on the full coefficient matrix
+    tensor = O.random_elems(field, c.n_rows, seed=5)
+    assert (c.collapse(tensor) == O.collapse(field, c.coeffs, tensor, c.n_rows, c.n_per_row)).all()
+    vals, paths = c.open_columns([7, 131071])
+    for i, col in enumerate([7, 131071]):
+        assert (vals[i] == comm[:, col]).all()
+        assert O.verify_column_path(field, vals[i], paths[i], col, c.get_root().root)
+
+
+def test_brakedown_ft127_2_24_sampled():
+    """config 3: lcpc-brakedown-pc commit, Ft127, 2^24 coefficients (72 x 235173 -> 357699)."""
+    field, length = P.FT127, 1 << 24
+    enc = P.SdigEncoding(field, length, seed=0)
+    assert (enc.n_per_row, enc.n_cols) == (235173, 357699)
+    pre, post = enc.matrices()
+    oenc = O.Encoding.sdig_from_matrices(field, pre, post)  # same code, no second matgen run
+    x = O.random_elems(field, length, seed=3)
+    c = P.LcCommit.commit(x, enc)
+    assert c.n_rows == 72
+    check_commit_samples(c, oenc, x, field, rows=[0, 35, 71], cols=[0, 1, 235172, 235173, 357698, 300000, 41861])
+    tensor = O.random_elems(field, c.n_rows, seed=6)
+    assert (c.collapse(tensor) == O.collapse(field, c.coeffs, tensor, c.n_rows, c.n_per_row)).all()

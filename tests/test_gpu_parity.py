@@ -1,0 +1,328 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle and the golden
+fixtures.  Bit-exact everywhere (integer prime-field arithmetic and hashing; no tolerance).
+
+Sizes: seeded inputs at sizes the oracle finishes in seconds; BASELINE.json's full sizes
+(2^20 / 2^24) are covered in test_gpu_fullsize.py through whole-row, sampled-column and Merkle-tree
+checks.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+import lcpc_b200 as P
+from lcpc_b200 import _cabi
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FIELDS = [P.FT63, P.FT127, P.FT191, P.FT255]
+
+
+def rows_from(field, n_rows, n_cols, seed):
+    return O.random_elems(field, n_rows * n_cols, seed=seed)
+
+
+# ------------------------------------------------------------------ field arithmetic
+@pytest.mark.parametrize("field", FIELDS)
+def test_field_ops(field):
+    n = 100_000
+    a, b = O.random_elems(field, n, seed=11), O.random_elems(field, n, seed=12)
+    p = O.field_info(field)["modulus"]
+    nl = O.FIELD_LIMBS[field]
+    edge = O.ints_to_elems([0, 1, p - 1, p - 2, (1 << (64 * nl - 1)) % p, 0xffffffff, 1 << 32, p - 0xffffffff], field)
+    a[:8], b[:8] = edge, edge[::-1]
+    a[8:16], b[8:16] = edge, edge
+    for op in ("add", "sub", "mul"):
+        assert (P.field_op(field, op, a, b) == O.field_op(field, op, a, b)).all(), op
+    assert (P.field_op(field, "from_mont", a) == O.field_op(field, "from_mont", a)).all()
+
+
+# ------------------------------------------------------------------ hashing / Merkle
+def test_leaf_rule_golden_vectors():
+    """leaf = D(0^32 || repr(col[0]) || ...) against the fixtures made with the Rust crate's binding."""
+    g = json.load(open(os.path.join(GOLD, "blake3_vectors.json")))
+    fld = {8: P.FT63, 16: P.FT127, 24: P.FT191, 32: P.FT255}
+    for v in g["leaf_of_1_to_n"]:
+        field, n_rows = fld[v["elem_bytes"]], v["n_rows"]
+        col = O.to_mont(field, list(range(1, n_rows + 1)))
+        comm = np.repeat(col[:, None, :], 3, axis=1).reshape(-1, O.FIELD_LIMBS[field])
+        h = P.merkleize(field, comm, n_rows, 3)
+        assert h.shape == (7, 32)
+        for c in range(3):
+            assert h[c].tobytes().hex() == v["hash"], (v["elem_bytes"], n_rows)
+        assert not h[3].any()  # padding leaf stays Output::default()
+        assert h[4].tobytes() == O.blake3(h[0].tobytes() + h[1].tobytes())
+        assert h[5].tobytes().hex() != g["node_zero_zero"]
+        assert h[6].tobytes() == O.blake3(h[4].tobytes() + h[5].tobytes())
+
+
+def test_node_rule_golden():
+    g = json.load(open(os.path.join(GOLD, "blake3_vectors.json")))
+    # 1 real column + 3 padding leaves: node over two zero leaves must be the golden constant
+    comm = O.to_mont(P.FT63, [5])
+    h = P.merkleize(P.FT63, np.tile(comm, (5, 1)), 1, 5)  # 5 columns -> np2 = 8
+    assert h[8 + 3].tobytes().hex() == g["node_zero_zero"]  # layer-1 node over leaves 6,7
+
+
+@pytest.mark.parametrize("field,n_rows,n_cols", [
+    (P.FT255, 1, 1), (P.FT255, 2, 1024), (P.FT255, 31, 100), (P.FT255, 32, 257), (P.FT255, 33, 64),
+    (P.FT255, 64, 300), (P.FT255, 256, 96), (P.FT255, 1024, 40),
+    (P.FT127, 1, 7), (P.FT127, 18, 1000), (P.FT127, 62, 129), (P.FT127, 63, 128), (P.FT127, 72, 513),
+    (P.FT127, 286, 70),
+    (P.FT63, 3, 50), (P.FT63, 124, 33), (P.FT63, 125, 32), (P.FT63, 500, 20),
+    (P.FT191, 1, 5), (P.FT191, 41, 77), (P.FT191, 42, 64), (P.FT191, 200, 31),
+])
+def test_merkleize_vs_oracle(field, n_rows, n_cols):
+    comm = rows_from(field, n_rows, n_cols, seed=n_rows * 1000 + n_cols)
+    got = P.merkleize(field, comm, n_rows, n_cols)
+    want = O.merkleize(field, comm, n_rows, n_cols)
+    assert (got == want).all()
+    assert (got == O.merkleize(field, comm, n_rows, n_cols, serial=True)).all()  # lcpc-2d tests.rs:136-149
+
+
+# ------------------------------------------------------------------ Ligero encode
+@pytest.mark.parametrize("field", FIELDS)
+@pytest.mark.parametrize("log_n", [1, 2, 3, 5, 8, 10, 11, 12, 13, 15])
+def test_ligero_encode_vs_oracle(field, log_n):
+    n_cols = 1 << log_n
+    n_per_row = n_cols // 2
+    enc = P.LigeroEncoding.new_from_dims(field, n_per_row, n_cols)
+    oenc = O.Encoding.ligero_from_dims(field, n_per_row, n_cols)
+    n_rows = 3 if log_n < 13 else 2
+    rows = np.zeros((n_rows, n_cols, enc.L), np.uint64)
+    rows[:, :n_per_row] = O.random_elems(field, n_rows * n_per_row, seed=log_n).reshape(n_rows, n_per_row, -1)
+    got = enc.encode(rows)
+    for r in range(n_rows):
+        assert (got[r] == oenc.encode(rows[r])).all(), r
+    # the whole row is input (verifier use, lcpc-2d/src/lib.rs:886): a dense row must work too
+    dense = O.random_elems(field, n_cols, seed=99)
+    assert (enc.encode(dense) == oenc.encode(dense)).all()
+
+
+@pytest.mark.parametrize("rho,n_cols", [((1, 4), 1 << 12), ((39, 40), 1 << 13), ((1, 2), 1 << 16)])
+def test_ligero_commit_other_rates(rho, n_cols):
+    field = P.FT127
+    n_per_row = n_cols * rho[0] // rho[1]
+    enc = P.LigeroEncoding.new_from_dims(field, n_per_row, n_cols, rho=rho)
+    oenc = O.Encoding.ligero_from_dims(field, n_per_row, n_cols, rho=rho)
+    length = 3 * n_per_row - 17
+    x = O.random_elems(field, length, seed=5)
+    c, oc = P.LcCommit.commit(x, enc), oenc.commit(x)
+    assert c.get_root().root == oc["root"]
+    assert (c.comm == oc["comm"]).all() and (c.coeffs == oc["coeffs"]).all() and (c.hashes == oc["hashes"]).all()
+
+
+def test_ligero_errors():
+    with pytest.raises(P.LcpcError) as e:
+        P.LigeroEncoding.new_from_dims(P.FT255, 8, 12)  # not a power of two: dims_ok fails
+    assert e.value.code == _cabi.ERR_BAD_ARG
+    with pytest.raises(P.LcpcError):
+        P.LigeroEncoding.new_from_dims(P.FT255, 16, 16)  # n_per_row must be < n_cols
+    enc = P.LigeroEncoding.new_from_dims(P.FT63, 8, 16)
+    with pytest.raises(P.LcpcError):
+        enc.encode(np.zeros((15, 1), np.uint64))
+    with pytest.raises(P.LcpcError):
+        P.LcCommit.commit(np.zeros((0, 1), np.uint64), enc)
+    assert enc.dims_ok(8, 16) and not enc.dims_ok(4, 16) and not enc.dims_ok(8, 32)
+    assert enc.get_dims(17) == (3, 8, 16)
+
+
+# ------------------------------------------------------------------ Ligero commit (config 1 of BASELINE.json)
+def test_commit_ligero_ft255_2_10_bit_exact_root():
+    """lcpc-ligero-pc commit, Ft255, 2^10 coefficients: every LcCommit field and the LcRoot."""
+    field, length = P.FT255, 1 << 10
+    enc = P.LigeroEncoding(field, length)
+    oenc = O.Encoding.ligero(field, length)
+    assert (enc.n_per_row, enc.n_cols) == (oenc.n_per_row, oenc.n_cols) == (512, 1024)
+    assert enc.get_n_col_opens() == oenc.get_n_col_opens() == 309
+    assert enc.get_n_degree_tests() == oenc.get_n_degree_tests() == 1
+    for seed in (0, 1, 2):
+        x = O.random_elems(field, length, seed=seed)
+        c, oc = P.LcCommit.commit(x, enc), oenc.commit(x)
+        assert (c.n_rows, c.n_per_row, c.n_cols) == (2, 512, 1024)
+        assert c.get_root() == P.LcRoot(oc["root"])
+        assert (c.coeffs == oc["coeffs"]).all()
+        assert (c.comm == oc["comm"]).all()
+        assert (c.hashes == oc["hashes"]).all()
+
+
+@pytest.mark.parametrize("field,lgl", [(P.FT255, 14), (P.FT255, 16), (P.FT127, 15), (P.FT63, 13), (P.FT191, 12)])
+def test_commit_ligero_vs_oracle(field, lgl):
+    length = (1 << lgl) - 3  # ragged: last row zero-padded (lcpc-2d/src/lib.rs:640-645)
+    enc = P.LigeroEncoding(field, length)
+    oenc = O.Encoding.ligero(field, length)
+    x = O.random_elems(field, length, seed=lgl)
+    c, oc = P.LcCommit.commit(x, enc), oenc.commit(x)
+    assert c.get_root().root == oc["root"]
+    assert (c.comm == oc["comm"]).all() and (c.coeffs == oc["coeffs"]).all() and (c.hashes == oc["hashes"]).all()
+    # the one-shot host form fills caller-owned arrays identically
+    comm, coeffs, hashes = (np.empty_like(oc[k]) for k in ("comm", "coeffs", "hashes"))
+    rc = _cabi.lib().lcpc_b200_commit_to_host(enc._h, x.ctypes.data, length, comm.ctypes.data, coeffs.ctypes.data,
+                                             hashes.ctypes.data)
+    assert rc == 0 and (comm == oc["comm"]).all() and (coeffs == oc["coeffs"]).all() and (hashes == oc["hashes"]).all()
+
+
+# ------------------------------------------------------------------ Brakedown
+def _npz_case(z, name):
+    field = int(z[name + "_field"][0])
+    nlev = int(z[name + "_n_levels"][0])
+
+    def mats(tag):
+        out = []
+        for i in range(nlev):
+            m, n = (int(v) for v in z[f"{name}_{tag}{i}_shape"])
+            out.append(dict(m=m, n=n, ptrs=z[f"{name}_{tag}{i}_ptrs"], idxs=z[f"{name}_{tag}{i}_idxs"].astype(np.uint64),
+                            data=z[f"{name}_{tag}{i}_data"]))
+        return out
+    return field, mats("pre"), mats("post"), z[name + "_input_mont"], z[name + "_codeword_mont"]
+
+
+@pytest.mark.parametrize("name", ["ft63_n400", "ft127_n150", "ft255_n64"])
+def test_expander_encode_vs_reference_python_spec(name):
+    """Codewords produced by the reference's own doc/encoding.py (tests/golden/make_expander_vectors.py)."""
+    z = np.load(os.path.join(GOLD, "expander_vectors.npz"))
+    field, pre, post, x, want = _npz_case(z, name)
+    enc = P.SdigEncoding.from_matrices(field, pre, post)
+    assert enc.n_per_row == x.shape[0] and enc.n_cols == want.shape[0]
+    row = np.zeros((enc.n_cols, enc.L), np.uint64)
+    row[:x.shape[0]] = x
+    assert (enc.encode(row) == want).all()
+    # batch of identical and of different rows
+    rows = np.stack([row, np.zeros_like(row), row])
+    got = enc.encode(rows)
+    assert (got[0] == want).all() and not got[1].any() and (got[2] == want).all()
+
+
+@pytest.mark.parametrize("field,n,seed", [(P.FT63, 256, 0), (P.FT127, 1500, 1), (P.FT255, 4351, 2), (P.FT191, 333, 3)])
+def test_sdig_encode_vs_oracle(field, n, seed):
+    enc = P.SdigEncoding.new_from_dims(field, n, seed=seed)
+    oenc = O.Encoding.sdig_from_dims(field, n, seed=seed)
+    assert enc.n_cols == oenc.n_cols
+    n_rows = 5
+    rows = np.zeros((n_rows, enc.n_cols, enc.L), np.uint64)
+    rows[:, :n] = O.random_elems(field, n_rows * n, seed=seed + 50).reshape(n_rows, n, -1)
+    rows[:, n:] = 7  # junk beyond n_per_row must be ignored and overwritten (encode.rs:46-90)
+    got = enc.encode(rows)
+    for r in range(n_rows):
+        assert (got[r] == oenc.encode(rows[r])).all()
+
+
+@pytest.mark.parametrize("field,length,seed", [(P.FT127, 1 << 14, 0), (P.FT127, (1 << 16) - 11, 1), (P.FT255, 1 << 13, 0),
+                                               (P.FT63, 5000, 1)])
+def test_commit_brakedown_vs_oracle(field, length, seed):
+    enc = P.SdigEncoding(field, length, seed=seed)
+    oenc = O.Encoding.sdig(field, length, seed=seed)
+    assert (enc.n_per_row, enc.n_cols) == (oenc.n_per_row, oenc.n_cols)
+    assert enc.get_n_col_opens() == oenc.get_n_col_opens() == 6593
+    assert enc.get_n_degree_tests() == oenc.get_n_degree_tests()
+    x = O.random_elems(field, length, seed=seed + 7)
+    c, oc = P.LcCommit.commit(x, enc), oenc.commit(x)
+    assert c.get_root().root == oc["root"]
+    assert (c.comm == oc["comm"]).all() and (c.coeffs == oc["coeffs"]).all() and (c.hashes == oc["hashes"]).all()
+    np2 = 1 << (c.n_cols - 1).bit_length()
+    assert not c.hashes[c.n_cols:np2].any()
+
+
+def test_sdig_rejects_inconsistent_matrices():
+    pre, post, _ = P.host.generate_sdig_code(P.FT63, 300, 0)
+    bad = [dict(m) for m in post]
+    bad[0] = dict(bad[0], n=bad[0]["n"] + 1, ptrs=np.append(bad[0]["ptrs"], bad[0]["ptrs"][-1]))
+    with pytest.raises(P.LcpcError):
+        P.SdigEncoding.from_matrices(P.FT63, pre, bad)
+    bad2 = [dict(m) for m in pre]
+    idx = bad2[0]["idxs"].copy()
+    idx[0] = bad2[0]["m"]  # row index out of range
+    bad2[0] = dict(bad2[0], idxs=idx)
+    with pytest.raises(P.LcpcError):
+        P.SdigEncoding.from_matrices(P.FT63, bad2, post)
+
+
+# ------------------------------------------------------------------ prove pieces
+@pytest.mark.parametrize("field,n_rows,n_per_row", [(P.FT255, 2, 512), (P.FT255, 64, 1000), (P.FT127, 7, 100),
+                                                    (P.FT127, 72, 4099), (P.FT63, 300, 33), (P.FT191, 9, 65), (P.FT255, 1, 1)])
+def test_collapse_vs_oracle(field, n_rows, n_per_row):
+    coeffs = O.random_elems(field, n_rows * n_per_row, seed=n_rows)
+    tensor = O.random_elems(field, n_rows, seed=n_per_row)
+    got = P.collapse_columns(field, coeffs, tensor, n_rows, n_per_row)
+    assert (got == O.collapse(field, coeffs, tensor, n_rows, n_per_row)).all()
+    assert (got == O.collapse(field, coeffs, tensor, n_rows, n_per_row, serial=True)).all()  # tests.rs:151-165
+
+
+def test_collapse_edge_tensors():
+    field, n_rows, n_per_row = P.FT255, 16, 200
+    p = O.field_info(field)["modulus"]
+    coeffs = O.to_mont(field, [p - 1] * (n_rows * n_per_row))
+    tensor = O.to_mont(field, [p - 1] * n_rows)
+    assert (P.collapse_columns(field, coeffs, tensor, n_rows, n_per_row) == O.collapse(field, coeffs, tensor, n_rows, n_per_row)).all()
+    zero = np.zeros((n_rows, 4), np.uint64)
+    assert not P.collapse_columns(field, coeffs, zero, n_rows, n_per_row).any()
+
+
+def test_commit_collapse_and_open_columns():
+    field, length = P.FT255, 1 << 14
+    enc = P.LigeroEncoding(field, length)
+    oenc = O.Encoding.ligero(field, length)
+    x = O.random_elems(field, length, seed=3)
+    c, oc = P.LcCommit.commit(x, enc), oenc.commit(x)
+    tensor = O.random_elems(field, c.n_rows, seed=4)
+    assert (c.collapse(tensor) == O.collapse(field, oc["coeffs"], tensor, c.n_rows, c.n_per_row)).all()
+    with pytest.raises(P.LcpcError):
+        c.collapse(tensor[:-1])
+    rng = np.random.default_rng(0)
+    cols = [0, 1, c.n_cols - 1, c.n_cols // 2] + [int(v) for v in rng.integers(0, c.n_cols, 60)]
+    vals, paths = c.open_columns(cols)
+    root = c.get_root().root
+    for i, col in enumerate(cols):  # lcpc-2d/src/tests.rs:167-191
+        ov, op = O.open_column(field, oc["comm"], oc["hashes"], c.n_rows, c.n_cols, col)
+        assert (vals[i] == ov).all() and (paths[i] == op).all()
+        assert O.verify_column_path(field, vals[i], paths[i], col, root)
+    with pytest.raises(P.LcpcError) as e:
+        c.open_columns([c.n_cols])
+    assert e.value.code == _cabi.ERR_COLUMN
+
+
+def test_open_columns_non_power_of_two():
+    field, length = P.FT127, 1 << 13
+    enc = P.SdigEncoding(field, length, seed=2)
+    oenc = O.Encoding.sdig(field, length, seed=2)
+    x = O.random_elems(field, length, seed=9)
+    c, oc = P.LcCommit.commit(x, enc), oenc.commit(x)
+    cols = [0, c.n_cols - 1, c.n_cols - 2, 12345 % c.n_cols]
+    vals, paths = c.open_columns(cols)
+    for i, col in enumerate(cols):
+        ov, op = O.open_column(field, oc["comm"], oc["hashes"], c.n_rows, c.n_cols, col)
+        assert (vals[i] == ov).all() and (paths[i] == op).all()
+        assert O.verify_column_path(field, vals[i], paths[i], col, c.get_root().root)
+
+
+def test_commit_evaluation_property():
+    """lcpc-2d/src/tests.rs:193-236 (i): sum_i coeffs_i x^i == <inner, collapse(coeffs, outer)>."""
+    field = P.FT63
+    p = O.field_info(field)["modulus"]
+    enc = P.LigeroEncoding.new_from_dims(field, 32, 64)
+    x = O.random_elems(field, 128, seed=21)
+    c = P.LcCommit.commit(x, enc)
+    pt = 0x123456789abcdef % p
+    direct = sum(v * pow(pt, i, p) for i, v in enumerate(O.from_mont(field, x))) % p
+    inner = [pow(pt, i, p) for i in range(32)]
+    outer = O.to_mont(field, [pow(pt, 32 * r, p) for r in range(4)])
+    poly = O.from_mont(field, c.collapse(outer))
+    assert sum(a * b for a, b in zip(poly, inner)) % p == direct
+
+
+def test_rerun_and_launch_counter():
+    field, length = P.FT127, 1 << 12
+    enc = P.LigeroEncoding(field, length)
+    x0, x1 = O.random_elems(field, length, seed=0), O.random_elems(field, length, seed=1)
+    c = P.LcCommit.commit(x0, enc)
+    r0 = c.get_root()
+    before = enc.ctx.launch_count
+    c.rerun(x1)
+    assert enc.ctx.launch_count > before
+    r1 = c.get_root()
+    assert r0 != r1 and r1.root == O.Encoding.ligero(field, length).commit(x1)["root"]
+    c.rerun(x0)
+    assert c.get_root() == r0
