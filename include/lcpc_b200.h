@@ -156,6 +156,15 @@ int lcpc_b200_hash_columns_dev(lcpc_b200_ctx *ctx, int field, const uint64_t *d_
                                size_t n_cols, size_t row_stride, uint8_t *d_leaves);
 /* merkle_tree (lcpc-2d/src/lib.rs:747-760) in place on device: d_hashes[0..np2) given */
 int lcpc_b200_merkle_tree_dev(lcpc_b200_ctx *ctx, uint8_t *d_hashes, size_t np2);
+/* n_layers Merkle layers over n_leaves nodes laid out [nodes | layer 1 | .. | layer n_layers]; n_leaves a
+ * multiple of 2^n_layers (several equal aligned subtrees side by side are reduced together) */
+int lcpc_b200_merkle_layers_dev(lcpc_b200_ctx *ctx, uint8_t *d_hashes, size_t n_leaves, unsigned n_layers);
+/* multi-GPU transpose step (no reference analogue; the reference is one process): split the device
+ * row-block d_rows[n_rows][n_cols] into n_blocks column-block tiles; tile h = columns
+ * [starts[h], starts[h+1]) stored as [n_rows][width_h] at element offset n_rows*starts[h] of d_out,
+ * i.e. the send buffer of one all-to-all.  d_starts: n_blocks+1 u64 in DEVICE memory. */
+int lcpc_b200_pack_column_blocks_dev(lcpc_b200_ctx *ctx, int field, const uint64_t *d_rows, size_t n_rows,
+                                     size_t n_cols, size_t n_blocks, const uint64_t *d_starts, uint64_t *d_out);
 int lcpc_b200_collapse_dev(lcpc_b200_ctx *ctx, int field, const uint64_t *d_coeffs, size_t row_stride,
                            const uint64_t *d_tensor, uint64_t *d_poly, size_t n_rows, size_t n_per_row);
 /* element-wise field arithmetic on host arrays (parity tests of the device arithmetic):

@@ -72,6 +72,8 @@ SIGNATURES = {
     "lcpc_b200_merkleize": (_i, [_vp, _i, _vp, _sz, _sz, _vp]),
     "lcpc_b200_hash_columns_dev": (_i, [_vp, _i, _vp, _sz, _sz, _sz, _vp]),
     "lcpc_b200_merkle_tree_dev": (_i, [_vp, _vp, _sz]),
+    "lcpc_b200_merkle_layers_dev": (_i, [_vp, _vp, _sz, C.c_uint]),
+    "lcpc_b200_pack_column_blocks_dev": (_i, [_vp, _i, _vp, _sz, _sz, _sz, _vp, _vp]),
     "lcpc_b200_collapse_dev": (_i, [_vp, _i, _vp, _sz, _vp, _vp, _sz, _sz]),
     "lcpc_b200_field_op": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz]),
     # host-side setup (include/lcpc_b200_host.h)

@@ -680,6 +680,33 @@ int lcpc_b200_merkle_tree_dev(lcpc_b200_ctx *ctx, uint8_t *d_hashes, size_t np2)
   return LCPC_B200_OK;
 }
 
+int lcpc_b200_merkle_layers_dev(lcpc_b200_ctx *ctx, uint8_t *d_hashes, size_t n_leaves, unsigned n_layers) {
+  if (!ctx || !d_hashes) return LCPC_B200_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (n_layers >= 48 || (n_leaves & (((size_t)1 << n_layers) - 1)))
+    return fail(ctx, LCPC_B200_ERR_BAD_ARG, "merkle_layers: %zu nodes are not a multiple of 2^%u", n_leaves, n_layers);
+  if (int rc = bind_device(ctx)) return rc;
+  int nl = 0;
+  cudaError_t ce = launch_merkle_layers(d_hashes, n_leaves, n_layers, ctx->stream, &nl);
+  ctx->launches += nl;
+  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "merkle_layers");
+  return LCPC_B200_OK;
+}
+
+int lcpc_b200_pack_column_blocks_dev(lcpc_b200_ctx *ctx, int field, const uint64_t *d_rows, size_t n_rows, size_t n_cols,
+                                     size_t n_blocks, const uint64_t *d_starts, uint64_t *d_out) {
+  if (!ctx || !d_rows || !d_starts || !d_out) return LCPC_B200_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (field_limbs32(field) < 0 || n_blocks == 0 || n_blocks > 64)
+    return fail(ctx, LCPC_B200_ERR_BAD_ARG, "pack: bad field or block count");
+  if (int rc = bind_device(ctx)) return rc;
+  cudaError_t ce = launch_pack_column_blocks(field, (const uint32_t *)d_rows, n_rows, n_cols, (unsigned)n_blocks, d_starts,
+                                             (uint32_t *)d_out, ctx->stream);
+  ctx->launches += 1;
+  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "pack_column_blocks");
+  return LCPC_B200_OK;
+}
+
 int lcpc_b200_merkleize(lcpc_b200_ctx *ctx, int field, const uint64_t *comm, size_t n_rows, size_t n_cols,
                         uint8_t *hashes) {
   if (!ctx || !comm || !hashes || n_cols == 0) return LCPC_B200_ERR_BAD_ARG;

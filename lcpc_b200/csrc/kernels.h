@@ -37,6 +37,17 @@ cudaError_t launch_hash_columns(int field, const uint32_t *comm, size_t n_rows, 
 // hashes = [leaves(np2) | layer 1 | ... | root]; leaves given, upper layers computed
 cudaError_t launch_merkle_tree(uint8_t *hashes, size_t np2, cudaStream_t stream, int *n_launches);
 
+// n_layers Merkle layers over n_leaves nodes (a forest of equal aligned subtrees side by side)
+cudaError_t launch_merkle_layers(uint8_t *hashes, size_t n_leaves, unsigned n_layers, cudaStream_t stream,
+                                 int *n_launches);
+
+// ---- multi-GPU transpose step: split a row-block [n_rows][n_cols] into per-destination column-block
+// tiles, tile h = columns [starts[h], starts[h+1]) stored contiguously as [n_rows][width_h] at element
+// offset n_rows * starts[h] of dst (the send buffer of the all-to-all) ----
+cudaError_t launch_pack_column_blocks(int field, const uint32_t *src, size_t n_rows, size_t n_cols,
+                                      unsigned n_blocks, const uint64_t *d_starts, uint32_t *dst,
+                                      cudaStream_t stream);
+
 // ---- collapse_columns (lcpc-2d/src/lib.rs:1095-1123): poly[c] = sum_r tensor[r] * coeffs[r][c] ----
 size_t collapse_scratch_bytes(int field, size_t n_rows, size_t n_per_row);
 cudaError_t launch_collapse(int field, const uint32_t *coeffs, size_t row_stride, const uint32_t *tensor,

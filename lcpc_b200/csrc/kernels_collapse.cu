@@ -113,6 +113,44 @@ cudaError_t launch_gather_columns(int field, const uint32_t *comm, size_t n_rows
   return cudaGetLastError();
 }
 
+// pack_column_blocks: 16-byte (or 8-byte) granules, one thread each; reads are fully coalesced, writes are
+// coalesced within a tile row
+template <typename V>
+__global__ void pack_column_blocks_kernel(const V *__restrict__ src, size_t n_rows, size_t n_cols, unsigned per_elem,
+                                          unsigned n_blocks, const uint64_t *__restrict__ starts, V *__restrict__ dst) {
+  __shared__ uint64_t s_starts[65];
+  for (unsigned i = threadIdx.x; i <= n_blocks; i += blockDim.x) s_starts[i] = starts[i];
+  __syncthreads();
+  const size_t row_granules = n_cols * per_elem, total = n_rows * row_granules;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = idx / row_granules, g = idx % row_granules;
+    const size_t c = g / per_elem, part = g % per_elem;
+    unsigned h = 0;
+    while (h + 1 < n_blocks && c >= s_starts[h + 1]) h++;
+    const size_t start = s_starts[h], width = s_starts[h + 1] - start;
+    dst[(n_rows * start + r * width + (c - start)) * per_elem + part] = src[idx];
+  }
+}
+
+cudaError_t launch_pack_column_blocks(int field, const uint32_t *src, size_t n_rows, size_t n_cols, unsigned n_blocks,
+                                      const uint64_t *d_starts, uint32_t *dst, cudaStream_t stream) {
+  int nl = field_limbs32(field);
+  if (nl < 0 || n_blocks == 0 || n_blocks > 64) return cudaErrorInvalidValue;
+  if (n_rows * n_cols == 0) return cudaSuccess;
+  if (nl % 4 == 0) {
+    size_t total = n_rows * n_cols * (nl / 4);
+    unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 32);
+    pack_column_blocks_kernel<uint4><<<grid, 256, 0, stream>>>((const uint4 *)src, n_rows, n_cols, nl / 4, n_blocks,
+                                                               d_starts, (uint4 *)dst);
+  } else {
+    size_t total = n_rows * n_cols * (nl / 2);
+    unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 32);
+    pack_column_blocks_kernel<uint2><<<grid, 256, 0, stream>>>((const uint2 *)src, n_rows, n_cols, nl / 2, n_blocks,
+                                                               d_starts, (uint2 *)dst);
+  }
+  return cudaGetLastError();
+}
+
 // open_column's path walk (lcpc-2d/src/lib.rs:811-821): on layer l the sibling of node (col >> l) is
 // (col >> l) ^ 1; layer l starts at offset sum_{q<l} np2 >> q of the flat hashes array.
 __global__ void gather_paths_kernel(const uint8_t *__restrict__ hashes, size_t np2, const uint64_t *__restrict__ cols,

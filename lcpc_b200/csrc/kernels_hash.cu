@@ -287,29 +287,39 @@ merkle_subtree_kernel(uint32_t *hashes, size_t layer_off, size_t layer_len, unsi
   }
 }
 
-cudaError_t launch_merkle_tree(uint8_t *hashes, size_t np2, cudaStream_t stream, int *n_launches) {
+// n_layers layers above `n_leaves` nodes laid out [nodes | layer 1 | ... | layer n_layers]; n_leaves must be
+// a multiple of 2^n_layers (a forest of equal subtrees side by side is fine)
+cudaError_t launch_merkle_layers(uint8_t *hashes, size_t n_leaves, unsigned n_layers, cudaStream_t stream,
+                                 int *n_launches) {
   if (n_launches) *n_launches = 0;
+  if (n_layers && (n_leaves & (((size_t)1 << n_layers) - 1))) return cudaErrorInvalidValue;
   uint32_t *h = (uint32_t *)hashes;
-  size_t off = 0, len = np2;
-  while (len > 1) {
-    unsigned log_len = 0;
-    while (((size_t)1 << log_len) < len) log_len++;
+  size_t off = 0, len = n_leaves;
+  unsigned left = n_layers;
+  while (left > 0) {
     if (len >= 2 * HASH_THREADS * 148u) {
       // wide layer: one thread per node keeps every SM busy
       size_t n_out = len >> 1;
       merkle_layer_kernel<<<(unsigned)((n_out + HASH_THREADS - 1) / HASH_THREADS), HASH_THREADS, 0, stream>>>(
           h + off * 8, h + (off + len) * 8, n_out);
-      off += len, len = n_out;
+      off += len, len = n_out, left -= 1;
     } else {
-      unsigned nl = log_len < (unsigned)MERKLE_LOG_SUB ? log_len : (unsigned)MERKLE_LOG_SUB;
+      unsigned nl = left < (unsigned)MERKLE_LOG_SUB ? left : (unsigned)MERKLE_LOG_SUB;
       merkle_subtree_kernel<<<(unsigned)(len >> nl), 128, 0, stream>>>(h, off, len, nl);
       for (unsigned l = 0; l < nl; l++) off += len, len >>= 1;
+      left -= nl;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (n_launches) ++*n_launches;
   }
   return cudaSuccess;
+}
+
+cudaError_t launch_merkle_tree(uint8_t *hashes, size_t np2, cudaStream_t stream, int *n_launches) {
+  unsigned log_len = 0;
+  while (((size_t)1 << log_len) < np2) log_len++;
+  return launch_merkle_layers(hashes, np2, log_len, stream, n_launches);
 }
 
 }  // namespace lcpc

@@ -1,0 +1,296 @@
+"""Multi-GPU commit: row-block encode -> one all-to-all -> column-block hashing (one process per GPU).
+
+The reference is a single process (rayon threads); its two data-parallel loops are row-parallel
+(`enc.encode` per row, lcpc-2d/src/lib.rs:648-653) and column-parallel (`hash_columns`, :706-745).
+Between them sits a transpose, which across GPUs is exactly one all-to-all:
+
+  rank g   : encodes rows [row_lo_g, row_hi_g)            -> comm_rows[rows_g][n_cols]      (device)
+           : packs per-destination tiles                   -> send[h] = comm_rows[:, cols_h] (device)
+  all ranks: torch.distributed.all_to_all_single over NCCL/NVLink (the only bulk collective)
+  rank h   : holds comm[:, cols_h] as [n_rows][width_h]    -> leaf digests of its columns
+           : reduces its aligned Merkle subtrees on device -> subtree roots (32 B each)
+  all ranks: all_gather of the subtree roots (<= 2 KiB; commitment assembly, not bulk data), then the
+             top log2(S) layers on every rank -> every rank holds the same LcRoot.
+
+Column blocks are unions of ALIGNED Merkle subtrees (np2 / S leaves each, S = 8 * world), dealt
+contiguously over the subtrees that contain real columns, so that non-power-of-two `n_cols`
+(Brakedown) still balances: the all-padding subtrees have a constant root that is computed once.
+
+`torch.distributed` is plumbing only: the process group, the NCCL call, and (for tests on CPU) the
+gloo backend for the planning logic.  All field / hash work goes through the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _cabi
+from .host import FIELD_LIMBS, LcRoot, _check
+
+
+@dataclass
+class Plan:
+    """Static partition of one commit over `world` ranks."""
+    world: int
+    n_rows: int
+    n_per_row: int
+    n_cols: int
+    np2: int
+    sub_leaves: int          # leaves per aligned subtree (T)
+    n_sub: int               # S = np2 / T
+    n_real_sub: int          # subtrees containing at least one real column
+    row_lo: list             # world + 1 row boundaries
+    sub_lo: list             # world + 1 subtree boundaries (over the real subtrees)
+    col_lo: list             # world + 1 column boundaries
+
+    def rows(self, r):
+        return self.row_lo[r], self.row_lo[r + 1]
+
+    def cols(self, r):
+        return self.col_lo[r], self.col_lo[r + 1]
+
+    def subs(self, r):
+        return self.sub_lo[r], self.sub_lo[r + 1]
+
+
+def make_plan(n_rows: int, n_per_row: int, n_cols: int, world: int, sub_per_rank: int = 8) -> Plan:
+    np2 = 1 << (n_cols - 1).bit_length() if n_cols > 1 else 1
+    n_sub = min(np2, 1 << ((world * sub_per_rank) - 1).bit_length())
+    T = np2 // n_sub
+    n_real = (n_cols + T - 1) // T
+    row_lo = [(g * n_rows) // world for g in range(world + 1)]
+    sub_lo = [(g * n_real) // world for g in range(world + 1)]
+    col_lo = [min(s * T, n_cols) for s in sub_lo]
+    col_lo[-1] = n_cols
+    return Plan(world, n_rows, n_per_row, n_cols, np2, T, n_sub, n_real, row_lo, sub_lo, col_lo)
+
+
+def _sz(v):
+    return C.c_size_t(int(v))
+
+
+class CudaOps:
+    """Compute steps of the distributed commit on this rank's GPU, through the C ABI."""
+
+    def __init__(self, enc):
+        import torch
+        self.torch, self.enc, self.ctx = torch, enc, enc.ctx
+        self.field, self.L = enc.field, enc.L
+        self.device = torch.device("cuda", self.ctx.device)
+        self.stream = torch.cuda.ExternalStream(self.ctx.stream, device=self.device)
+
+    def on_stream(self):
+        return self.torch.cuda.stream(self.stream)
+
+    def synchronize(self):
+        self.ctx.synchronize()
+
+    def encode_rows(self, coeffs, comm_rows, n_rows, n_per_row):
+        _check(_cabi.lib().lcpc_b200_encode_rows_dev(self.enc._h, C.c_void_p(coeffs.data_ptr()), _sz(n_per_row),
+                                                     _sz(n_per_row), C.c_void_p(comm_rows.data_ptr()), _sz(n_rows)), self.ctx)
+
+    def pack(self, comm_rows, n_rows, n_cols, n_blocks, starts, send):
+        _check(_cabi.lib().lcpc_b200_pack_column_blocks_dev(self.ctx._h, self.field, C.c_void_p(comm_rows.data_ptr()),
+                                                            _sz(n_rows), _sz(n_cols), _sz(n_blocks),
+                                                            C.c_void_p(starts.data_ptr()), C.c_void_p(send.data_ptr())), self.ctx)
+
+    def hash_columns(self, cols, n_rows, n_cols, leaves):
+        _check(_cabi.lib().lcpc_b200_hash_columns_dev(self.ctx._h, self.field, C.c_void_p(cols.data_ptr()), _sz(n_rows),
+                                                      _sz(n_cols), _sz(n_cols), C.c_void_p(leaves.data_ptr())), self.ctx)
+
+    def merkle_layers(self, nodes, n_leaves, n_layers):
+        _check(_cabi.lib().lcpc_b200_merkle_layers_dev(self.ctx._h, C.c_void_p(nodes.data_ptr()), _sz(n_leaves), n_layers), self.ctx)
+
+
+class DistributedCommit:
+    """Device-resident, column-sharded LcCommit over a torch.distributed process group.
+
+    `ops` supplies the per-rank compute steps (default: CudaOps, the C ABI).  The orchestration --
+    partition, split sizes, the all-to-all, root assembly -- is backend-independent, which is how the
+    world_size-2 gloo tests exercise it on CPU with a checker backend.
+    """
+
+    def __init__(self, enc, n_coeffs: int, group=None, ops=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.enc, self.group = enc, group
+        self.ops = ops if ops is not None else CudaOps(enc)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.field, self.L = enc.field, enc.L
+        n_rows, n_per_row, n_cols = enc.get_dims(n_coeffs)
+        self.n_coeffs = n_coeffs
+        self.plan = p = make_plan(n_rows, n_per_row, n_cols, self.world)
+        dev = self.ops.device
+        L = self.L
+        r0, r1 = p.rows(self.rank)
+        c0, c1 = p.cols(self.rank)
+        s0, s1 = p.subs(self.rank)
+        self.my_rows, self.my_cols, self.my_subs = r1 - r0, c1 - c0, s1 - s0
+        i64 = torch.int64
+        self.d_coeffs = torch.zeros(max(1, self.my_rows * n_per_row * L), dtype=i64, device=dev)
+        self.d_comm_rows = torch.empty(max(1, self.my_rows * n_cols * L), dtype=i64, device=dev)
+        self.d_send = torch.empty(max(1, self.my_rows * n_cols * L), dtype=i64, device=dev)
+        self.d_recv = torch.empty(max(1, n_rows * self.my_cols * L), dtype=i64, device=dev)
+        self.in_splits = [self.my_rows * (p.col_lo[h + 1] - p.col_lo[h]) * L for h in range(self.world)]
+        self.out_splits = [(p.row_lo[g + 1] - p.row_lo[g]) * self.my_cols * L for g in range(self.world)]
+        self.d_starts = torch.tensor(p.col_lo, dtype=i64, device=dev)
+        # local forest: my_subs aligned subtrees side by side, [leaves | layer 1 | ... | roots]
+        T = p.sub_leaves
+        self.sub_layers = T.bit_length() - 1
+        n_leaves = self.my_subs * T
+        self.forest_nodes = sum(n_leaves >> l for l in range(self.sub_layers + 1))
+        self.d_forest = torch.zeros(max(1, self.forest_nodes) * 32, dtype=torch.uint8, device=dev)
+        self.roots_off = sum(n_leaves >> l for l in range(self.sub_layers)) * 32
+        self.max_subs = max(p.sub_lo[g + 1] - p.sub_lo[g] for g in range(self.world))
+        self.d_my_roots = torch.zeros(max(1, self.max_subs) * 32, dtype=torch.uint8, device=dev)
+        self.d_all_roots = torch.zeros(self.world * max(1, self.max_subs) * 32, dtype=torch.uint8, device=dev)
+        self.d_top = torch.zeros((2 * p.n_sub - 1) * 32, dtype=torch.uint8, device=dev)
+        self.zero_root = self._zero_subtree_root()
+        if p.n_real_sub < p.n_sub:
+            pad = torch.from_numpy(np.tile(np.frombuffer(self.zero_root, np.uint8), p.n_sub - p.n_real_sub).copy()).to(dev)
+            with self.ops.on_stream():
+                self.d_top[p.n_real_sub * 32:p.n_sub * 32] = pad
+        self.ops.synchronize()
+
+    # root of an all-padding subtree: T zero leaves hashed up (lcpc-2d/src/lib.rs:665,696 leave them zero)
+    def _zero_subtree_root(self) -> bytes:
+        torch = self.torch
+        dev = self.ops.device
+        buf = torch.zeros(3 * 32, dtype=torch.uint8, device=dev)
+        with self.ops.on_stream():
+            for _ in range(self.sub_layers):
+                self.ops.merkle_layers(buf, 2, 1)
+                buf[:32] = buf[64:96]
+                buf[32:64] = buf[64:96]
+            out = buf[:32].cpu()
+        self.ops.synchronize()
+        return out.numpy().tobytes()
+
+    def load_rows_from_host(self, host_rows):
+        """H2D of this rank's row block (a pinned int64 torch tensor or numpy array of limbs)."""
+        torch = self.torch
+        t = host_rows if isinstance(host_rows, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(host_rows).view(np.int64).reshape(-1))
+        with self.ops.on_stream():
+            self.d_coeffs[:t.numel()].copy_(t.reshape(-1), non_blocking=True)
+            if t.numel() < self.d_coeffs.numel():
+                self.d_coeffs[t.numel():].zero_()
+
+    def run(self):
+        """Enqueue one distributed commit on the engine stream (no host synchronisation)."""
+        dist, p, ops = self.dist, self.plan, self.ops
+        with ops.on_stream():
+            if self.my_rows:
+                ops.encode_rows(self.d_coeffs, self.d_comm_rows, self.my_rows, p.n_per_row)
+                ops.pack(self.d_comm_rows, self.my_rows, p.n_cols, self.world, self.d_starts, self.d_send)
+            n_send, n_recv = sum(self.in_splits), sum(self.out_splits)
+            dist.all_to_all_single(self.d_recv[:n_recv], self.d_send[:n_send], self.out_splits, self.in_splits,
+                                   group=self.group)
+            if self.my_cols:
+                ops.hash_columns(self.d_recv, p.n_rows, self.my_cols, self.d_forest)
+                if self.sub_layers:
+                    ops.merkle_layers(self.d_forest, self.my_subs * p.sub_leaves, self.sub_layers)
+                self.d_my_roots[:self.my_subs * 32] = self.d_forest[self.roots_off:self.roots_off + self.my_subs * 32]
+            dist.all_gather_into_tensor(self.d_all_roots, self.d_my_roots, group=self.group)
+            stride = max(1, self.max_subs) * 32
+            for g in range(self.world):
+                s0, s1 = p.subs(g)
+                if s1 > s0:
+                    self.d_top[s0 * 32:s1 * 32] = self.d_all_roots[g * stride:g * stride + (s1 - s0) * 32]
+            if p.n_sub > 1:
+                ops.merkle_layers(self.d_top, p.n_sub, p.n_sub.bit_length() - 1)
+
+    def get_root(self) -> LcRoot:
+        with self.ops.on_stream():
+            root = self.d_top[-32:].cpu()
+        self.ops.synchronize()
+        return LcRoot(root.numpy().tobytes())
+
+    # ---- inspection helpers (tests) ----
+    def local_columns(self) -> np.ndarray:
+        """This rank's column block of comm as (n_rows, my_cols, L)."""
+        self.ops.synchronize()
+        n = self.plan.n_rows * self.my_cols * self.L
+        return self.d_recv[:n].cpu().numpy().view(np.uint64).reshape(self.plan.n_rows, self.my_cols, self.L)
+
+    def local_leaves(self) -> np.ndarray:
+        self.ops.synchronize()
+        return self.d_forest[:self.my_cols * 32].cpu().numpy().reshape(self.my_cols, 32)
+
+
+def bench_distributed(args, ctx, enc, field, n, synthetic_coeffs):
+    """The N>1 arm of bench.py: one commit of `n` coefficients sharded over all ranks."""
+    import time
+
+    import torch
+    import torch.distributed as dist
+
+    import bench as B  # ClockSampler
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    L = FIELD_LIMBS[field]
+    dc = DistributedCommit(enc, n)
+    p = dc.plan
+    r0, r1 = p.rows(rank)
+    # this rank's rows of the same seeded polynomial every world size would commit
+    lo, hi = r0 * p.n_per_row, min(r1 * p.n_per_row, n)
+    x = synthetic_coeffs(field, n, seed=0)[lo:hi] if world <= 2 or n <= (1 << 22) else _slice_coeffs(synthetic_coeffs, field, n, lo, hi)
+    host = torch.from_numpy(np.ascontiguousarray(x).view(np.int64).reshape(-1)).pin_memory()
+    dc.load_rows_from_host(host)
+    ctx.synchronize()
+    for _ in range(args.warmup):
+        dc.run()
+    ctx.synchronize()
+    root0 = dc.get_root()
+    sampler = B.ClockSampler(torch.cuda.current_device())
+    launches0 = ctx.launch_count
+    dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(dc.ops.stream)
+    for _ in range(args.steps):
+        dc.run()
+    ev1.record(dc.ops.stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = torch.tensor([ctx.launch_count - launches0], device="cuda")
+    dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+    assert dc.get_root() == root0
+    # end to end: pinned host rows -> H2D -> commit -> D2H root, wall clock bracketed by barriers
+    for _ in range(2):
+        dc.load_rows_from_host(host)
+        dc.run()
+        dc.get_root()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e2e_steps = max(3, args.steps // 2)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        dc.load_rows_from_host(host)
+        dc.run()
+        r = dc.get_root()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e2e = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device="cuda")
+    dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop()
+    assert r == root0
+    ms_per_step = float(ms.item()) / args.steps
+    e2e_s = float(e2e.item())
+    return dict(value=n / (ms_per_step * 1e-3), ms_per_step=ms_per_step, gpu_launches=int(launches.item()), clocks=clocks,
+                root=root0.root.hex(), dominant=None,
+                e2e={"value": n / e2e_s, "unit": "field-elts/s", "h2d_bytes_per_step": int(n * 8 * L),
+                     "d2h_bytes_per_step": 32 * world, "ms_per_step": e2e_s * 1e3,
+                     "mode": "row blocks from pinned host memory on every rank; every rank reads back the LcRoot"})
+
+
+def _slice_coeffs(synthetic_coeffs, field, n, lo, hi):
+    # synthetic_coeffs is a pure function of (field, n, seed): generate once, slice; kept separate so a
+    # future streaming generator can avoid materialising all n elements on every rank
+    return synthetic_coeffs(field, n, seed=0)[lo:hi]
