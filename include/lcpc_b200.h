@@ -62,6 +62,14 @@ int lcpc_b200_ctx_synchronize(lcpc_b200_ctx *ctx);
 /* kernels launched by this context since creation (bench.py's `gpu_launches`) */
 uint64_t lcpc_b200_ctx_launch_count(const lcpc_b200_ctx *ctx);
 
+/* page-locked host buffers (no reference analogue: the reference never leaves host memory).  commit()
+ * accepts any host pointer; from a buffer obtained here (or registered in place, e.g. a Rust Vec<F>'s
+ * allocation) the coefficient rows cross PCIe at full rate while earlier rows are already being encoded. */
+int lcpc_b200_host_alloc(size_t bytes, void **out);
+void lcpc_b200_host_free(void *p);
+int lcpc_b200_host_register(void *p, size_t bytes);
+int lcpc_b200_host_unregister(void *p);
+
 /* ---- encodings (impl LcEncoding, lcpc-2d/src/lib.rs:74-104) ----
  * Dimension choosing (`_get_dims`, lcpc-ligero-pc/src/lib.rs:70-112; `_new_from_np1`,
  * lcpc-brakedown-pc/src/lib.rs:69-99) and Brakedown code generation (matgen.rs) stay on the host
@@ -103,6 +111,12 @@ int lcpc_b200_encode_dev(lcpc_b200_enc *enc, uint64_t *d_rows, size_t n_rows, si
 /* out of place on DEVICE memory: source rows are src_stride elements apart with `valid` leading
  * elements each; destination rows are n_cols apart (the row-block step of the multi-GPU commit) */
 int lcpc_b200_encode_rows_dev(lcpc_b200_enc *enc, const uint64_t *d_src, size_t src_stride, size_t valid,
+                              uint64_t *d_dst, size_t n_rows);
+
+/* the same fed from HOST memory: `len` coefficients (the rank's row block; the last row may be short and is
+ * zero-padded) are copied into d_coeffs[n_rows][n_per_row] in row-chunks on a copy stream while the engine
+ * stream encodes the chunks that have landed into d_dst[n_rows][n_cols].  Enqueues only. */
+int lcpc_b200_encode_rows_h2d(lcpc_b200_enc *enc, const uint64_t *rows, size_t len, uint64_t *d_coeffs,
                               uint64_t *d_dst, size_t n_rows);
 
 /* ---- commit (LcCommit::commit, lcpc-2d/src/lib.rs:299-301 -> :622-671) ----

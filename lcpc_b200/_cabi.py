@@ -45,6 +45,10 @@ SIGNATURES = {
     "lcpc_b200_ctx_stream": (_vp, [_vp]),
     "lcpc_b200_ctx_synchronize": (_i, [_vp]),
     "lcpc_b200_ctx_launch_count": (_u64, [_vp]),
+    "lcpc_b200_host_alloc": (_i, [_sz, _pvp]),
+    "lcpc_b200_host_free": (None, [_vp]),
+    "lcpc_b200_host_register": (_i, [_vp, _sz]),
+    "lcpc_b200_host_unregister": (_i, [_vp]),
     "lcpc_b200_ligero_new": (_i, [_vp, _i, _sz, _sz, _pvp]),
     "lcpc_b200_sdig_new": (_i, [_vp, _i, _sz, C.POINTER(Csc), C.POINTER(Csc), _pvp]),
     "lcpc_b200_enc_free": (None, [_vp]),
@@ -64,6 +68,7 @@ SIGNATURES = {
     "lcpc_b200_commit_download": (_i, [_vp, _vp, _vp, _vp]),
     "lcpc_b200_commit_phase_times": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "lcpc_b200_encode_rows_dev": (_i, [_vp, _vp, _sz, _sz, _vp, _sz]),
+    "lcpc_b200_encode_rows_h2d": (_i, [_vp, _vp, _sz, _vp, _vp, _sz]),
     "lcpc_b200_commit_device_ptrs": (_i, [_vp, _pvp, _pvp, _pvp]),
     "lcpc_b200_commit_to_host": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "lcpc_b200_commit_collapse": (_i, [_vp, _vp, _vp]),

@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -21,6 +22,12 @@ using namespace lcpc;
 struct lcpc_b200_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // host->device staging stream + events: commit() from host memory copies the coefficient rows in
+  // row-chunks on this stream while the engine stream encodes the chunks that have already landed
+  cudaStream_t copy_stream = nullptr;
+  static constexpr int MAX_CHUNKS = 16;
+  cudaEvent_t chunk_ev[MAX_CHUNKS] = {};
+  cudaEvent_t begin_ev = nullptr;
   std::mutex mu;
   std::string err;
   uint64_t launches = 0;
@@ -171,9 +178,13 @@ int lcpc_b200_ctx_create(int device, lcpc_b200_ctx **out) {
   lcpc_b200_ctx *ctx = new (std::nothrow) lcpc_b200_ctx;
   if (!ctx) return LCPC_B200_ERR_OOM;
   ctx->device = device;
-  if (cudaSetDevice(device) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
-    delete ctx;
+  bool ok = cudaSetDevice(device) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->begin_ev, cudaEventDisableTiming) == cudaSuccess;
+  for (auto &e : ctx->chunk_ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
+    lcpc_b200_ctx_destroy(ctx);
     return LCPC_B200_ERR_CUDA;
   }
   *out = ctx;
@@ -187,6 +198,13 @@ void lcpc_b200_ctx_destroy(lcpc_b200_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->stream);
   }
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+  }
+  for (auto &e : ctx->chunk_ev)
+    if (e) cudaEventDestroy(e);
+  if (ctx->begin_ev) cudaEventDestroy(ctx->begin_ev);
   if (ctx->scratch) cudaFree(ctx->scratch);
   delete ctx;
 }
@@ -202,6 +220,27 @@ int lcpc_b200_ctx_synchronize(lcpc_b200_ctx *ctx) {
   if (int rc = bind_device(ctx)) return rc;
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   return LCPC_B200_OK;
+}
+
+// page-locked host memory: a caller that keeps its coefficient vector in such a buffer gets full-rate,
+// truly asynchronous PCIe copies in commit() (pageable memory is staged by the driver at about half rate)
+int lcpc_b200_host_alloc(size_t bytes, void **out) {
+  if (!out) return LCPC_B200_ERR_BAD_ARG;
+  *out = nullptr;
+  cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+  if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? LCPC_B200_ERR_OOM : LCPC_B200_ERR_CUDA;
+  return LCPC_B200_OK;
+}
+void lcpc_b200_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+int lcpc_b200_host_register(void *p, size_t bytes) {
+  if (!p || !bytes) return LCPC_B200_ERR_BAD_ARG;
+  return cudaHostRegister(p, bytes, cudaHostRegisterPortable) == cudaSuccess ? LCPC_B200_OK : LCPC_B200_ERR_CUDA;
+}
+int lcpc_b200_host_unregister(void *p) {
+  if (!p) return LCPC_B200_ERR_BAD_ARG;
+  return cudaHostUnregister(p) == cudaSuccess ? LCPC_B200_OK : LCPC_B200_ERR_CUDA;
 }
 
 // ---------------------------------------------------------------------------------------- encodings
@@ -320,6 +359,52 @@ static size_t enc_scratch_bytes(const lcpc_b200_enc *enc, size_t n_rows) {
   return enc->kind == LCPC_B200_ENC_SDIG ? expander_scratch_bytes(enc->code, n_rows) : 0;
 }
 
+// pad + copy (lcpc-2d/src/lib.rs:636-645) overlapped with the per-row encode (:648-653): rows are
+// independent, so the `len` coefficients at host address `src` cross PCIe in row-chunks on the copy
+// stream (into d_coeffs, zero-padded to n_rows * n_per_row) while the engine stream encodes the chunks
+// that have landed into d_comm.  `first_ev` (optional) is recorded on the engine stream when the first
+// chunk is in.
+static int encode_rows_from_host(lcpc_b200_enc *enc, const void *src, size_t len, uint32_t *d_coeffs, uint32_t *d_comm,
+                                 size_t n_rows, void *enc_scratch, cudaEvent_t first_ev) {
+  lcpc_b200_ctx *ctx = enc->ctx;
+  cudaStream_t st = ctx->stream;
+  const size_t B = field_bytes(enc->field), N = B / 4;
+  const size_t n_per_row = enc->n_per_row, padded = n_rows * n_per_row;
+  const size_t row_bytes = n_per_row * B;
+  size_t n_chunks = std::min<size_t>(enc->kind == LCPC_B200_ENC_LIGERO ? 16 : 4, n_rows);
+  while (n_chunks > 1 && (n_rows / n_chunks) * row_bytes < ((size_t)4 << 20)) n_chunks--;
+  CU(ctx, cudaEventRecord(ctx->begin_ev, st));  // earlier readers of d_coeffs on the engine stream
+  CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->begin_ev, 0));
+  for (size_t k = 0; k < n_chunks; k++) {
+    const size_t r0 = k * n_rows / n_chunks, r1 = (k + 1) * n_rows / n_chunks;
+    const size_t e0 = r0 * n_per_row, e1 = std::min(r1 * n_per_row, len);
+    if (e1 > e0)
+      CU(ctx, cudaMemcpyAsync((uint8_t *)d_coeffs + e0 * B, (const uint8_t *)src + e0 * B, (e1 - e0) * B,
+                              cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (k + 1 == n_chunks && padded > len)
+      CU(ctx, cudaMemsetAsync((uint8_t *)d_coeffs + len * B, 0, (padded - len) * B, ctx->copy_stream));
+    CU(ctx, cudaEventRecord(ctx->chunk_ev[k], ctx->copy_stream));
+    CU(ctx, cudaStreamWaitEvent(st, ctx->chunk_ev[k], 0));
+    if (k == 0 && first_ev) CU(ctx, cudaEventRecord(first_ev, st));
+    if (int rc = encode_rows(enc, d_coeffs + r0 * n_per_row * N, n_per_row, n_per_row, d_comm + r0 * enc->n_cols * N,
+                             r1 - r0, enc_scratch))
+      return rc;
+  }
+  return LCPC_B200_OK;
+}
+
+int lcpc_b200_encode_rows_h2d(lcpc_b200_enc *enc, const uint64_t *rows, size_t len, uint64_t *d_coeffs, uint64_t *d_dst,
+                              size_t n_rows) {
+  if (!enc || !rows || !d_coeffs || !d_dst || n_rows == 0) return LCPC_B200_ERR_BAD_ARG;
+  lcpc_b200_ctx *ctx = enc->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (len > n_rows * enc->n_per_row || len + enc->n_per_row <= n_rows * enc->n_per_row)
+    return fail(ctx, LCPC_B200_ERR_BAD_ARG, "encode_rows_h2d: %zu elements do not fill %zu rows", len, n_rows);
+  if (int rc = bind_device(ctx)) return rc;
+  if (int rc = ensure_scratch(ctx, enc_scratch_bytes(enc, n_rows))) return rc;
+  return encode_rows_from_host(enc, rows, len, (uint32_t *)d_coeffs, (uint32_t *)d_dst, n_rows, ctx->scratch, nullptr);
+}
+
 int lcpc_b200_encode_dev(lcpc_b200_enc *enc, uint64_t *d_rows, size_t n_rows, size_t valid) {
   if (!enc || (!d_rows && n_rows)) return LCPC_B200_ERR_BAD_ARG;
   lcpc_b200_ctx *ctx = enc->ctx;
@@ -422,14 +507,18 @@ static int commit_run(lcpc_b200_commit *c, const void *src, size_t len, cudaMemc
     return fail(ctx, LCPC_B200_ERR_BAD_ARG, "commit: length %zu does not give %zu rows", len, c->n_rows);
   cudaStream_t st = ctx->stream;
   CU(ctx, cudaEventRecord(c->ev[0], st));
-  // pad + copy (lcpc-2d/src/lib.rs:636-645): coeffs = coeffs_in || zeros
-  CU(ctx, cudaMemcpyAsync(c->d_coeffs, src, len * B, kind, st));
-  size_t padded = c->n_rows * c->n_per_row;
-  if (padded > len) CU(ctx, cudaMemsetAsync((uint8_t *)c->d_coeffs + len * B, 0, (padded - len) * B, st));
-  CU(ctx, cudaEventRecord(c->ev[1], st));
-  // per-row encode (:648-653); reads the padded coefficient rows, writes comm
+  const size_t padded = c->n_rows * c->n_per_row;
   uint64_t l0 = ctx->launches;
-  if (int rc = encode_rows(enc, c->d_coeffs, c->n_per_row, c->n_per_row, c->d_comm, c->n_rows, c->d_enc_scratch)) return rc;
+  if (kind == cudaMemcpyHostToDevice && c->n_rows > 1) {
+    if (int rc = encode_rows_from_host(enc, src, len, c->d_coeffs, c->d_comm, c->n_rows, c->d_enc_scratch, c->ev[1])) return rc;
+  } else {
+    // pad + copy (lcpc-2d/src/lib.rs:636-645): coeffs = coeffs_in || zeros
+    CU(ctx, cudaMemcpyAsync(c->d_coeffs, src, len * B, kind, st));
+    if (padded > len) CU(ctx, cudaMemsetAsync((uint8_t *)c->d_coeffs + len * B, 0, (padded - len) * B, st));
+    CU(ctx, cudaEventRecord(c->ev[1], st));
+    // per-row encode (:648-653); reads the padded coefficient rows, writes comm
+    if (int rc = encode_rows(enc, c->d_coeffs, c->n_per_row, c->n_per_row, c->d_comm, c->n_rows, c->d_enc_scratch)) return rc;
+  }
   c->encode_launches = (int)(ctx->launches - l0);
   CU(ctx, cudaEventRecord(c->ev[2], st));
   // leaves beyond n_cols stay Output::default() = zeros (:665, :696)

@@ -83,3 +83,22 @@ def test_brakedown_ft127_2_24_sampled():
     check_commit_samples(c, oenc, x, field, rows=[0, 35, 71], cols=[0, 1, 235172, 235173, 357698, 300000, 41861])
     tensor = O.random_elems(field, c.n_rows, seed=6)
     assert (c.collapse(tensor) == O.collapse(field, c.coeffs, tensor, c.n_rows, c.n_per_row)).all()
+
+
+def test_ligero_ragged_length_chunked_host_copy():
+    """A length that leaves the last row short, large enough that the host->device copy runs in several
+    row-chunks overlapped with the encode: the zero padding (lcpc-2d/src/lib.rs:636-645) must land in the
+    last chunk only."""
+    field, length = P.FT255, (1 << 20) - 12345
+    enc = P.LigeroEncoding.new_from_dims(field, 16384, 32768)
+    oenc = O.Encoding.ligero_from_dims(field, 16384, 32768)
+    x = O.random_elems(field, length, seed=21)
+    c = P.LcCommit.commit(x, enc)
+    assert c.n_rows == 64
+    oc = oenc.commit(x)
+    assert oc["root"] == c.get_root().root and (oc["hashes"] == c.hashes).all() and (oc["comm"] == c.comm).all()
+    assert (oc["coeffs"] == c.coeffs).all()
+    # same object, re-run from the host with different data: no stale rows
+    y = O.random_elems(field, length, seed=22)
+    c.rerun(y)
+    assert oenc.commit(y)["root"] == c.get_root().root
