@@ -182,7 +182,8 @@ int lcpc_b200_pack_column_blocks_dev(lcpc_b200_ctx *ctx, int field, const uint64
 int lcpc_b200_collapse_dev(lcpc_b200_ctx *ctx, int field, const uint64_t *d_coeffs, size_t row_stride,
                            const uint64_t *d_tensor, uint64_t *d_poly, size_t n_rows, size_t n_per_row);
 /* element-wise field arithmetic on host arrays (parity tests of the device arithmetic):
- * op 0 add, 1 sub, 2 mul, 4 from_mont (b ignored) */
+ * op 0 add, 1 sub, 2 mul, 4 from_mont (b ignored), 5 mul as full product + separate reduction,
+ * 6 r[i] = sum_{k<37} a[(i+k)%n] * b[(7i+k)%n] accumulated double-width and reduced once */
 int lcpc_b200_field_op(lcpc_b200_ctx *ctx, int field, int op, uint64_t *r, const uint64_t *a,
                        const uint64_t *b, size_t n);
 

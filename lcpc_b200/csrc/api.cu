@@ -826,9 +826,10 @@ int lcpc_b200_merkleize(lcpc_b200_ctx *ctx, int field, const uint64_t *comm, siz
 
 int lcpc_b200_field_op(lcpc_b200_ctx *ctx, int field, int op, uint64_t *r, const uint64_t *a, const uint64_t *b, size_t n) {
   if (!ctx || !r || !a) return LCPC_B200_ERR_BAD_ARG;
-  if (field_limbs32(field) < 0 || !(op == 0 || op == 1 || op == 2 || op == 4))
+  if (field_limbs32(field) < 0 || !(op == 0 || op == 1 || op == 2 || op == 4 || op == 5 || op == 6))
     return fail(ctx, LCPC_B200_ERR_BAD_ARG, "bad field/op %d/%d", field, op);
-  if ((op <= 2) && !b) return LCPC_B200_ERR_BAD_ARG;
+  const bool two = op != 4;
+  if (two && !b) return LCPC_B200_ERR_BAD_ARG;
   if (n == 0) return LCPC_B200_OK;
   std::lock_guard<std::mutex> g(ctx->mu);
   if (int rc = bind_device(ctx)) return rc;
@@ -836,9 +837,9 @@ int lcpc_b200_field_op(lcpc_b200_ctx *ctx, int field, int op, uint64_t *r, const
   if (int rc = ensure_scratch(ctx, 3 * al)) return rc;
   uint8_t *base = (uint8_t *)ctx->scratch;
   CU(ctx, cudaMemcpyAsync(base, a, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  if (op <= 2) CU(ctx, cudaMemcpyAsync(base + al, b, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (two) CU(ctx, cudaMemcpyAsync(base + al, b, bytes, cudaMemcpyHostToDevice, ctx->stream));
   cudaError_t ce = launch_field_op(field, op, (uint32_t *)(base + 2 * al), (const uint32_t *)base,
-                                   op <= 2 ? (const uint32_t *)(base + al) : nullptr, n, ctx->stream);
+                                   two ? (const uint32_t *)(base + al) : nullptr, n, ctx->stream);
   ctx->launches += 1;
   if (ce != cudaSuccess) return cuda_fail(ctx, ce, "field_op");
   CU(ctx, cudaMemcpyAsync(r, base + 2 * al, bytes, cudaMemcpyDeviceToHost, ctx->stream));

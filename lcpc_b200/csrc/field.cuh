@@ -265,20 +265,141 @@ template <int FID> struct Field {
     return finish(E, O);
   }
 
+  // ---- double-width products, lazily reduced sums of products, stand-alone reduction ----
+  // Used where many products feed ONE result (sparse rows of the expander code, the prover's
+  // row combination): sum_k a_k b_k is accumulated as a 2N-limb integer and Montgomery-reduced once,
+  // which removes the N(N-1) reduction multiplies from every term but the last.  REDC is linear
+  // mod p, so the canonical result is the one the reference gets by reducing every product.
+  struct Wide { uint32_t v[2 * N]; };
+
+  // One row of a schoolbook product on two 64-bit-aligned accumulator arrays.  X receives
+  // a[1],a[3],.. times bi on the pairs (X[0],X[1]), (X[2],X[3]), ..; Y receives a[0],a[2],.. times bi
+  // on (Y[0],Y[1]), ..; X sits one limb above Y.  The top pair of X is first written by this row, so
+  // the carry out of the Y chain can be absorbed there without rippling further.
+  template <int M, bool X_FRESH, bool P0_IS_ONE>
+  LCPC_DEV static void mad_row(uint32_t *X, uint32_t *Y, const uint32_t *a, uint32_t bi) {
+    if (X_FRESH || M == 2) {
+#pragma unroll
+      for (int j = 1; j < M; j += 2) {
+        if (X_FRESH || j == M - 1) mul_wide(X[j - 1], X[j], a[j], bi);
+      }
+    } else {
+      mad_wide_cc(X[0], X[1], a[1], bi, X[0], X[1]);
+#pragma unroll
+      for (int j = 3; j < M - 1; j += 2) madc_wide_cc(X[j - 1], X[j], a[j], bi, X[j - 1], X[j]);
+      madc_wide(X[M - 2], X[M - 1], a[M - 1], bi, 0u, 0u);
+    }
+    if (P0_IS_ONE) {  // a[0] == 1: the product is bi itself
+      add_cc(Y[0], Y[0], bi);
+      addc_cc(Y[1], Y[1], 0u);
+    } else {
+      mad_wide_cc(Y[0], Y[1], a[0], bi, Y[0], Y[1]);
+    }
+#pragma unroll
+    for (int j = 2; j < M; j += 2) madc_wide_cc(Y[j], Y[j + 1], a[j], bi, Y[j], Y[j + 1]);
+    addc(X[M - 1], X[M - 1], 0u);
+  }
+
+  // T[0..2M) = a[0..M) * b[0..M), M even: M^2 wide multiply-adds, M - 1 + 2M - 1 carry adds
+  template <int M>
+  LCPC_DEV static void mul_full_n(uint32_t *T, const uint32_t *a, const uint32_t *b) {
+    uint32_t O[2 * M];  // O[k] sits at limb position k + 1
+#pragma unroll
+    for (int j = 0; j < M; j += 2) mul_wide(T[j], T[j + 1], a[j], b[0]);
+#pragma unroll
+    for (int j = 1; j < M; j += 2) mul_wide(O[j - 1], O[j], a[j], b[0]);
+#pragma unroll
+    for (int i = 1; i < M; i++) {
+      if (i & 1) mad_row<M, false, false>(&T[i + 1], &O[i - 1], a, b[i]);
+      else mad_row<M, false, false>(&O[i], &T[i], a, b[i]);
+    }
+    add_cc(T[1], T[1], O[0]);
+#pragma unroll
+    for (int k = 1; k < 2 * M - 2; k++) addc_cc(T[1 + k], T[1 + k], O[k]);
+    addc(T[2 * M - 1], T[2 * M - 1], 0u);
+  }
+
+  LCPC_DEV static Wide mul_full(const Elem &a, const Elem &b) {
+    Wide t;
+    mul_full_n<N>(t.v, a.v, b.v);
+    return t;
+  }
+
+  LCPC_DEV static Wide wide_zero() {
+    Wide t;
+#pragma unroll
+    for (int i = 0; i < 2 * N; i++) t.v[i] = 0;
+    return t;
+  }
+
+  // acc += t, then acc -= p * 2^(32N) if that leaves acc >= 2^(64N - 1).  Invariant: acc < 2^(64N-1)
+  // before and after (every product is < p^2 < 0.19 * 2^(64N), and 0.27 <= p / 2^(32N) < 0.44 for the
+  // four moduli); subtracting a multiple of p * R does not change REDC's result mod p.
+  LCPC_DEV static void wide_add_fold(Wide &acc, const Wide &t) {
+    add_cc(acc.v[0], acc.v[0], t.v[0]);
+#pragma unroll
+    for (int i = 1; i < 2 * N - 1; i++) addc_cc(acc.v[i], acc.v[i], t.v[i]);
+    addc(acc.v[2 * N - 1], acc.v[2 * N - 1], t.v[2 * N - 1]);
+    const uint32_t mask = (uint32_t)((int32_t)acc.v[2 * N - 1] >> 31);
+    sub_cc(acc.v[N], acc.v[N], FP::P(0) & mask);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) subc_cc(acc.v[N + i], acc.v[N + i], FP::P(i) & mask);
+    subc(acc.v[2 * N - 1], acc.v[2 * N - 1], FP::P(N - 1) & mask);
+  }
+  LCPC_DEV static void mac_wide(Wide &acc, const Elem &a, const Elem &b) { wide_add_fold(acc, mul_full(a, b)); }
+
+  // Montgomery reduction of the low half: (lo + q p) / 2^(32N) for the q that clears the low N limbs;
+  // the result is <= p.  Rows of q*p are laid out as in mul_full_n (operand p, digits found on the fly);
+  // `c` is the carry that the two arrays still owe to the position being cleared.
+  LCPC_DEV static Elem redc_low(const uint32_t *lo) {
+    uint32_t E[2 * N], O[2 * N];  // E[k] at limb position k, O[k] at position k + 1
+    uint32_t pl[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) { E[j] = lo[j]; pl[j] = PM(j); }
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      uint32_t *Y = (i & 1) ? &O[i - 1] : &E[i];
+      uint32_t *X = (i & 1) ? &E[i + 1] : &O[i];
+      const uint32_t w = i == 0 ? 0u : ((i & 1) ? E[i] : O[i - 1]);  // the other array's limb at position i
+      const uint32_t v = Y[0] + w + c;
+#ifdef __CUDA_ARCH__
+      const uint32_t m = v * kMontInv32;
+#else
+      const uint32_t m = 0u - v;
+#endif
+      if (i == 0) mad_row<N, true, true>(X, Y, pl, m);
+      else mad_row<N, false, true>(X, Y, pl, m);
+      const uint32_t rest = Y[0] | w | c;  // position i now sums to 0 or 2^32
+      c = rest != 0u ? 1u : 0u;
+    }
+    Elem t;
+    uint32_t dummy;
+    add_cc(dummy, c, 0xffffffffu);  // carry flag <- c
+    (void)dummy;
+#pragma unroll
+    for (int k = 0; k < N - 1; k++) addc_cc(t.v[k], E[N + k], O[N + k - 1]);
+    addc(t.v[N - 1], E[2 * N - 1], 0u);
+    return t;
+  }
+
+  // REDC of a double-width value t < 2^(64N-1): t * R^{-1} mod p in [0, p).  SUBS = how many conditional
+  // subtractions of p the bound on t needs (1 for a single product a*b with a, b < p; 2 for folded sums)
+  template <int SUBS>
+  LCPC_DEV static Elem redc(const Wide &t) {
+    Elem r = redc_low(t.v);
+    add_cc(r.v[0], r.v[0], t.v[N]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) addc_cc(r.v[i], r.v[i], t.v[N + i]);
+    addc(r.v[N - 1], r.v[N - 1], t.v[2 * N - 1]);
+#pragma unroll
+    for (int s = 0; s < SUBS; s++) r = cond_sub_p(r);
+    return r;
+  }
+
   // canonical integer of a Montgomery-form element: a * R^{-1} mod p  (what to_repr serialises,
   // reference: FieldHash::digest_update, lcpc-2d/src/lib.rs:42-57)
-  LCPC_DEV static Elem from_mont(const Elem &a) {
-    uint32_t E[N], O[N];
-#pragma unroll
-    for (int j = 0; j < N; j++) { E[j] = a.v[j]; O[j] = 0; }
-    step<true, false>(E, O, a.v, 0u);
-#pragma unroll
-    for (int i = 1; i < N; i += 2) {
-      step<false, false>(O, E, a.v, 0u);
-      if (i + 1 < N) step<false, false>(E, O, a.v, 0u);
-    }
-    return finish(E, O);
-  }
+  LCPC_DEV static Elem from_mont(const Elem &a) { return cond_sub_p(redc_low(a.v)); }
 };
 
 }  // namespace lcpc

@@ -12,7 +12,7 @@ namespace lcpc {
 int field_limbs32(int field);  // 2/4/6/8, or -1
 inline size_t field_bytes(int field) { return 4 * (size_t)field_limbs32(field); }
 
-// element-wise field ops (test hook): op 0 add, 1 sub, 2 mul, 4 from_mont
+// element-wise field ops (test hook): op 0 add, 1 sub, 2 mul, 4 from_mont, 5 mul_full+redc, 6 lazy 37-term sums
 cudaError_t launch_field_op(int field, int op, uint32_t *r, const uint32_t *a, const uint32_t *b, size_t n,
                             cudaStream_t stream);
 

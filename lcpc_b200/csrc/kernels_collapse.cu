@@ -44,15 +44,16 @@ collapse_kernel(const uint32_t *__restrict__ coeffs, size_t row_stride, const ui
   __shared__ uint32_t part[ROW_GROUPS][N][COL_TILE];
   const unsigned lane = threadIdx.x % COL_TILE, grp = threadIdx.x / COL_TILE;
   const size_t col = (size_t)blockIdx.x * COL_TILE + lane;
-  typename F::Elem acc = F::zero();
+  typename F::Wide wide = F::wide_zero();
   if (col < n_per_row) {
     for (size_t r = grp; r < n_rows; r += ROW_GROUPS) {
       typename F::Elem a, t;
       ld_elem<N>(a.v, coeffs + (r * row_stride + col) * N);
       ld_elem<N>(t.v, tensor + r * N);
-      acc = F::add(acc, F::mul(a, t));
+      F::mac_wide(wide, a, t);
     }
   }
+  typename F::Elem acc = F::template redc<2>(wide);
 #pragma unroll
   for (int l = 0; l < N; l++) part[grp][l][lane] = acc.v[l];
   __syncthreads();

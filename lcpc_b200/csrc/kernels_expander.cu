@@ -236,7 +236,9 @@ transpose_kernel(const uint32_t *__restrict__ src, size_t src_ld, uint32_t *__re
   }
 }
 
-// y[i][r] = sum_k vals[k] * x[colidx[k]][r]; one thread per (output i, batch row r), r fastest
+// y[i][r] = sum_k vals[k] * x[colidx[k]][r]; one thread per (output i, batch row r), r fastest.
+// The sum is kept double-width and Montgomery-reduced once per output (field.cuh, mac_wide / redc):
+// a sparse row has 8..45 terms, so this halves the multiplier work against reduce-every-product.
 template <int FID>
 __global__ void __launch_bounds__(256)
 spmm_kernel(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ colidx, const uint32_t *__restrict__ vals,
@@ -247,15 +249,16 @@ spmm_kernel(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ co
   if (item >= m * n_rows) return;
   const size_t i = item / n_rows, r = item % n_rows;
   const uint32_t k0 = __ldg(rowptr + i), k1 = __ldg(rowptr + i + 1);
-  typename F::Elem acc = F::zero();
+  typename F::Wide acc = F::wide_zero();
   for (uint32_t k = k0; k < k1; k++) {
     const size_t j = __ldg(colidx + k);
     typename F::Elem a, xv;
     ldv<N>(a.v, vals + (size_t)k * N);
     ldv<N>(xv.v, x + (j * n_rows + r) * N);
-    acc = F::add(acc, F::mul(a, xv));
+    F::mac_wide(acc, a, xv);
   }
-  stv<N>(y + (i * n_rows + r) * N, acc.v);
+  typename F::Elem out = F::template redc<2>(acc);
+  stv<N>(y + (i * n_rows + r) * N, out.v);
 }
 
 // reed_solomon (encode.rs:97-110): out[k][r] = Horner of in[.][r] at the point k+1

@@ -124,6 +124,18 @@ __global__ void field_op_kernel(int op, uint32_t *r, const uint32_t *a, const ui
     case 0: z = F::add(x, y); break;
     case 1: z = F::sub(x, y); break;
     case 2: z = F::mul(x, y); break;
+    case 5: z = F::template redc<1>(F::mul_full(x, y)); break;
+    case 6: {  // 37-term lazily reduced sum of products starting at element i (indices wrap)
+      typename F::Wide acc = F::wide_zero();
+      for (size_t k = 0; k < 37; k++) {
+        typename F::Elem u, v;
+        gload<F::N>(u.v, a + ((i + k) % n) * F::N);
+        gload<F::N>(v.v, b + ((i * 7 + k) % n) * F::N);
+        F::mac_wide(acc, u, v);
+      }
+      z = F::template redc<2>(acc);
+      break;
+    }
     default: z = F::from_mont(x); break;
   }
   gstore<F::N>(r + i * F::N, z.v);

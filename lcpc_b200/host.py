@@ -421,7 +421,7 @@ def collapse_columns(field: int, coeffs, tensor, n_rows: int, n_per_row: int, ct
     return out
 
 
-_OPS = {"add": 0, "sub": 1, "mul": 2, "from_mont": 4}
+_OPS = {"add": 0, "sub": 1, "mul": 2, "from_mont": 4, "mul_sos": 5, "lazy_sum37": 6}
 
 
 def field_op(field: int, op: str, a, b=None, ctx: Context | None = None) -> np.ndarray:

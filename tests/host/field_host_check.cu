@@ -22,6 +22,18 @@ static int run(int op, uint64_t *r, const uint64_t *a, const uint64_t *b, size_t
       case 1: z = F::sub(x, y); break;
       case 2: z = F::mul(x, y); break;
       case 4: z = F::from_mont(x); break;
+      case 5: z = F::template redc<1>(F::mul_full(x, y)); break;  // product and reduction done separately
+      case 6: {  // lazily reduced sum of LAZY_TERMS products starting at element i (indices wrap)
+        typename F::Wide acc = F::wide_zero();
+        for (size_t k = 0; k < 37; k++) {
+          typename F::Elem u, v;
+          memcpy(u.v, a + ((i + k) % n) * (F::N / 2), F::BYTES);
+          memcpy(v.v, b + ((i * 7 + k) % n) * (F::N / 2), F::BYTES);
+          F::mac_wide(acc, u, v);
+        }
+        z = F::template redc<2>(acc);
+        break;
+      }
       default: return -1;
     }
     memcpy(r + i * (F::N / 2), z.v, F::BYTES);

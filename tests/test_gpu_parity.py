@@ -38,6 +38,17 @@ def test_field_ops(field):
     for op in ("add", "sub", "mul"):
         assert (P.field_op(field, op, a, b) == O.field_op(field, op, a, b)).all(), op
     assert (P.field_op(field, "from_mont", a) == O.field_op(field, "from_mont", a)).all()
+    # full product + separate reduction, and double-width sums of 37 products reduced once
+    assert (P.field_op(field, "mul_sos", a, b) == O.field_op(field, "mul", a, b)).all()
+    m = 5000
+    a2, b2 = a[:m].copy(), b[:m].copy()
+    a2[100:164] = O.ints_to_elems([p - 1] * 64, field)   # runs of (p-1)^2 terms: worst case of the fold bound
+    b2[700:1200] = O.ints_to_elems([p - 1] * 500, field)
+    idx = np.arange(m)
+    want = O.ints_to_elems([0] * m, field)
+    for k in range(37):
+        want = O.field_op(field, "add", want, O.field_op(field, "mul", a2[(idx + k) % m], b2[(idx * 7 + k) % m]))
+    assert (P.field_op(field, "lazy_sum37", a2, b2) == want).all()
 
 
 # ------------------------------------------------------------------ hashing / Merkle

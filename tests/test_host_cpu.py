@@ -147,3 +147,28 @@ def test_field_carry_chains_on_host_emulation(hostcheck, field):
                                           b.ctypes.data_as(C.c_void_p), C.c_size_t(n))
         assert rc == 0
         assert (r == O.field_op(field, name, a, b if op < 3 else None)).all(), name
+    # product and reduction done separately (mul_full + redc) == the interleaved product
+    r = np.empty_like(a)
+    assert hostcheck.hostcheck_field_op(field, 5, r.ctypes.data_as(C.c_void_p), a.ctypes.data_as(C.c_void_p),
+                                        b.ctypes.data_as(C.c_void_p), C.c_size_t(n)) == 0
+    assert (r == O.field_op(field, "mul", a, b)).all()
+    # 37-term sums of products accumulated double-width and reduced once == reduce-every-product
+    m = 3000
+    r = np.empty_like(a[:m])
+    assert hostcheck.hostcheck_field_op(field, 6, r.ctypes.data_as(C.c_void_p), a[:m].ctypes.data_as(C.c_void_p),
+                                        b[:m].ctypes.data_as(C.c_void_p), C.c_size_t(m)) == 0
+    want = O.ints_to_elems([0] * m, field)
+    idx = np.arange(m)
+    for k in range(37):
+        want = O.field_op(field, "add", want, O.field_op(field, "mul", a[:m][(idx + k) % m], b[:m][(idx * 7 + k) % m]))
+    assert (r == want).all()
+    # worst case for the fold bound: every term is (p-1)^2
+    big = O.ints_to_elems([p - 1] * 64, field)
+    r = np.empty_like(big)
+    assert hostcheck.hostcheck_field_op(field, 6, r.ctypes.data_as(C.c_void_p), big.ctypes.data_as(C.c_void_p),
+                                        big.ctypes.data_as(C.c_void_p), C.c_size_t(64)) == 0
+    sq = O.field_op(field, "mul", big, big)
+    want = O.ints_to_elems([0] * 64, field)
+    for k in range(37):
+        want = O.field_op(field, "add", want, sq)
+    assert (r == want).all()
