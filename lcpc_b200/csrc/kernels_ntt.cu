@@ -195,95 +195,197 @@ cudaError_t launch_root_table(int field, uint32_t *roots, const uint32_t *w, siz
 }
 
 // ---- one NTT pass -----------------------------------------------------------------------------
+// Geometry of a pass (host side fills NttPass): the pass runs S consecutive stages, the ones whose
+// butterfly gap in row positions is 2^(hi-1) .. 2^(hi-S).  A CTA stages a tile of 2^S "t" values (the
+// S row-index bits the pass works on) times C = 2^logC other positions:
+//   stride pass (hi > S):  element (t, c) is row position  base + t * 2^(hi-S) + c,  c = C adjacent points
+//   last pass   (hi == S): element (t, c) is row position  base + c * 2^S + t,       C adjacent sub-transforms
+// so a tile is always made of runs of >= C*B (resp. 2^S*B) contiguous bytes in HBM.
+//
+// Inside the tile the S stages run as ceil(S/3) ROUNDS: a thread pulls 8 (4, 2) elements that differ in
+// the 3 (2, 1) t-bits of the round into registers, does those stages there, and puts them back -- one
+// shared-memory round trip and one barrier per three stages, and up to four independent Montgomery
+// products in flight per thread to keep the IMAD pipe fed.  In the final round of the last pass the
+// twiddle exponent of lane r of every stage is r * n/(2 gap): the r = 0 products are by w^0 = 1 and are
+// dropped at compile time (5 products per 8 points instead of 12).
 struct NttPass {
   unsigned log_n;      // transform length 2^log_n
   unsigned hi;         // this pass runs the stages with gaps 2^(hi-1) .. 2^(hi-S)
   unsigned S;          // stages in this pass
-  unsigned logC;       // log2 of adjacent points per tile
+  unsigned logC;       // log2 of adjacent points (or sub-transforms) per tile
   unsigned tiles_per_row_log;  // log2(n / (2^S * C))
   size_t src_stride, src_valid, dst_stride;
 };
 
 constexpr int NTT_THREADS = 256;
 
+struct NttGeom {
+  unsigned log_n, S, tile, tshift, cshift, tmask, cmask, log_stride;
+  bool last;
+  size_t base;
+};
+
+// shared-memory slot of tile element e: XOR the 16-byte-bank index with the next three index bits, so
+// that the 8 lanes of a quarter warp hit 8 different bank groups in every round (their e differ either
+// in bits 0-2 or in bits 3-5)
+__device__ __forceinline__ unsigned swz(unsigned e) { return e ^ ((e >> 3) & 7u); }
+
+template <int N> struct SmemLayout {
+  static constexpr int PW = Planes<N>::PW, NP = Planes<N>::NP;
+  // planes are PLANE_PAD elements apart beyond the tile so that the two 16-byte halves of an element
+  // land in different bank groups (staging writes both halves of 16 elements per warp instruction)
+  static constexpr unsigned PLANE_PAD = 4;
+  __host__ __device__ static size_t bytes(unsigned tile) { return (size_t)NP * (tile + PLANE_PAD) * PW * 4; }
+};
+
+template <int N>
+__device__ __forceinline__ void sload2(uint32_t (&v)[N], const uint32_t *smem, unsigned slot, unsigned tile) {
+  constexpr int PW = SmemLayout<N>::PW, NP = SmemLayout<N>::NP;
+#pragma unroll
+  for (int pl = 0; pl < NP; pl++) {
+    const uint32_t *q = smem + ((size_t)pl * (tile + SmemLayout<N>::PLANE_PAD) + slot) * PW;
+    if constexpr (PW == 4) {
+      uint4 t = *reinterpret_cast<const uint4 *>(q);
+      v[4 * pl] = t.x, v[4 * pl + 1] = t.y, v[4 * pl + 2] = t.z, v[4 * pl + 3] = t.w;
+    } else {
+      uint2 t = *reinterpret_cast<const uint2 *>(q);
+      v[2 * pl] = t.x, v[2 * pl + 1] = t.y;
+    }
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void sstore2(uint32_t *smem, unsigned slot, unsigned tile, const uint32_t (&v)[N]) {
+  constexpr int PW = SmemLayout<N>::PW, NP = SmemLayout<N>::NP;
+#pragma unroll
+  for (int pl = 0; pl < NP; pl++) {
+    uint32_t *q = smem + ((size_t)pl * (tile + SmemLayout<N>::PLANE_PAD) + slot) * PW;
+    if constexpr (PW == 4)
+      *reinterpret_cast<uint4 *>(q) = make_uint4(v[4 * pl], v[4 * pl + 1], v[4 * pl + 2], v[4 * pl + 3]);
+    else
+      *reinterpret_cast<uint2 *>(q) = make_uint2(v[2 * pl], v[2 * pl + 1]);
+  }
+}
+
+// KL stages (t-bits lg_top .. lg_top-KL+1) on 2^KL elements per work item, in registers
+template <int FID, int KL, bool FINAL>
+__device__ __forceinline__ void ntt_round(uint32_t *smem, const uint32_t *__restrict__ roots, const NttGeom &g,
+                                          unsigned lg_top) {
+  using F = Field<FID>;
+  constexpr int N = F::N;
+  constexpr int K = 1 << KL;
+  const unsigned pos = lg_top + 1 - KL + g.tshift;  // tile-index bit of the round's lowest t-bit
+  const unsigned items = g.tile >> KL;
+  const unsigned log_h = g.log_stride + lg_top + 1 - KL;  // log2 row distance between the item's elements
+  for (unsigned w = threadIdx.x; w < items; w += NTT_THREADS) {
+    const unsigned e0 = ((w >> pos) << (pos + KL)) | (w & ((1u << pos) - 1u));
+    typename F::Elem x[K];
+#pragma unroll
+    for (int q = 0; q < K; q++) sload2<N>(x[q].v, smem, swz(e0 | ((unsigned)q << pos)), g.tile);
+    const unsigned t0 = (e0 >> g.tshift) & g.tmask, c = (e0 >> g.cshift) & g.cmask;
+    const size_t j0 = g.last ? g.base + ((size_t)c << g.S) + t0 : g.base + ((size_t)t0 << g.log_stride) + c;
+#pragma unroll
+    for (int u = 0; u < KL; u++) {
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int gq = K >> (u + 1);
+      const unsigned logG = g.log_stride + lg_top - u;  // log2 of this stage's gap in row positions
+      const unsigned twshift = g.log_n - 1 - logG;
+#pragma unroll
+      for (int r = 0; r < gq; r++) {
+        const bool unit = FINAL && r == 0;  // exponent r * n/(2 gap) = 0
+        typename F::Elem wv;
+        if (!unit) {
+          const size_t tw = ((j0 + ((size_t)r << log_h)) & (((size_t)1 << logG) - 1)) << twshift;
+          gload_ro<N>(wv.v, roots + tw * N);
+        }
+#pragma unroll
+        for (int blk = 0; blk < K; blk += 2 * gq) {
+          const int qa = blk + r, qb = qa + gq;
+          typename F::Elem sum = F::add(x[qa], x[qb]);
+          typename F::Elem dif = F::sub(x[qa], x[qb]);
+          x[qa] = sum;
+          x[qb] = unit ? dif : F::mul(dif, wv);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < K; q++) sstore2<N>(smem, swz(e0 | ((unsigned)q << pos)), g.tile, x[q].v);
+  }
+}
+
 template <int FID>
-__global__ void __launch_bounds__(NTT_THREADS)
+__global__ void __launch_bounds__(NTT_THREADS, 2)
 ntt_pass_kernel(const uint32_t *__restrict__ src, uint32_t *dst, const uint32_t *__restrict__ roots, NttPass p) {
   using F = Field<FID>;
   constexpr int N = F::N;
+  constexpr int PW = SmemLayout<N>::PW, NP = SmemLayout<N>::NP;
   extern __shared__ __align__(16) uint32_t smem[];
-  const unsigned S = p.S, logC = p.logC;
-  const unsigned tile = 1u << (S + logC);
+  NttGeom g;
+  g.log_n = p.log_n, g.S = p.S;
+  g.tile = 1u << (p.S + p.logC);
+  g.last = (p.hi == p.S);
   const size_t row = blockIdx.x >> p.tiles_per_row_log;
   const size_t tid_in_row = blockIdx.x & ((1u << p.tiles_per_row_log) - 1);
-  const bool last = (p.hi == S);  // stride-1 pass: the tile is C contiguous sub-transforms
-  // element (t, c) of the tile sits at  base + t * tstride + c * cstride  in the row
-  size_t base, tstride;
-  unsigned tshift, cshift;  // smem index e = (t << tshift) | (c << cshift)
-  if (last) {
-    base = tid_in_row << (S + logC);
-    tstride = 1;
-    tshift = 0, cshift = S;
+  if (g.last) {
+    g.base = tid_in_row << (p.S + p.logC);
+    g.log_stride = 0;
+    g.tshift = 0, g.cshift = p.S;
   } else {
-    const unsigned log_stride = p.hi - S;
-    const size_t lowblocks_log = log_stride - logC;
+    g.log_stride = p.hi - p.S;
+    const size_t lowblocks_log = g.log_stride - p.logC;
     const size_t high = tid_in_row >> lowblocks_log;
     const size_t lowblock = tid_in_row & (((size_t)1 << lowblocks_log) - 1);
-    base = (high << p.hi) + (lowblock << logC);
-    tstride = (size_t)1 << log_stride;
-    tshift = logC, cshift = 0;
+    g.base = (high << p.hi) + (lowblock << p.logC);
+    g.tshift = p.logC, g.cshift = 0;
   }
-  const unsigned tmask = (1u << S) - 1, cmask = (1u << logC) - 1;
+  g.tmask = (1u << p.S) - 1, g.cmask = (1u << p.logC) - 1;
   const uint32_t *srow = src + row * p.src_stride * N;
   uint32_t *drow = dst + row * p.dst_stride * N;
+  const unsigned granules = g.tile * NP;  // PW-limb pieces; consecutive lanes move consecutive pieces of HBM
 
-  // load: smem index e enumerates the tile in its HBM-contiguous order
-  for (unsigned e = threadIdx.x; e < tile; e += NTT_THREADS) {
-    unsigned t = (e >> tshift) & tmask, c = (e >> cshift) & cmask;
-    size_t j = last ? base + e : base + t * tstride + c;
-    typename F::Elem x;
-    if (j < p.src_valid) gload<N>(x.v, srow + j * N);
-    else x = F::zero();
-    sstore<N>(smem, e, tile, x.v);
+  for (unsigned gi = threadIdx.x; gi < granules; gi += NTT_THREADS) {
+    const unsigned e = gi / NP, pl = gi % NP;
+    const unsigned t = (e >> g.tshift) & g.tmask, c = (e >> g.cshift) & g.cmask;
+    const size_t j = g.last ? g.base + e : g.base + ((size_t)t << g.log_stride) + c;
+    uint32_t *q = smem + ((size_t)pl * (g.tile + SmemLayout<N>::PLANE_PAD) + swz(e)) * PW;
+    if constexpr (PW == 4) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (j < p.src_valid) v = __ldg(reinterpret_cast<const uint4 *>(srow + j * N) + pl);
+      *reinterpret_cast<uint4 *>(q) = v;
+    } else {
+      uint2 v = make_uint2(0, 0);
+      if (j < p.src_valid) v = __ldg(reinterpret_cast<const uint2 *>(srow + j * N) + pl);
+      *reinterpret_cast<uint2 *>(q) = v;
+    }
   }
   __syncthreads();
 
-  const unsigned half = tile >> 1;
-  for (unsigned s = 0; s < S; s++) {
-    const unsigned lg = S - 1 - s;          // log2 of the gap in t units
-    const unsigned logG = p.hi - 1 - s;     // log2 of the gap in row positions
-    const unsigned twshift = p.log_n - 1 - logG;
-    for (unsigned w = threadIdx.x; w < half; w += NTT_THREADS) {
-      unsigned q, c;
-      if (last) q = w & ((1u << (S - 1)) - 1), c = w >> (S - 1);
-      else c = w & cmask, q = w >> logC;
-      unsigned t_lo = ((q >> lg) << (lg + 1)) | (q & ((1u << lg) - 1));
-      unsigned e_lo = (t_lo << tshift) | (c << cshift);
-      unsigned e_hi = e_lo + ((1u << lg) << tshift);
-      typename F::Elem a, b;
-      sload<N>(a.v, smem, e_lo, tile);
-      sload<N>(b.v, smem, e_hi, tile);
-      typename F::Elem sum = F::add(a, b);
-      typename F::Elem dif = F::sub(a, b);
-      if (logG != 0) {  // the gap-1 stage multiplies by w^0 = 1 only
-        size_t j_lo = last ? base + ((size_t)c << S) + t_lo : base + t_lo * tstride + c;
-        size_t tw = (j_lo & (((size_t)1 << logG) - 1)) << twshift;
-        typename F::Elem wv;
-        gload_ro<N>(wv.v, roots + tw * N);
-        dif = F::mul(dif, wv);
-      }
-      sstore<N>(smem, e_lo, tile, sum.v);
-      sstore<N>(smem, e_hi, tile, dif.v);
+  unsigned rem = p.S, lg_top = p.S - 1;
+  while (rem > 0) {
+    if (rem >= 3) {
+      if (g.last && rem == 3) ntt_round<FID, 3, true>(smem, roots, g, lg_top);
+      else ntt_round<FID, 3, false>(smem, roots, g, lg_top);
+      rem -= 3, lg_top -= 3;
+    } else if (rem == 2) {
+      if (g.last) ntt_round<FID, 2, true>(smem, roots, g, lg_top);
+      else ntt_round<FID, 2, false>(smem, roots, g, lg_top);
+      rem = 0;
+    } else {
+      if (g.last) ntt_round<FID, 1, true>(smem, roots, g, lg_top);
+      else ntt_round<FID, 1, false>(smem, roots, g, lg_top);
+      rem = 0;
     }
     __syncthreads();
   }
 
-  for (unsigned e = threadIdx.x; e < tile; e += NTT_THREADS) {
-    unsigned t = (e >> tshift) & tmask, c = (e >> cshift) & cmask;
-    size_t j = last ? base + e : base + t * tstride + c;
-    typename F::Elem x;
-    sload<N>(x.v, smem, e, tile);
-    gstore<N>(drow + j * N, x.v);
+  for (unsigned gi = threadIdx.x; gi < granules; gi += NTT_THREADS) {
+    const unsigned e = gi / NP, pl = gi % NP;
+    const unsigned t = (e >> g.tshift) & g.tmask, c = (e >> g.cshift) & g.cmask;
+    const size_t j = g.last ? g.base + e : g.base + ((size_t)t << g.log_stride) + c;
+    const uint32_t *q = smem + ((size_t)pl * (g.tile + SmemLayout<N>::PLANE_PAD) + swz(e)) * PW;
+    if constexpr (PW == 4) reinterpret_cast<uint4 *>(drow + j * N)[pl] = *reinterpret_cast<const uint4 *>(q);
+    else reinterpret_cast<uint2 *>(drow + j * N)[pl] = *reinterpret_cast<const uint2 *>(q);
   }
 }
 
@@ -293,11 +395,11 @@ static cudaError_t ntt_rows_impl(const uint32_t *src, size_t src_stride, size_t 
                                  cudaStream_t stream, int *n_launches) {
   using F = Field<FID>;
   static bool attr_set = false;
-  constexpr unsigned LOG_TILE = 11;  // 2048 elements: 64 KiB for Ft255 -> 3 CTAs/SM
+  constexpr unsigned LOG_TILE = 11;  // 2048 elements: 64 KiB for Ft255
   constexpr unsigned MAX_S = 9;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(ntt_pass_kernel<FID>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)((1u << LOG_TILE) * F::BYTES));
+                                         (int)SmemLayout<F::N>::bytes(1u << LOG_TILE));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -309,7 +411,7 @@ static cudaError_t ntt_rows_impl(const uint32_t *src, size_t src_stride, size_t 
                                cudaMemcpyDeviceToDevice, stream);
     return cudaSuccess;
   }
-  unsigned n_pass, S_first;
+  unsigned n_pass;
   if (log_n <= LOG_TILE) n_pass = 1;
   else n_pass = (log_n + MAX_S - 1) / MAX_S;
   unsigned hi = log_n;
@@ -318,7 +420,6 @@ static cudaError_t ntt_rows_impl(const uint32_t *src, size_t src_stride, size_t 
   for (unsigned ip = 0; ip < n_pass; ip++) {
     unsigned remaining = n_pass - ip;
     unsigned S = (hi + remaining - 1) / remaining;  // balanced split, larger passes first
-    (void)S_first;
     NttPass p;
     p.log_n = log_n, p.hi = hi, p.S = S;
     unsigned logC = S >= LOG_TILE ? 0 : LOG_TILE - S;
@@ -330,7 +431,7 @@ static cudaError_t ntt_rows_impl(const uint32_t *src, size_t src_stride, size_t 
     p.src_stride = cur_stride, p.src_valid = cur_valid, p.dst_stride = dst_stride;
     size_t grid = n_rows << p.tiles_per_row_log;
     if (grid > 0x7fffffffu) return cudaErrorInvalidValue;
-    size_t smem = ((size_t)1 << (S + logC)) * F::BYTES;
+    size_t smem = SmemLayout<F::N>::bytes(1u << (S + logC));
     ntt_pass_kernel<FID><<<(unsigned)grid, NTT_THREADS, smem, stream>>>(cur_src, dst, roots, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
