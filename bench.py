@@ -224,7 +224,8 @@ def run_ours(args):
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "u32 limbs (Montgomery prime field) + BLAKE3 u32", "data": "synthetic",
            "config": {"workload": wl["name"], "n_rows": n_rows, "n_per_row": n_per_row, "n_cols": n_cols,
-                      "parallelism": f"row-block x{world} + all-to-all" if world > 1 else "1 GPU",
+                      "parallelism": (f"row-block x{world}, exchange={result.get('transport')}, column-block hash"
+                                      if world > 1 else "1 GPU"),
                       "l2": "inputs+outputs (>= 1.5 GiB at 2^24) exceed the 126 MB L2; no flush needed",
                       "timing": "CUDA events on the engine stream, max over ranks"},
            "e2e": result["e2e"], "gpu_launches": result["gpu_launches"], "clocks": result["clocks"],

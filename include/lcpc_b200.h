@@ -119,6 +119,24 @@ int lcpc_b200_encode_rows_dev(lcpc_b200_enc *enc, const uint64_t *d_src, size_t 
 int lcpc_b200_encode_rows_h2d(lcpc_b200_enc *enc, const uint64_t *rows, size_t len, uint64_t *d_coeffs,
                               uint64_t *d_dst, size_t n_rows);
 
+/* Row-block encode whose result is stored per COLUMN BLOCK instead of row-major: the fused "encode +
+ * transpose" step of the multi-GPU commit (no reference analogue).  Column block h = columns
+ * [starts[h], starts[h+1]) of every encoded row lands in the matrix dst[h][all rows][width_h]; dst[h] is
+ * device memory of this GPU or a peer-mapped buffer of another GPU (written over NVLink by the encode's last
+ * pass itself).  This call's rows are rows row0 .. row0+n_rows-1 of those matrices.  d_tmp: n_rows*n_cols
+ * elements of row-major scratch for the passes before the last.  Enqueues only. */
+typedef struct {
+  size_t n_blocks;        /* 1..16 */
+  const uint64_t *starts; /* n_blocks + 1 column boundaries, starts[0] = 0, starts[n_blocks] = n_cols (host) */
+  uint64_t *const *dst;   /* n_blocks device pointers (host array) */
+  size_t row0;
+} lcpc_b200_scatter;
+int lcpc_b200_encode_rows_scatter_dev(lcpc_b200_enc *enc, const uint64_t *d_src, size_t src_stride, size_t valid,
+                                      uint64_t *d_tmp, size_t n_rows, const lcpc_b200_scatter *scatter);
+/* the same fed from host rows (see lcpc_b200_encode_rows_h2d) */
+int lcpc_b200_encode_rows_scatter_h2d(lcpc_b200_enc *enc, const uint64_t *rows, size_t len, uint64_t *d_coeffs,
+                                      uint64_t *d_tmp, size_t n_rows, const lcpc_b200_scatter *scatter);
+
 /* ---- commit (LcCommit::commit, lcpc-2d/src/lib.rs:299-301 -> :622-671) ----
  * coeffs_in: `len` elements on the host.  Pads to n_rows x n_per_row (:636-645), encodes every row
  * (:648-653), hashes columns and builds the Merkle tree (:656-668).  The result stays on the device. */

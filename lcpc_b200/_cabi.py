@@ -31,6 +31,10 @@ class Csc(C.Structure):
                 ("data", C.c_void_p)]
 
 
+class Scatter(C.Structure):
+    _fields_ = [("n_blocks", C.c_size_t), ("starts", C.c_void_p), ("dst", C.c_void_p), ("row0", C.c_size_t)]
+
+
 _vp, _sz, _i, _u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64
 _pvp, _psz = C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)
 
@@ -69,6 +73,8 @@ SIGNATURES = {
     "lcpc_b200_commit_phase_times": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "lcpc_b200_encode_rows_dev": (_i, [_vp, _vp, _sz, _sz, _vp, _sz]),
     "lcpc_b200_encode_rows_h2d": (_i, [_vp, _vp, _sz, _vp, _vp, _sz]),
+    "lcpc_b200_encode_rows_scatter_dev": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, C.POINTER(Scatter)]),
+    "lcpc_b200_encode_rows_scatter_h2d": (_i, [_vp, _vp, _sz, _vp, _vp, _sz, C.POINTER(Scatter)]),
     "lcpc_b200_commit_device_ptrs": (_i, [_vp, _pvp, _pvp, _pvp]),
     "lcpc_b200_commit_to_host": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "lcpc_b200_commit_collapse": (_i, [_vp, _vp, _vp]),

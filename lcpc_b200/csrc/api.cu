@@ -340,15 +340,16 @@ int lcpc_b200_enc_dims_ok(const lcpc_b200_enc *enc, size_t n_per_row, size_t n_c
 
 // encode n_rows rows: src (stride/valid) -> dst (stride n_cols); enqueues only
 static int encode_rows(lcpc_b200_enc *enc, const uint32_t *src, size_t src_stride, size_t valid, uint32_t *dst,
-                       size_t n_rows, void *enc_scratch) {
+                       size_t n_rows, void *enc_scratch, const Scatter *scatter = nullptr) {
   lcpc_b200_ctx *ctx = enc->ctx;
   int nl = 0;
   cudaError_t ce;
   if (enc->kind == LCPC_B200_ENC_LIGERO) {
     ce = launch_ntt_rows(enc->field, src, src_stride, valid, dst, enc->n_cols, enc->d_roots, enc->log_n, n_rows,
-                         ctx->stream, &nl);
+                         ctx->stream, &nl, scatter);
   } else {
-    ce = expander_encode_rows(enc->code, src, src_stride, valid, dst, enc->n_cols, n_rows, enc_scratch, ctx->stream, &nl);
+    ce = expander_encode_rows(enc->code, src, src_stride, valid, dst, enc->n_cols, n_rows, enc_scratch, ctx->stream, &nl,
+                              scatter);
   }
   ctx->launches += nl;
   if (ce != cudaSuccess) return cuda_fail(ctx, ce, "encode");
@@ -365,7 +366,8 @@ static size_t enc_scratch_bytes(const lcpc_b200_enc *enc, size_t n_rows) {
 // that have landed into d_comm.  `first_ev` (optional) is recorded on the engine stream when the first
 // chunk is in.
 static int encode_rows_from_host(lcpc_b200_enc *enc, const void *src, size_t len, uint32_t *d_coeffs, uint32_t *d_comm,
-                                 size_t n_rows, void *enc_scratch, cudaEvent_t first_ev) {
+                                 size_t n_rows, void *enc_scratch, cudaEvent_t first_ev,
+                                 const Scatter *scatter = nullptr) {
   lcpc_b200_ctx *ctx = enc->ctx;
   cudaStream_t st = ctx->stream;
   const size_t B = field_bytes(enc->field), N = B / 4;
@@ -386,11 +388,63 @@ static int encode_rows_from_host(lcpc_b200_enc *enc, const void *src, size_t len
     CU(ctx, cudaEventRecord(ctx->chunk_ev[k], ctx->copy_stream));
     CU(ctx, cudaStreamWaitEvent(st, ctx->chunk_ev[k], 0));
     if (k == 0 && first_ev) CU(ctx, cudaEventRecord(first_ev, st));
+    Scatter sc;
+    if (scatter) {
+      sc = *scatter;
+      sc.row0 += r0;
+    }
     if (int rc = encode_rows(enc, d_coeffs + r0 * n_per_row * N, n_per_row, n_per_row, d_comm + r0 * enc->n_cols * N,
-                             r1 - r0, enc_scratch))
+                             r1 - r0, enc_scratch, scatter ? &sc : nullptr))
       return rc;
   }
   return LCPC_B200_OK;
+}
+
+// validate a scatter descriptor of the ABI and turn it into the kernels' by-value form
+static int make_scatter(lcpc_b200_enc *enc, const lcpc_b200_scatter *in, Scatter *out) {
+  lcpc_b200_ctx *ctx = enc->ctx;
+  if (!in || !in->starts || !in->dst || in->n_blocks == 0 || in->n_blocks > (size_t)MAX_SCATTER)
+    return fail(ctx, LCPC_B200_ERR_BAD_ARG, "scatter: 1..%d column blocks expected", MAX_SCATTER);
+  if (in->starts[0] != 0 || in->starts[in->n_blocks] != enc->n_cols)
+    return fail(ctx, LCPC_B200_ERR_BAD_ARG, "scatter: column blocks must cover [0, n_cols)");
+  out->n_blocks = (unsigned)in->n_blocks, out->row0 = in->row0;
+  for (size_t h = 0; h <= in->n_blocks; h++) {
+    if (h && in->starts[h] < in->starts[h - 1]) return fail(ctx, LCPC_B200_ERR_BAD_ARG, "scatter: starts not monotone");
+    out->starts[h] = in->starts[h];
+  }
+  for (size_t h = 0; h < in->n_blocks; h++) {
+    if (!in->dst[h] && in->starts[h + 1] > in->starts[h]) return fail(ctx, LCPC_B200_ERR_BAD_ARG, "scatter: null block %zu", h);
+    out->dst[h] = (uint32_t *)in->dst[h];
+  }
+  return LCPC_B200_OK;
+}
+
+int lcpc_b200_encode_rows_scatter_dev(lcpc_b200_enc *enc, const uint64_t *d_src, size_t src_stride, size_t valid,
+                                      uint64_t *d_tmp, size_t n_rows, const lcpc_b200_scatter *scatter) {
+  if (!enc || ((!d_src || !d_tmp) && n_rows)) return LCPC_B200_ERR_BAD_ARG;
+  lcpc_b200_ctx *ctx = enc->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (valid > enc->n_cols || valid > src_stride)
+    return fail(ctx, LCPC_B200_ERR_BAD_ARG, "valid %zu exceeds row (stride %zu, n_cols %zu)", valid, src_stride, enc->n_cols);
+  Scatter sc;
+  if (int rc = make_scatter(enc, scatter, &sc)) return rc;
+  if (int rc = bind_device(ctx)) return rc;
+  if (int rc = ensure_scratch(ctx, enc_scratch_bytes(enc, n_rows))) return rc;
+  return encode_rows(enc, (const uint32_t *)d_src, src_stride, valid, (uint32_t *)d_tmp, n_rows, ctx->scratch, &sc);
+}
+
+int lcpc_b200_encode_rows_scatter_h2d(lcpc_b200_enc *enc, const uint64_t *rows, size_t len, uint64_t *d_coeffs,
+                                      uint64_t *d_tmp, size_t n_rows, const lcpc_b200_scatter *scatter) {
+  if (!enc || !rows || !d_coeffs || !d_tmp || n_rows == 0) return LCPC_B200_ERR_BAD_ARG;
+  lcpc_b200_ctx *ctx = enc->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (len > n_rows * enc->n_per_row || len + enc->n_per_row <= n_rows * enc->n_per_row)
+    return fail(ctx, LCPC_B200_ERR_BAD_ARG, "encode_rows_scatter_h2d: %zu elements do not fill %zu rows", len, n_rows);
+  Scatter sc;
+  if (int rc = make_scatter(enc, scatter, &sc)) return rc;
+  if (int rc = bind_device(ctx)) return rc;
+  if (int rc = ensure_scratch(ctx, enc_scratch_bytes(enc, n_rows))) return rc;
+  return encode_rows_from_host(enc, rows, len, (uint32_t *)d_coeffs, (uint32_t *)d_tmp, n_rows, ctx->scratch, nullptr, &sc);
 }
 
 int lcpc_b200_encode_rows_h2d(lcpc_b200_enc *enc, const uint64_t *rows, size_t len, uint64_t *d_coeffs, uint64_t *d_dst,

@@ -6,6 +6,8 @@
 
 #include <string>
 
+#include "kernels.h"
+
 namespace lcpc {
 
 // borrowed view of one CsMat::new_csc((m, n), ptrs, idxs, data) (matgen.rs:187), host memory
@@ -28,6 +30,6 @@ size_t expander_scratch_bytes(const ExpanderCode *code, size_t n_rows);
 // are dst_stride apart and receive the full codeword.  src may equal dst.
 cudaError_t expander_encode_rows(const ExpanderCode *code, const uint32_t *src, size_t src_stride, size_t valid,
                                  uint32_t *dst, size_t dst_stride, size_t n_rows, void *scratch, cudaStream_t stream,
-                                 int *n_launches);
+                                 int *n_launches, const Scatter *scatter = nullptr);
 
 }  // namespace lcpc

@@ -16,6 +16,18 @@ inline size_t field_bytes(int field) { return 4 * (size_t)field_limbs32(field); 
 cudaError_t launch_field_op(int field, int op, uint32_t *r, const uint32_t *a, const uint32_t *b, size_t n,
                             cudaStream_t stream);
 
+// Destination of a row-block encode that feeds column-sharded hashing (the multi-GPU commit): column block
+// h = columns [starts[h], starts[h+1]) of every encoded row goes to the matrix dst[h][total rows][width_h],
+// which may live on this GPU or be a peer-mapped buffer of another GPU reached over NVLink; this call's
+// rows start at row0 of those matrices.  n_blocks == 0 means a plain row-major destination.
+constexpr int MAX_SCATTER = 16;
+struct Scatter {
+  unsigned n_blocks;
+  unsigned long long row0;
+  unsigned long long starts[MAX_SCATTER + 1];
+  uint32_t *dst[MAX_SCATTER];
+};
+
 // ---- Ligero: radix-2 DIF NTT, in-order in / bit-reversed out (fffft `fft_io_pc`) ----
 // roots: w^0 .. w^(n_cols/2-1), w = root_of_unity()^(2^(S-log2 n_cols))  (FFTPrecomp)
 // src rows hold `src_valid` leading elements (the rest of the n_cols-long row is implicit zeros) and
@@ -23,7 +35,7 @@ cudaError_t launch_field_op(int field, int op, uint32_t *r, const uint32_t *a, c
 // when src_stride == dst_stride.  Returns the number of kernels launched through *n_launches.
 cudaError_t launch_ntt_rows(int field, const uint32_t *src, size_t src_stride, size_t src_valid, uint32_t *dst,
                             size_t dst_stride, const uint32_t *roots, unsigned log_n, size_t n_rows,
-                            cudaStream_t stream, int *n_launches);
+                            cudaStream_t stream, int *n_launches, const Scatter *scatter = nullptr);
 // powers of w into roots[0..half): roots[i] = w^i (Montgomery); `w` points at 2N limbs: [w | R mod p]
 cudaError_t launch_root_table(int field, uint32_t *roots, const uint32_t *w, size_t half, cudaStream_t stream);
 

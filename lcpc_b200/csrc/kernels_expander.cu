@@ -206,12 +206,14 @@ __device__ __forceinline__ void stv(uint32_t *p, const uint32_t (&v)[N]) {
   }
 }
 
-// tiled transpose of elements: dst[c * dst_ld + r] = src[r * src_ld + c], r < n_r, c < n_c
+// tiled transpose of elements: dst[c * dst_ld + r] = src[r * src_ld + c], r < n_r, c < n_c.  With a scatter
+// descriptor (the final transpose of a multi-GPU row block) destination row c, position r goes to column
+// block h(r)'s matrix instead: sc.dst[h][(row0 + c) * width_h + (r - start_h)].
 constexpr int TT = 32;
 template <int N>
 __global__ void __launch_bounds__(256)
 transpose_kernel(const uint32_t *__restrict__ src, size_t src_ld, uint32_t *__restrict__ dst, size_t dst_ld,
-                 size_t n_r, size_t n_c) {
+                 size_t n_r, size_t n_c, Scatter sc) {
   __shared__ uint32_t tile[N][TT][TT + 1];
   const size_t c0 = (size_t)blockIdx.x * TT, r0 = (size_t)blockIdx.y * TT;
   const unsigned tx = threadIdx.x % TT, ty = threadIdx.x / TT;  // 32 x 8
@@ -231,7 +233,14 @@ transpose_kernel(const uint32_t *__restrict__ src, size_t src_ld, uint32_t *__re
       uint32_t v[N];
 #pragma unroll
       for (int l = 0; l < N; l++) v[l] = tile[l][tx][cc];
-      stv<N>(dst + (cidx * dst_ld + r) * N, v);
+      uint32_t *out = dst + (cidx * dst_ld + r) * N;
+      if (sc.n_blocks) {
+        unsigned h = 0;
+        while (h + 1 < sc.n_blocks && r >= sc.starts[h + 1]) h++;
+        const size_t start = sc.starts[h], width = sc.starts[h + 1] - start;
+        out = sc.dst[h] + ((sc.row0 + cidx) * width + (r - start)) * N;
+      }
+      stv<N>(out, v);
     }
   }
 }
@@ -295,7 +304,7 @@ template <int FID> __global__ void one_mont_kernel(uint32_t *out) {
 template <int FID>
 static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_t src_stride, size_t valid,
                                uint32_t *dst, size_t dst_stride, size_t n_rows, void *scratch, cudaStream_t st,
-                               int *n_launches) {
+                               int *n_launches, const Scatter *scatter) {
   using F = Field<FID>;
   constexpr int N = F::N;
   if (n_launches) *n_launches = 0;
@@ -307,7 +316,9 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
   // coefficients -> W[0 .. n_in)
   {
     dim3 grid((unsigned)((c->n_in + TT - 1) / TT), (unsigned)((n_rows + TT - 1) / TT));
-    transpose_kernel<N><<<grid, 256, 0, st>>>(src, src_stride, W, n_rows, n_rows, c->n_in);
+    Scatter none;
+    none.n_blocks = 0;
+    transpose_kernel<N><<<grid, 256, 0, st>>>(src, src_stride, W, n_rows, n_rows, c->n_in, none);
     launches++;
   }
   for (const ExpanderOp &op : c->ops) {
@@ -335,7 +346,10 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
   // W -> row-major codewords
   {
     dim3 grid((unsigned)((n_rows + TT - 1) / TT), (unsigned)((c->n_cols + TT - 1) / TT));
-    transpose_kernel<N><<<grid, 256, 0, st>>>(W, n_rows, dst, dst_stride, c->n_cols, n_rows);
+    Scatter sc;
+    sc.n_blocks = 0;
+    if (scatter && scatter->n_blocks) sc = *scatter;
+    transpose_kernel<N><<<grid, 256, 0, st>>>(W, n_rows, dst, dst_stride, c->n_cols, n_rows, sc);
     launches++;
   }
   if (n_launches) *n_launches = launches;
@@ -344,12 +358,12 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
 
 cudaError_t expander_encode_rows(const ExpanderCode *c, const uint32_t *src, size_t src_stride, size_t valid,
                                  uint32_t *dst, size_t dst_stride, size_t n_rows, void *scratch, cudaStream_t st,
-                                 int *n_launches) {
+                                 int *n_launches, const Scatter *scatter) {
   switch (c->field) {
-    case FT63: return encode_impl<FT63>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches);
-    case FT127: return encode_impl<FT127>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches);
-    case FT191: return encode_impl<FT191>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches);
-    case FT255: return encode_impl<FT255>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches);
+    case FT63: return encode_impl<FT63>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches, scatter);
+    case FT127: return encode_impl<FT127>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches, scatter);
+    case FT191: return encode_impl<FT191>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches, scatter);
+    case FT255: return encode_impl<FT255>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches, scatter);
     default: return cudaErrorInvalidValue;
   }
 }

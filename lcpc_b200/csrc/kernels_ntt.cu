@@ -215,6 +215,7 @@ struct NttPass {
   unsigned logC;       // log2 of adjacent points (or sub-transforms) per tile
   unsigned tiles_per_row_log;  // log2(n / (2^S * C))
   size_t src_stride, src_valid, dst_stride;
+  Scatter sc;          // last pass only: store straight into per-column-block (possibly peer) matrices
 };
 
 constexpr int NTT_THREADS = 256;
@@ -384,15 +385,22 @@ ntt_pass_kernel(const uint32_t *__restrict__ src, uint32_t *dst, const uint32_t 
     const unsigned t = (e >> g.tshift) & g.tmask, c = (e >> g.cshift) & g.cmask;
     const size_t j = g.last ? g.base + e : g.base + ((size_t)t << g.log_stride) + c;
     const uint32_t *q = smem + ((size_t)pl * (g.tile + SmemLayout<N>::PLANE_PAD) + swz(e)) * PW;
-    if constexpr (PW == 4) reinterpret_cast<uint4 *>(drow + j * N)[pl] = *reinterpret_cast<const uint4 *>(q);
-    else reinterpret_cast<uint2 *>(drow + j * N)[pl] = *reinterpret_cast<const uint2 *>(q);
+    uint32_t *out = drow + j * N;
+    if (p.sc.n_blocks) {  // column block of position j, then (global row, local column) inside that block's matrix
+      unsigned h = 0;
+      while (h + 1 < p.sc.n_blocks && j >= p.sc.starts[h + 1]) h++;
+      const size_t start = p.sc.starts[h], width = p.sc.starts[h + 1] - start;
+      out = p.sc.dst[h] + ((p.sc.row0 + row) * width + (j - start)) * N;
+    }
+    if constexpr (PW == 4) reinterpret_cast<uint4 *>(out)[pl] = *reinterpret_cast<const uint4 *>(q);
+    else reinterpret_cast<uint2 *>(out)[pl] = *reinterpret_cast<const uint2 *>(q);
   }
 }
 
 template <int FID>
 static cudaError_t ntt_rows_impl(const uint32_t *src, size_t src_stride, size_t src_valid, uint32_t *dst,
                                  size_t dst_stride, const uint32_t *roots, unsigned log_n, size_t n_rows,
-                                 cudaStream_t stream, int *n_launches) {
+                                 cudaStream_t stream, int *n_launches, const Scatter *scatter) {
   using F = Field<FID>;
   static bool attr_set = false;
   constexpr unsigned LOG_TILE = 11;  // 2048 elements: 64 KiB for Ft255
@@ -406,6 +414,7 @@ static cudaError_t ntt_rows_impl(const uint32_t *src, size_t src_stride, size_t 
   if (n_launches) *n_launches = 0;
   if (n_rows == 0) return cudaSuccess;
   if (log_n == 0) {  // length-1 transform: identity
+    if (scatter && scatter->n_blocks) return cudaErrorInvalidValue;
     if (src != dst)
       return cudaMemcpy2DAsync(dst, dst_stride * F::BYTES, src, src_stride * F::BYTES, F::BYTES, n_rows,
                                cudaMemcpyDeviceToDevice, stream);
@@ -429,6 +438,8 @@ static cudaError_t ntt_rows_impl(const uint32_t *src, size_t src_stride, size_t 
     p.logC = logC;
     p.tiles_per_row_log = log_n - S - logC;
     p.src_stride = cur_stride, p.src_valid = cur_valid, p.dst_stride = dst_stride;
+    p.sc.n_blocks = 0;
+    if (last && scatter && scatter->n_blocks) p.sc = *scatter;
     size_t grid = n_rows << p.tiles_per_row_log;
     if (grid > 0x7fffffffu) return cudaErrorInvalidValue;
     size_t smem = SmemLayout<F::N>::bytes(1u << (S + logC));
@@ -444,12 +455,12 @@ static cudaError_t ntt_rows_impl(const uint32_t *src, size_t src_stride, size_t 
 
 cudaError_t launch_ntt_rows(int field, const uint32_t *src, size_t src_stride, size_t src_valid, uint32_t *dst,
                             size_t dst_stride, const uint32_t *roots, unsigned log_n, size_t n_rows,
-                            cudaStream_t stream, int *n_launches) {
+                            cudaStream_t stream, int *n_launches, const Scatter *scatter) {
   switch (field) {
-    case FT63: return ntt_rows_impl<FT63>(src, src_stride, src_valid, dst, dst_stride, roots, log_n, n_rows, stream, n_launches);
-    case FT127: return ntt_rows_impl<FT127>(src, src_stride, src_valid, dst, dst_stride, roots, log_n, n_rows, stream, n_launches);
-    case FT191: return ntt_rows_impl<FT191>(src, src_stride, src_valid, dst, dst_stride, roots, log_n, n_rows, stream, n_launches);
-    case FT255: return ntt_rows_impl<FT255>(src, src_stride, src_valid, dst, dst_stride, roots, log_n, n_rows, stream, n_launches);
+    case FT63: return ntt_rows_impl<FT63>(src, src_stride, src_valid, dst, dst_stride, roots, log_n, n_rows, stream, n_launches, scatter);
+    case FT127: return ntt_rows_impl<FT127>(src, src_stride, src_valid, dst, dst_stride, roots, log_n, n_rows, stream, n_launches, scatter);
+    case FT191: return ntt_rows_impl<FT191>(src, src_stride, src_valid, dst, dst_stride, roots, log_n, n_rows, stream, n_launches, scatter);
+    case FT255: return ntt_rows_impl<FT255>(src, src_stride, src_valid, dst, dst_stride, roots, log_n, n_rows, stream, n_launches, scatter);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -97,6 +97,23 @@ class CudaOps:
                                                      C.c_void_p(coeffs.data_ptr()), C.c_void_p(comm_rows.data_ptr()),
                                                      _sz(n_rows)), self.ctx)
 
+    def encode_rows_scatter(self, src, n_rows, n_per_row, tmp, starts, ptrs, row0, coeffs=None, n_elems=None):
+        """Row-block encode whose last pass stores per column block: block h -> the matrix at device
+        address ptrs[h] (local or peer-mapped).  `src` is a device tensor, or -- with `coeffs` (device
+        staging) and `n_elems` -- a pinned host tensor whose PCIe copy is overlapped with the encode."""
+        starts = np.ascontiguousarray(starts, dtype=np.uint64)
+        ptrs = np.ascontiguousarray(ptrs, dtype=np.uint64)
+        sc = _cabi.Scatter(len(ptrs), starts.ctypes.data, ptrs.ctypes.data, int(row0))
+        lib = _cabi.lib()
+        if coeffs is None:
+            _check(lib.lcpc_b200_encode_rows_scatter_dev(self.enc._h, C.c_void_p(src.data_ptr()), _sz(n_per_row),
+                                                         _sz(n_per_row), C.c_void_p(tmp.data_ptr()), _sz(n_rows),
+                                                         C.byref(sc)), self.ctx)
+        else:
+            _check(lib.lcpc_b200_encode_rows_scatter_h2d(self.enc._h, C.c_void_p(src.data_ptr()), _sz(n_elems),
+                                                         C.c_void_p(coeffs.data_ptr()), C.c_void_p(tmp.data_ptr()),
+                                                         _sz(n_rows), C.byref(sc)), self.ctx)
+
     def pack(self, comm_rows, n_rows, n_cols, n_blocks, starts, send):
         _check(_cabi.lib().lcpc_b200_pack_column_blocks_dev(self.ctx._h, self.field, C.c_void_p(comm_rows.data_ptr()),
                                                             _sz(n_rows), _sz(n_cols), _sz(n_blocks),
@@ -118,7 +135,9 @@ class DistributedCommit:
     world_size-2 gloo tests exercise it on CPU with a checker backend.
     """
 
-    def __init__(self, enc, n_coeffs: int, group=None, ops=None):
+    def __init__(self, enc, n_coeffs: int, group=None, ops=None, transport=None):
+        import os
+
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -139,7 +158,38 @@ class DistributedCommit:
         self.d_coeffs = torch.zeros(max(1, self.my_rows * n_per_row * L), dtype=i64, device=dev)
         self.d_comm_rows = torch.empty(max(1, self.my_rows * n_cols * L), dtype=i64, device=dev)
         self.d_send = torch.empty(max(1, self.my_rows * n_cols * L), dtype=i64, device=dev)
-        self.d_recv = torch.empty(max(1, n_rows * self.my_cols * L), dtype=i64, device=dev)
+        # how encoded row blocks reach the column owners:
+        #   "p2p"    the encode's last pass stores straight into every owner's receive matrix through
+        #            peer-mapped (symmetric) memory over NVLink -- compute and exchange are one kernel
+        #   "nccl"   the last pass stores per-destination tiles into a local send buffer (fused pack), then one
+        #            all_to_all_single
+        #   "staged" row-major encode + pack kernel + all_to_all_single (backends without the scatter store)
+        want = transport or os.environ.get("LCPC_B200_TRANSPORT", "auto")
+        self.max_cols = max(p.col_lo[h + 1] - p.col_lo[h] for h in range(self.world))
+        self.symm = None
+        self.transport = "staged"
+        if hasattr(self.ops, "encode_rows_scatter"):
+            self.transport = "nccl"
+            if want in ("auto", "p2p") and self.world > 1:
+                try:
+                    import torch.distributed._symmetric_memory as symm_mem
+                    g = group if group is not None else dist.group.WORLD
+                    buf = symm_mem.empty(max(1, n_rows * self.max_cols * L), dtype=i64, device=dev)
+                    self.symm = symm_mem.rendezvous(buf, g.group_name)
+                    self.d_recv = buf
+                    self.peer_ptrs = [int(x) for x in self.symm.buffer_ptrs]
+                    self.transport = "p2p"
+                except Exception as e:  # no peer access / allocator unavailable: NCCL moves the tiles instead
+                    if want == "p2p":
+                        raise
+                    self.symm_error = repr(e)
+            # every rank must take the same path (the collectives differ)
+            flag = torch.tensor([1 if self.transport == "p2p" else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 0:
+                self.transport, self.symm = "nccl", None
+        if self.transport != "p2p":
+            self.d_recv = torch.empty(max(1, n_rows * self.my_cols * L), dtype=i64, device=dev)
         self.in_splits = [self.my_rows * (p.col_lo[h + 1] - p.col_lo[h]) * L for h in range(self.world)]
         self.out_splits = [(p.row_lo[g + 1] - p.row_lo[g]) * self.my_cols * L for g in range(self.world)]
         self.d_starts = torch.tensor(p.col_lo, dtype=i64, device=dev)
@@ -193,17 +243,34 @@ class DistributedCommit:
         `load_rows_from_host` are encoded."""
         dist, p, ops = self.dist, self.plan, self.ops
         with ops.on_stream():
-            if self.my_rows and host_rows is not None and hasattr(ops, "encode_rows_h2d"):
-                ops.encode_rows_h2d(host_rows, host_rows.numel() // self.L, self.d_coeffs, self.d_comm_rows, self.my_rows)
-                ops.pack(self.d_comm_rows, self.my_rows, p.n_cols, self.world, self.d_starts, self.d_send)
-            elif self.my_rows:
-                if host_rows is not None:
-                    self.load_rows_from_host(host_rows)
-                ops.encode_rows(self.d_coeffs, self.d_comm_rows, self.my_rows, p.n_per_row)
-                ops.pack(self.d_comm_rows, self.my_rows, p.n_cols, self.world, self.d_starts, self.d_send)
-            n_send, n_recv = sum(self.in_splits), sum(self.out_splits)
-            dist.all_to_all_single(self.d_recv[:n_recv], self.d_send[:n_send], self.out_splits, self.in_splits,
-                                   group=self.group)
+            if self.transport == "staged":
+                if self.my_rows:
+                    if host_rows is not None:
+                        self.load_rows_from_host(host_rows)
+                    ops.encode_rows(self.d_coeffs, self.d_comm_rows, self.my_rows, p.n_per_row)
+                    ops.pack(self.d_comm_rows, self.my_rows, p.n_cols, self.world, self.d_starts, self.d_send)
+            else:
+                if self.transport == "p2p":
+                    # owners must be done reading the previous commit's columns before anyone overwrites them
+                    self.symm.barrier(channel=0)
+                    ptrs, row0 = self.peer_ptrs, p.row_lo[self.rank]
+                else:  # tile h of the send buffer = [my_rows][width_h] at element offset my_rows * col_lo[h]
+                    base = self.d_send.data_ptr()
+                    ptrs = [base + self.my_rows * p.col_lo[h] * self.L * 8 for h in range(self.world)]
+                    row0 = 0
+                if self.my_rows:
+                    if host_rows is not None:
+                        ops.encode_rows_scatter(host_rows, self.my_rows, p.n_per_row, self.d_comm_rows, p.col_lo, ptrs,
+                                                row0, coeffs=self.d_coeffs, n_elems=host_rows.numel() // self.L)
+                    else:
+                        ops.encode_rows_scatter(self.d_coeffs, self.my_rows, p.n_per_row, self.d_comm_rows, p.col_lo,
+                                                ptrs, row0)
+            if self.transport == "p2p":
+                self.symm.barrier(channel=1)  # every rank's stores into this rank's matrix have landed
+            else:
+                n_send, n_recv = sum(self.in_splits), sum(self.out_splits)
+                dist.all_to_all_single(self.d_recv[:n_recv], self.d_send[:n_send], self.out_splits, self.in_splits,
+                                       group=self.group)
             if self.my_cols:
                 ops.hash_columns(self.d_recv, p.n_rows, self.my_cols, self.d_forest)
                 if self.sub_layers:
@@ -297,7 +364,7 @@ def bench_distributed(args, ctx, enc, field, n, synthetic_coeffs):
     ms_per_step = float(ms.item()) / args.steps
     e2e_s = float(e2e.item())
     return dict(value=n / (ms_per_step * 1e-3), ms_per_step=ms_per_step, gpu_launches=int(launches.item()), clocks=clocks,
-                root=root0.root.hex(), dominant=None,
+                root=root0.root.hex(), dominant=None, transport=dc.transport,
                 e2e={"value": n / e2e_s, "unit": "field-elts/s", "h2d_bytes_per_step": int(n * 8 * L),
                      "d2h_bytes_per_step": 32 * world, "ms_per_step": e2e_s * 1e3,
                      "mode": "row blocks from pinned host memory on every rank; every rank reads back the LcRoot"})

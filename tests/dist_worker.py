@@ -81,6 +81,7 @@ class OracleOps:
 
 def main():
     backend, kind, field, n, seed = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
+    transport = sys.argv[6] if len(sys.argv) > 6 else None
     rank = int(os.environ["RANK"])
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if backend == "nccl":
@@ -94,7 +95,7 @@ def main():
         import lcpc_b200 as P
         ctx = P.Context(local_rank)
         enc = P.LigeroEncoding(field, n, ctx=ctx) if kind == "ligero" else P.SdigEncoding(field, n, seed=seed, ctx=ctx)
-        dc = D.DistributedCommit(enc, n)
+        dc = D.DistributedCommit(enc, n, transport=transport)
     else:
         enc = OracleEnc(oenc)
         dc = D.DistributedCommit(enc, n, ops=OracleOps(enc))
@@ -108,10 +109,15 @@ def main():
     comm = oc["comm"].reshape(p.n_rows, p.n_cols, -1)
     ok_cols = bool((dc.local_columns() == comm[:, c0:c1]).all())
     ok_leaves = bool((dc.local_leaves() == oc["hashes"][c0:c1]).all())
-    dc.run()  # a second run into the same buffers must reproduce the root
+    if backend == "nccl":  # second run straight from pinned host rows (PCIe copy overlapped with the encode)
+        rows = x[r0 * p.n_per_row:min(r1 * p.n_per_row, n)]
+        host = torch.from_numpy(np.ascontiguousarray(rows).view(np.int64).reshape(-1)).pin_memory()
+        dc.run(host if host.numel() else None)
+    else:
+        dc.run()  # a second run into the same buffers must reproduce the root
     again = dc.get_root().root
     print(json.dumps(dict(rank=rank, root=root.hex(), want=oc["root"].hex(), ok_cols=ok_cols, ok_leaves=ok_leaves,
-                          again=again.hex(), rows=[r0, r1], cols=[c0, c1])), flush=True)
+                          again=again.hex(), rows=[r0, r1], cols=[c0, c1], transport=dc.transport)), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -25,12 +25,24 @@ def free_port():
     return port
 
 
-def run_workers(world, backend, kind, field, n, seed=0, timeout=600):
+def run_workers(world, backend, kind, field, n, seed=0, timeout=600, transport=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
            os.path.join(HERE, "dist_worker.py"), backend, kind, str(field), str(n), str(seed)]
+    if transport:
+        cmd.append(transport)
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
-    lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+    # ranks share one pipe: two records can end up on one line, so decode objects one after another
+    lines, dec = [], json.JSONDecoder()
+    for l in out.stdout.splitlines():
+        pos = l.find("{")
+        while pos >= 0:
+            try:
+                obj, end = dec.raw_decode(l, pos)
+            except json.JSONDecodeError:
+                break
+            lines.append(obj)
+            pos = l.find("{", end)
     assert out.returncode == 0 and len(lines) == world, out.stderr[-3000:]
     return sorted(lines, key=lambda d: d["rank"])
 
@@ -82,16 +94,32 @@ def _n_gpus():
 
 
 @pytest.mark.gpu
-def test_nccl_ligero_ft255():
+@pytest.mark.parametrize("transport", ["auto", "nccl"])
+def test_nccl_ligero_ft255(transport):
+    """auto = peer-mapped stores from the encode's last pass when the GPUs allow it; nccl = fused pack + all-to-all"""
     n = _n_gpus()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
-    check(run_workers(min(n, 8), "nccl", "ligero", 4, 1 << 16))
+    lines = run_workers(min(n, 8), "nccl", "ligero", 4, 1 << 16, transport=transport)
+    check(lines)
+    assert len({d["transport"] for d in lines}) == 1
+    if transport == "nccl":
+        assert lines[0]["transport"] == "nccl"
 
 
 @pytest.mark.gpu
-def test_nccl_brakedown_ft127():
+@pytest.mark.parametrize("transport", ["auto", "nccl"])
+def test_nccl_brakedown_ft127(transport):
     n = _n_gpus()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
-    check(run_workers(min(n, 8), "nccl", "sdig", 2, 1 << 15, seed=0))
+    check(run_workers(min(n, 8), "nccl", "sdig", 2, 1 << 15, seed=0, transport=transport))
+
+
+@pytest.mark.gpu
+def test_nccl_ligero_ft255_2_20_multi_pass():
+    """2^15-point rows: the scatter store sits in the second NTT pass"""
+    n = _n_gpus()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    check(run_workers(min(n, 8), "nccl", "ligero", 4, 1 << 20))
