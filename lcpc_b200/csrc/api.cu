@@ -565,6 +565,16 @@ static int commit_run(lcpc_b200_commit *c, const void *src, size_t len, cudaMemc
   uint64_t l0 = ctx->launches;
   if (kind == cudaMemcpyHostToDevice && c->n_rows > 1) {
     if (int rc = encode_rows_from_host(enc, src, len, c->d_coeffs, c->d_comm, c->n_rows, c->d_enc_scratch, c->ev[1])) return rc;
+  } else if (kind == cudaMemcpyDeviceToDevice && enc->kind == LCPC_B200_ENC_LIGERO && padded == len && enc->log_n > 0 &&
+             (const void *)c->d_coeffs != src) {
+    // pad + copy (:636-645) folded into the first transform pass: it reads the caller's coefficient rows and
+    // stores the commit's own copy on the way
+    CU(ctx, cudaEventRecord(c->ev[1], st));
+    int nl = 0;
+    cudaError_t ce = launch_ntt_rows(enc->field, (const uint32_t *)src, c->n_per_row, c->n_per_row, c->d_comm, c->n_cols,
+                                     enc->d_roots, enc->log_n, c->n_rows, st, &nl, nullptr, c->d_coeffs, c->n_per_row);
+    ctx->launches += nl;
+    if (ce != cudaSuccess) return cuda_fail(ctx, ce, "encode");
   } else {
     // pad + copy (lcpc-2d/src/lib.rs:636-645): coeffs = coeffs_in || zeros
     CU(ctx, cudaMemcpyAsync(c->d_coeffs, src, len * B, kind, st));

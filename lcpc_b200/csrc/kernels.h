@@ -33,9 +33,12 @@ struct Scatter {
 // src rows hold `src_valid` leading elements (the rest of the n_cols-long row is implicit zeros) and
 // are `src_stride` elements apart; dst rows are `dst_stride` apart.  src == dst (in place) is allowed
 // when src_stride == dst_stride.  Returns the number of kernels launched through *n_launches.
+// copy_dst (optional): the first pass also stores every source element it reads to copy_dst, rows
+// copy_stride apart (commit()'s private copy of the coefficients without a second read).
 cudaError_t launch_ntt_rows(int field, const uint32_t *src, size_t src_stride, size_t src_valid, uint32_t *dst,
                             size_t dst_stride, const uint32_t *roots, unsigned log_n, size_t n_rows,
-                            cudaStream_t stream, int *n_launches, const Scatter *scatter = nullptr);
+                            cudaStream_t stream, int *n_launches, const Scatter *scatter = nullptr,
+                            uint32_t *copy_dst = nullptr, size_t copy_stride = 0);
 // powers of w into roots[0..half): roots[i] = w^i (Montgomery); `w` points at 2N limbs: [w | R mod p]
 cudaError_t launch_root_table(int field, uint32_t *roots, const uint32_t *w, size_t half, cudaStream_t stream);
 

@@ -216,6 +216,8 @@ struct NttPass {
   unsigned tiles_per_row_log;  // log2(n / (2^S * C))
   size_t src_stride, src_valid, dst_stride;
   Scatter sc;          // last pass only: store straight into per-column-block (possibly peer) matrices
+  uint32_t *copy_dst;  // first pass only (optional): every source element read is also stored here, rows
+  size_t copy_stride;  // copy_stride apart -- commit()'s own copy of the coefficients for free
 };
 
 constexpr int NTT_THREADS = 256;
@@ -352,11 +354,17 @@ ntt_pass_kernel(const uint32_t *__restrict__ src, uint32_t *dst, const uint32_t 
     uint32_t *q = smem + ((size_t)pl * (g.tile + SmemLayout<N>::PLANE_PAD) + swz(e)) * PW;
     if constexpr (PW == 4) {
       uint4 v = make_uint4(0, 0, 0, 0);
-      if (j < p.src_valid) v = __ldg(reinterpret_cast<const uint4 *>(srow + j * N) + pl);
+      if (j < p.src_valid) {
+        v = __ldg(reinterpret_cast<const uint4 *>(srow + j * N) + pl);
+        if (p.copy_dst) reinterpret_cast<uint4 *>(p.copy_dst + (row * p.copy_stride + j) * N)[pl] = v;
+      }
       *reinterpret_cast<uint4 *>(q) = v;
     } else {
       uint2 v = make_uint2(0, 0);
-      if (j < p.src_valid) v = __ldg(reinterpret_cast<const uint2 *>(srow + j * N) + pl);
+      if (j < p.src_valid) {
+        v = __ldg(reinterpret_cast<const uint2 *>(srow + j * N) + pl);
+        if (p.copy_dst) reinterpret_cast<uint2 *>(p.copy_dst + (row * p.copy_stride + j) * N)[pl] = v;
+      }
       *reinterpret_cast<uint2 *>(q) = v;
     }
   }
@@ -400,7 +408,8 @@ ntt_pass_kernel(const uint32_t *__restrict__ src, uint32_t *dst, const uint32_t 
 template <int FID>
 static cudaError_t ntt_rows_impl(const uint32_t *src, size_t src_stride, size_t src_valid, uint32_t *dst,
                                  size_t dst_stride, const uint32_t *roots, unsigned log_n, size_t n_rows,
-                                 cudaStream_t stream, int *n_launches, const Scatter *scatter) {
+                                 cudaStream_t stream, int *n_launches, const Scatter *scatter, uint32_t *copy_dst,
+                                 size_t copy_stride) {
   using F = Field<FID>;
   static bool attr_set = false;
   constexpr unsigned LOG_TILE = 11;  // 2048 elements: 64 KiB for Ft255
@@ -414,7 +423,7 @@ static cudaError_t ntt_rows_impl(const uint32_t *src, size_t src_stride, size_t 
   if (n_launches) *n_launches = 0;
   if (n_rows == 0) return cudaSuccess;
   if (log_n == 0) {  // length-1 transform: identity
-    if (scatter && scatter->n_blocks) return cudaErrorInvalidValue;
+    if ((scatter && scatter->n_blocks) || copy_dst) return cudaErrorInvalidValue;
     if (src != dst)
       return cudaMemcpy2DAsync(dst, dst_stride * F::BYTES, src, src_stride * F::BYTES, F::BYTES, n_rows,
                                cudaMemcpyDeviceToDevice, stream);
@@ -440,6 +449,7 @@ static cudaError_t ntt_rows_impl(const uint32_t *src, size_t src_stride, size_t 
     p.src_stride = cur_stride, p.src_valid = cur_valid, p.dst_stride = dst_stride;
     p.sc.n_blocks = 0;
     if (last && scatter && scatter->n_blocks) p.sc = *scatter;
+    p.copy_dst = ip == 0 ? copy_dst : nullptr, p.copy_stride = copy_stride;
     size_t grid = n_rows << p.tiles_per_row_log;
     if (grid > 0x7fffffffu) return cudaErrorInvalidValue;
     size_t smem = SmemLayout<F::N>::bytes(1u << (S + logC));
@@ -455,12 +465,13 @@ static cudaError_t ntt_rows_impl(const uint32_t *src, size_t src_stride, size_t 
 
 cudaError_t launch_ntt_rows(int field, const uint32_t *src, size_t src_stride, size_t src_valid, uint32_t *dst,
                             size_t dst_stride, const uint32_t *roots, unsigned log_n, size_t n_rows,
-                            cudaStream_t stream, int *n_launches, const Scatter *scatter) {
+                            cudaStream_t stream, int *n_launches, const Scatter *scatter, uint32_t *copy_dst,
+                            size_t copy_stride) {
   switch (field) {
-    case FT63: return ntt_rows_impl<FT63>(src, src_stride, src_valid, dst, dst_stride, roots, log_n, n_rows, stream, n_launches, scatter);
-    case FT127: return ntt_rows_impl<FT127>(src, src_stride, src_valid, dst, dst_stride, roots, log_n, n_rows, stream, n_launches, scatter);
-    case FT191: return ntt_rows_impl<FT191>(src, src_stride, src_valid, dst, dst_stride, roots, log_n, n_rows, stream, n_launches, scatter);
-    case FT255: return ntt_rows_impl<FT255>(src, src_stride, src_valid, dst, dst_stride, roots, log_n, n_rows, stream, n_launches, scatter);
+    case FT63: return ntt_rows_impl<FT63>(src, src_stride, src_valid, dst, dst_stride, roots, log_n, n_rows, stream, n_launches, scatter, copy_dst, copy_stride);
+    case FT127: return ntt_rows_impl<FT127>(src, src_stride, src_valid, dst, dst_stride, roots, log_n, n_rows, stream, n_launches, scatter, copy_dst, copy_stride);
+    case FT191: return ntt_rows_impl<FT191>(src, src_stride, src_valid, dst, dst_stride, roots, log_n, n_rows, stream, n_launches, scatter, copy_dst, copy_stride);
+    case FT255: return ntt_rows_impl<FT255>(src, src_stride, src_valid, dst, dst_stride, roots, log_n, n_rows, stream, n_launches, scatter, copy_dst, copy_stride);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -337,3 +337,30 @@ def test_rerun_and_launch_counter():
     assert r0 != r1 and r1.root == O.Encoding.ligero(field, length).commit(x1)["root"]
     c.rerun(x0)
     assert c.get_root() == r0
+
+
+@pytest.mark.parametrize("kind,field,length", [("ligero", P.FT255, 1 << 16), ("ligero", P.FT255, 1 << 20),
+                                               ("ligero", P.FT127, (1 << 15) - 77), ("ligero", P.FT63, 1 << 13),
+                                               ("sdig", P.FT127, 1 << 14)])
+def test_commit_from_device_memory(kind, field, length):
+    """commit_new_dev / commit_rerun_dev (coefficients already in HBM: the roofline-timed region of bench.py).
+    For Ligero with a full last row the commit's own copy of the coefficients is written by the first
+    transform pass; a ragged length takes the copy + pad route.  Both must give the oracle's LcCommit."""
+    import torch
+    if kind == "ligero":
+        enc, oenc = P.LigeroEncoding(field, length), O.Encoding.ligero(field, length)
+    else:
+        enc, oenc = P.SdigEncoding(field, length, seed=4), O.Encoding.sdig(field, length, seed=4)
+    x0, x1 = O.random_elems(field, length, seed=31), O.random_elems(field, length, seed=32)
+    dev = torch.device("cuda", enc.ctx.device)
+    d0 = torch.from_numpy(x0.view(np.int64)).to(dev)
+    d1 = torch.from_numpy(x1.view(np.int64)).to(dev)
+    torch.cuda.synchronize()
+    c = P.LcCommit.commit_device(d0.data_ptr(), length, enc)
+    for x, d in ((x0, None), (x1, d1), (x0, d0)):
+        if d is not None:
+            c.rerun_device(d.data_ptr(), length)
+            enc.ctx.synchronize()
+        oc = oenc.commit(x)
+        assert c.get_root().root == oc["root"]
+        assert (c.coeffs == oc["coeffs"]).all() and (c.comm == oc["comm"]).all() and (c.hashes == oc["hashes"]).all()
