@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "liblcpc_b200.so")
+# LCPC_B200_LIB selects another build of the same library (A/B tuning builds); default: the in-tree one
+LIB_PATH = os.environ.get("LCPC_B200_LIB") or os.path.join(_HERE, "lib", "liblcpc_b200.so")
 
 OK = 0
 ERR_BAD_ARG, ERR_TOO_BIG, ERR_ENCODE, ERR_CUDA, ERR_OOM, ERR_COLUMN, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6, -7

@@ -67,6 +67,9 @@ __device__ __constant__ uint32_t kModulusLimbs[5][8] = {
 // quotient digit is produced by an ALU negate, ptxas 12.9 splits every dependent IMAD.WIDE.U32.X into
 // IMAD.X + IMAD.HI.U32.X (twice the FMA-pipe work); produced by an IMAD it keeps them fused.
 __device__ __constant__ uint32_t kMontInv32 = 0xffffffffu;
+// a zero ptxas cannot see through (A/B knob LCPC_OPAQUE_ZERO): `x + 0 + carry` written against it has to stay
+// a three-operand add on the ALU pipe instead of becoming IMAD.X on the multiplier pipe
+__device__ __constant__ uint32_t kZero32 = 0u;
 
 // ---- carry-flag primitives (PTX extended-precision integer arithmetic) ----
 // Each statement is `asm volatile` so NVVM keeps them in program order; ptxas tracks CC itself.
@@ -76,6 +79,14 @@ __device__ __constant__ uint32_t kMontInv32 = 0xffffffffu;
 LCPC_DEV void add_cc(uint32_t &d, uint32_t a, uint32_t b) { asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
 LCPC_DEV void addc_cc(uint32_t &d, uint32_t a, uint32_t b) { asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
 LCPC_DEV void addc(uint32_t &d, uint32_t a, uint32_t b) { asm volatile("addc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+// d += carry
+LCPC_DEV void add_carry(uint32_t &d) {
+#if defined(LCPC_OPAQUE_ZERO)
+  asm volatile("addc.u32 %0, %0, %1;" : "+r"(d) : "r"(kZero32));
+#else
+  asm volatile("addc.u32 %0, %0, 0;" : "+r"(d));
+#endif
+}
 LCPC_DEV void sub_cc(uint32_t &d, uint32_t a, uint32_t b) { asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
 LCPC_DEV void subc_cc(uint32_t &d, uint32_t a, uint32_t b) { asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
 LCPC_DEV void subc(uint32_t &d, uint32_t a, uint32_t b) { asm volatile("subc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
@@ -103,6 +114,7 @@ namespace hostcc { inline thread_local uint32_t cf = 0; }
 inline void add_cc(uint32_t &d, uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b; d = (uint32_t)s; hostcc::cf = (uint32_t)(s >> 32); }
 inline void addc_cc(uint32_t &d, uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b + hostcc::cf; d = (uint32_t)s; hostcc::cf = (uint32_t)(s >> 32); }
 inline void addc(uint32_t &d, uint32_t a, uint32_t b) { d = a + b + hostcc::cf; }
+inline void add_carry(uint32_t &d) { d = d + hostcc::cf; }
 inline void sub_cc(uint32_t &d, uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a - b; d = (uint32_t)s; hostcc::cf = (uint32_t)(s >> 63); }
 inline void subc_cc(uint32_t &d, uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a - b - hostcc::cf; d = (uint32_t)s; hostcc::cf = (uint32_t)(s >> 63); }
 inline void subc(uint32_t &d, uint32_t a, uint32_t b) { d = a - b - hostcc::cf; }
@@ -216,7 +228,7 @@ template <int FID> struct Field {
         mad_wide_cc(X[0], X[1], a[0], bi, X[0], X[1]);
 #pragma unroll
         for (int j = 2; j < N; j += 2) madc_wide_cc(X[j], X[j + 1], a[j], bi, X[j], X[j + 1]);
-        addc(O[N - 1], O[N - 1], 0u);
+        add_carry(O[N - 1]);
       } else {
 #pragma unroll
         for (int j = 0; j < N - 2; j++) addc_cc(O[j], O[j + 2], 0u);
@@ -225,7 +237,7 @@ template <int FID> struct Field {
       }
     }
     // reduction digit; p = 1 mod 2^32 so m = -X[0] and the p[0] column is X[0] + m = 2^32 [X[0] != 0]
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && !defined(LCPC_M_ALU)
     uint32_t m = X[0] * kMontInv32;
 #else
     uint32_t m = 0u - X[0];
@@ -239,7 +251,7 @@ template <int FID> struct Field {
     addc_cc(X[1], X[1], 0u);
 #pragma unroll
     for (int j = 2; j < N; j += 2) madc_wide_cc(X[j], X[j + 1], m, PM(j), X[j], X[j + 1]);
-    addc(O[N - 1], O[N - 1], 0u);
+    add_carry(O[N - 1]);
   }
 
   // merge the two arrays after the last step and bring the result into [0, p)

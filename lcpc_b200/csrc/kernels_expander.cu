@@ -17,6 +17,7 @@
 // is one broadcast load per warp instead of one load per row.  Two tiled transposes connect W to the
 // row-major coefficient / commitment matrices of the C ABI.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -194,6 +195,22 @@ __device__ __forceinline__ void ldv(uint32_t (&v)[N], const uint32_t *p) {
     }
   }
 }
+// the same load as a volatile asm statement: it keeps its place in front of the (volatile asm) multiply chains,
+// so a batch of gathers is really in flight before the first product instead of being sunk next to its use
+template <int N>
+__device__ __forceinline__ void ldv_early(uint32_t (&v)[N], const uint32_t *p) {
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 4; i++)
+      asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(v[4 * i]), "=r"(v[4 * i + 1]), "=r"(v[4 * i + 2]), "=r"(v[4 * i + 3])
+                   : "l"(p + 4 * i));
+  } else {
+#pragma unroll
+    for (int i = 0; i < N / 2; i++)
+      asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v[2 * i]), "=r"(v[2 * i + 1]) : "l"(p + 2 * i));
+  }
+}
 template <int N>
 __device__ __forceinline__ void stv(uint32_t *p, const uint32_t (&v)[N]) {
   if constexpr (N % 4 == 0) {
@@ -248,22 +265,45 @@ transpose_kernel(const uint32_t *__restrict__ src, size_t src_ld, uint32_t *__re
 // y[i][r] = sum_k vals[k] * x[colidx[k]][r]; one thread per (output i, batch row r), r fastest.
 // The sum is kept double-width and Montgomery-reduced once per output (field.cuh, mac_wide / redc):
 // a sparse row has 8..45 terms, so this halves the multiplier work against reduce-every-product.
+// The gathers are the latency that matters (random positions of a work buffer far larger than L1), so
+// the loop issues SPMM_UNROLL index loads, then that many gathers, before the first multiply.  A launch
+// covers the batch rows [r0, r0 + rg) (normally all of them, see encode_impl).
+constexpr int SPMM_UNROLL = 4;
 template <int FID>
 __global__ void __launch_bounds__(256)
 spmm_kernel(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ colidx, const uint32_t *__restrict__ vals,
-            const uint32_t *__restrict__ x, uint32_t *__restrict__ y, size_t m, size_t n_rows) {
+            const uint32_t *__restrict__ x, uint32_t *__restrict__ y, size_t m, size_t n_rows, unsigned r0, unsigned rg) {
   using F = Field<FID>;
   constexpr int N = F::N;
   const size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (item >= m * n_rows) return;
-  const size_t i = item / n_rows, r = item % n_rows;
+  if (item >= m * rg) return;
+  const size_t i = item / rg, r = r0 + item % rg;
   const uint32_t k0 = __ldg(rowptr + i), k1 = __ldg(rowptr + i + 1);
   typename F::Wide acc = F::wide_zero();
-  for (uint32_t k = k0; k < k1; k++) {
-    const size_t j = __ldg(colidx + k);
+  // address arithmetic kept off the multiplier pipe: one 32x32->64 product per gather, pointer bumps elsewhere
+  const uint32_t *xr = x + r * N;
+  const uint32_t pos_stride = (uint32_t)(n_rows * N);  // limbs between consecutive positions (host checks < 2^32)
+  const uint32_t *vp = vals + (size_t)k0 * N;
+  const uint32_t *cp = colidx + k0;
+  uint32_t left = k1 - k0;
+  for (; left >= SPMM_UNROLL; left -= SPMM_UNROLL, vp += SPMM_UNROLL * N, cp += SPMM_UNROLL) {
+    uint32_t j[SPMM_UNROLL];
+    typename F::Elem a[SPMM_UNROLL], xv[SPMM_UNROLL];
+#pragma unroll
+    for (int u = 0; u < SPMM_UNROLL; u++) j[u] = __ldg(cp + u);
+#pragma unroll
+    for (int u = 0; u < SPMM_UNROLL; u++) {
+      ldv_early<N>(xv[u].v, xr + (size_t)j[u] * pos_stride);
+      ldv_early<N>(a[u].v, vp + u * N);
+    }
+#pragma unroll
+    for (int u = 0; u < SPMM_UNROLL; u++) F::mac_wide(acc, a[u], xv[u]);
+  }
+  for (; left; left--, vp += N, cp++) {
+    const uint32_t j = __ldg(cp);
     typename F::Elem a, xv;
-    ldv<N>(a.v, vals + (size_t)k * N);
-    ldv<N>(xv.v, x + (j * n_rows + r) * N);
+    ldv<N>(a.v, vp);
+    ldv<N>(xv.v, xr + (size_t)j * pos_stride);
     F::mac_wide(acc, a, xv);
   }
   typename F::Elem out = F::template redc<2>(acc);
@@ -310,6 +350,7 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
   if (n_launches) *n_launches = 0;
   if (n_rows == 0) return cudaSuccess;
   if (valid < c->n_in || !scratch) return cudaErrorInvalidValue;
+  if (n_rows * N >= 0xffffffffull) return cudaErrorInvalidValue;  // spmm_kernel's 32-bit position stride
   uint32_t *W = (uint32_t *)scratch;                       // [n_cols][n_rows]
   uint32_t *T = W + c->n_cols * n_rows * N;                // [tmp_len][n_rows]
   int launches = 0;
@@ -326,9 +367,21 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
       const DeviceCsr &M = c->mats[op.mat];
       const uint32_t *x = W + op.in_off * n_rows * N;
       uint32_t *y = op.out_tmp ? T : W + op.out_off * n_rows * N;
-      size_t items = M.m * n_rows;
-      if (items) {
-        spmm_kernel<FID><<<(unsigned)((items + 255) / 256), 256, 0, st>>>(M.rowptr, M.colidx, M.vals, x, y, M.m, n_rows);
+      // batch rows per launch.  Splitting a level so that the gathered slice x[0..n)[r0..r0+rg) fits in L2 was
+      // measured (24/48/96 MB slices: 1.59/1.54/1.45 ms encode at 2^24) and lost to one launch over all rows
+      // (1.40 ms), so the default is no split; LCPC_B200_SPMM_SLICE_MB keeps the knob for other shapes.
+      size_t rg = n_rows;
+      static const size_t slice_cap = [] {
+        const char *e = getenv("LCPC_B200_SPMM_SLICE_MB");
+        size_t mb = e ? (size_t)atol(e) : 0;
+        return mb ? mb << 20 : ~(size_t)0;
+      }();
+      if (M.n * n_rows * F::BYTES > slice_cap) rg = std::max<size_t>(8, slice_cap / (M.n * F::BYTES));
+      rg = std::min(rg, n_rows);
+      for (size_t r0 = 0; r0 < n_rows && M.m; r0 += rg) {
+        const size_t cnt = std::min(rg, n_rows - r0), items = M.m * cnt;
+        spmm_kernel<FID><<<(unsigned)((items + 255) / 256), 256, 0, st>>>(M.rowptr, M.colidx, M.vals, x, y, M.m, n_rows,
+                                                                          (unsigned)r0, (unsigned)cnt);
         launches++;
       }
     } else {

@@ -221,6 +221,13 @@ struct NttPass {
 };
 
 constexpr int NTT_THREADS = 256;
+// tuning knobs (A/B builds): largest register round (3 = radix-8) and CTAs per SM the register budget allows
+#ifndef LCPC_NTT_MAX_KL
+#define LCPC_NTT_MAX_KL 3
+#endif
+#ifndef LCPC_NTT_MIN_BLOCKS
+#define LCPC_NTT_MIN_BLOCKS 2
+#endif
 
 struct NttGeom {
   unsigned log_n, S, tile, tshift, cshift, tmask, cmask, log_stride;
@@ -318,7 +325,7 @@ __device__ __forceinline__ void ntt_round(uint32_t *smem, const uint32_t *__rest
 }
 
 template <int FID>
-__global__ void __launch_bounds__(NTT_THREADS, 2)
+__global__ void __launch_bounds__(NTT_THREADS, LCPC_NTT_MIN_BLOCKS)
 ntt_pass_kernel(const uint32_t *__restrict__ src, uint32_t *dst, const uint32_t *__restrict__ roots, NttPass p) {
   using F = Field<FID>;
   constexpr int N = F::N;
@@ -372,14 +379,14 @@ ntt_pass_kernel(const uint32_t *__restrict__ src, uint32_t *dst, const uint32_t 
 
   unsigned rem = p.S, lg_top = p.S - 1;
   while (rem > 0) {
-    if (rem >= 3) {
+    if (LCPC_NTT_MAX_KL >= 3 && rem >= 3) {
       if (g.last && rem == 3) ntt_round<FID, 3, true>(smem, roots, g, lg_top);
       else ntt_round<FID, 3, false>(smem, roots, g, lg_top);
       rem -= 3, lg_top -= 3;
-    } else if (rem == 2) {
-      if (g.last) ntt_round<FID, 2, true>(smem, roots, g, lg_top);
+    } else if (rem >= 2) {
+      if (g.last && rem == 2) ntt_round<FID, 2, true>(smem, roots, g, lg_top);
       else ntt_round<FID, 2, false>(smem, roots, g, lg_top);
-      rem = 0;
+      rem -= 2, lg_top -= 2;
     } else {
       if (g.last) ntt_round<FID, 1, true>(smem, roots, g, lg_top);
       else ntt_round<FID, 1, false>(smem, roots, g, lg_top);
