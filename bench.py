@@ -229,11 +229,20 @@ def run_ours(args):
                       "l2": "inputs+outputs (>= 1.5 GiB at 2^24) exceed the 126 MB L2; no flush needed",
                       "timing": "CUDA events on the engine stream, max over ranks"},
            "e2e": result["e2e"], "gpu_launches": result["gpu_launches"], "clocks": result["clocks"],
-           "phases_ms": result.get("phases_ms"),
+           "phases_ms": result.get("phases_ms"), "prove": result.get("prove"),
            "roofline": None, "cpu_baseline": None}
     # roofline of the dominant kernel (per launch) + of the whole commit
     dk = result.get("dominant")
     if dk:
+        # dram bytes per launch of the same kernel from the committed `ncu --set full` capture (profiles/), if one
+        # exists for this workload; it is evidence copied from a profile, never a quantity measured in this run
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            key = f"{args.workload}_{FIELD_NAMES[field]}_2^{args.lgl}"
+            if key in tr:
+                dk["traffic"] = tr[key]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         ach = dk["bytes_per_launch"] / (dk["ms_per_launch"] * 1e-3) / 1e9
         out["roofline"] = {"bound": "hbm", "kernel": dk["kernel"], "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                            "frac": ach / hbm_peak, "traffic": dk.get("traffic"), "peak_source": peak_src,
@@ -256,9 +265,19 @@ def run_ours(args):
 def bench_single(args, ctx, enc, field, n, torch, P):
     L = P.FIELD_LIMBS[field]
     n_rows, n_per_row, n_cols = enc.get_dims(n)
-    x = synthetic_coeffs(field, n, seed=0)
-    host = torch.from_numpy(x.view(np.int64)).pin_memory()
-    dev = host.cuda(non_blocking=False)
+    if n >= (1 << 25):
+        # large sweep points: draw the limbs on the device (numpy would spend minutes on 8 GiB), same distribution
+        p_top = {1: 0x46d0760000000001, 2: 0x6e754097ba20e0bf, 3: 0x453708aa3fbc8dda, 4: 0x663c799b6e4d2900}[field]
+        g = torch.Generator(device="cuda").manual_seed(0)
+        dev = torch.randint(-(1 << 63), (1 << 63) - 1, (n, L), dtype=torch.int64, device="cuda", generator=g)
+        dev[:, L - 1] = torch.randint(0, p_top, (n,), dtype=torch.int64, device="cuda", generator=g)
+        host = torch.empty((n, L), dtype=torch.int64, pin_memory=True)
+        host.copy_(dev)
+        torch.cuda.synchronize()
+    else:
+        x = synthetic_coeffs(field, n, seed=0)
+        host = torch.from_numpy(x.view(np.int64)).pin_memory()
+        dev = host.cuda(non_blocking=False)
     stream = torch.cuda.ExternalStream(ctx.stream)
     commit = P.LcCommit.commit_device(dev.data_ptr(), n, enc)
     root0 = commit.get_root()
@@ -302,6 +321,23 @@ def bench_single(args, ctx, enc, field, n, torch, P):
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     assert r == root0
     clocks = sampler.stop()
+    # the prover's device work on the resident commit (lcpc-2d/src/lib.rs:1004-1093 minus transcript): n_degree_tests
+    # + 1 row combinations (collapse_columns) and n_col_opens column openings, through the host API (tiny H2D/D2H)
+    rng = np.random.default_rng(7)
+    n_comb = enc.get_n_degree_tests() + 1
+    tensors = [synthetic_coeffs(field, n_rows, seed=100 + i) for i in range(n_comb)]
+    cols = rng.integers(0, n_cols, size=enc.get_n_col_opens(), dtype=np.uint64)
+    commit.collapse(tensors[0])
+    commit.open_columns(cols)
+    t0 = time.perf_counter()
+    for t in tensors:
+        commit.collapse(t)
+    t_collapse = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    commit.open_columns(cols)
+    t_open = time.perf_counter() - t0
+    prove = {"collapse_ms": t_collapse * 1e3, "n_collapse": n_comb, "open_columns_ms": t_open * 1e3,
+             "n_col_opens": int(cols.shape[0]), "note": "host API wall time on the device-resident LcCommit"}
     ms_per_step = total_ms / args.steps
     B = 8 * L
     if enc.__class__.__name__ == "LigeroEncoding":
@@ -324,7 +360,7 @@ def bench_single(args, ctx, enc, field, n, torch, P):
                         bytes_per_launch=(B * n_rows * (n_per_row + n_cols) + code_bytes) / max(1, nl[0]), traffic=None)
     return dict(value=n / (ms_per_step * 1e-3), ms_per_step=ms_per_step, gpu_launches=int(launches),
                 clocks=clocks, phases_ms=dict(zip(["pad_copy", "encode", "leaf_hash", "merkle"], phases.tolist())),
-                dominant=dominant, code_bytes=code_bytes,
+                dominant=dominant, code_bytes=code_bytes, prove=prove,
                 e2e={"value": n / e2e_s, "unit": "field-elts/s", "h2d_bytes_per_step": int(n * B), "d2h_bytes_per_step": 32,
                      "ms_per_step": e2e_s * 1e3, "mode": "device-resident LcCommit; host receives the LcRoot"})
 

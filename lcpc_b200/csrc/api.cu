@@ -365,9 +365,18 @@ static size_t enc_scratch_bytes(const lcpc_b200_enc *enc, size_t n_rows) {
 // stream (into d_coeffs, zero-padded to n_rows * n_per_row) while the engine stream encodes the chunks
 // that have landed into d_comm.  `first_ev` (optional) is recorded on the engine stream when the first
 // chunk is in.
+// leaf hashing that trails the row encode: chunk k of every leaf input is hashed as soon as the rows it reads
+// are encoded (see leaf_chunk_rows_end)
+struct HashTrail {
+  uint8_t *leaves;
+  void *scratch;
+  unsigned next_chunk, n_chunks;
+  int launches;
+};
+
 static int encode_rows_from_host(lcpc_b200_enc *enc, const void *src, size_t len, uint32_t *d_coeffs, uint32_t *d_comm,
                                  size_t n_rows, void *enc_scratch, cudaEvent_t first_ev,
-                                 const Scatter *scatter = nullptr) {
+                                 const Scatter *scatter = nullptr, HashTrail *trail = nullptr) {
   lcpc_b200_ctx *ctx = enc->ctx;
   cudaStream_t st = ctx->stream;
   const size_t B = field_bytes(enc->field), N = B / 4;
@@ -396,6 +405,17 @@ static int encode_rows_from_host(lcpc_b200_enc *enc, const void *src, size_t len
     if (int rc = encode_rows(enc, d_coeffs + r0 * n_per_row * N, n_per_row, n_per_row, d_comm + r0 * enc->n_cols * N,
                              r1 - r0, enc_scratch, scatter ? &sc : nullptr))
       return rc;
+    if (trail && k + 1 < n_chunks) {  // the chunks still open after the last row-chunk are hashed by the caller
+      unsigned ready = trail->next_chunk;
+      while (ready < trail->n_chunks && leaf_chunk_rows_end(enc->field, n_rows, ready) <= r1) ready++;
+      if (ready > trail->next_chunk) {
+        cudaError_t ce = launch_leaf_chunks(enc->field, d_comm, n_rows, enc->n_cols, enc->n_cols, trail->leaves, trail->scratch,
+                                            trail->next_chunk, ready - trail->next_chunk, st);
+        if (ce != cudaSuccess) return cuda_fail(ctx, ce, "hash_columns");
+        ctx->launches += 1, trail->launches += 1;
+        trail->next_chunk = ready;
+      }
+    }
   }
   return LCPC_B200_OK;
 }
@@ -563,8 +583,11 @@ static int commit_run(lcpc_b200_commit *c, const void *src, size_t len, cudaMemc
   CU(ctx, cudaEventRecord(c->ev[0], st));
   const size_t padded = c->n_rows * c->n_per_row;
   uint64_t l0 = ctx->launches;
+  HashTrail trail{c->d_hashes, c->d_hash_scratch, 0, leaf_chunk_count(enc->field, c->n_rows), 0};
   if (kind == cudaMemcpyHostToDevice && c->n_rows > 1) {
-    if (int rc = encode_rows_from_host(enc, src, len, c->d_coeffs, c->d_comm, c->n_rows, c->d_enc_scratch, c->ev[1])) return rc;
+    if (int rc = encode_rows_from_host(enc, src, len, c->d_coeffs, c->d_comm, c->n_rows, c->d_enc_scratch, c->ev[1], nullptr,
+                                       &trail))
+      return rc;
   } else if (kind == cudaMemcpyDeviceToDevice && enc->kind == LCPC_B200_ENC_LIGERO && padded == len && enc->log_n > 0 &&
              (const void *)c->d_coeffs != src) {
     // pad + copy (:636-645) folded into the first transform pass: it reads the caller's coefficient rows and
@@ -587,11 +610,14 @@ static int commit_run(lcpc_b200_commit *c, const void *src, size_t len, cudaMemc
   CU(ctx, cudaEventRecord(c->ev[2], st));
   // leaves beyond n_cols stay Output::default() = zeros (:665, :696)
   if (c->np2 > c->n_cols) CU(ctx, cudaMemsetAsync(c->d_hashes + c->n_cols * 32, 0, (c->np2 - c->n_cols) * 32, st));
+  // column leaves (:706-745): whatever chunks did not already trail the encode, then the per-column chunk merge
   int nl = 0;
-  cudaError_t ce = launch_hash_columns(enc->field, c->d_comm, c->n_rows, c->n_cols, c->n_cols, c->d_hashes,
-                                       c->d_hash_scratch, st, &nl);
+  cudaError_t ce = launch_leaf_chunks(enc->field, c->d_comm, c->n_rows, c->n_cols, c->n_cols, c->d_hashes, c->d_hash_scratch,
+                                      trail.next_chunk, trail.n_chunks - trail.next_chunk, st);
+  if (ce == cudaSuccess) ce = launch_leaf_merge(enc->field, c->n_rows, c->n_cols, c->d_hashes, c->d_hash_scratch, st, &nl);
+  nl += 1;
   ctx->launches += nl;
-  c->hash_launches = nl;
+  c->hash_launches = nl + trail.launches;
   if (ce != cudaSuccess) return cuda_fail(ctx, ce, "hash_columns");
   CU(ctx, cudaEventRecord(c->ev[3], st));
   ce = launch_merkle_tree(c->d_hashes, c->np2, st, &nl);

@@ -49,6 +49,14 @@ cudaError_t launch_root_table(int field, uint32_t *roots, const uint32_t *w, siz
 size_t hash_scratch_bytes(int field, size_t n_rows, size_t n_cols);
 cudaError_t launch_hash_columns(int field, const uint32_t *comm, size_t n_rows, size_t n_cols, size_t row_stride,
                                 uint8_t *leaves, void *scratch, cudaStream_t stream, int *n_launches);
+// the same in pieces, for hashing that trails the row encode: chunk k of every leaf input needs the rows
+// [0, leaf_chunk_rows_end(k)) only
+unsigned leaf_chunk_count(int field, size_t n_rows);
+size_t leaf_chunk_rows_end(int field, size_t n_rows, unsigned k);
+cudaError_t launch_leaf_chunks(int field, const uint32_t *comm, size_t n_rows, size_t n_cols, size_t row_stride,
+                               uint8_t *leaves, void *scratch, unsigned k_first, unsigned k_count, cudaStream_t stream);
+cudaError_t launch_leaf_merge(int field, size_t n_rows, size_t n_cols, uint8_t *leaves, void *scratch, cudaStream_t stream,
+                              int *n_launches);
 // hashes = [leaves(np2) | layer 1 | ... | root]; leaves given, upper layers computed
 cudaError_t launch_merkle_tree(uint8_t *hashes, size_t np2, cudaStream_t stream, int *n_launches);
 

@@ -10,6 +10,8 @@
 // BLAKE3 chunks.  Chunks are independent until the tree merge, so the grid is (columns x chunks):
 // adjacent lanes own adjacent columns, which makes every row read a fully coalesced run of
 // 32*B bytes per warp; a second small kernel merges the chunk chaining values per column.
+#include <algorithm>
+
 #include "blake3.cuh"
 #include "field.cuh"
 #include "kernels.h"
@@ -41,7 +43,7 @@ __device__ __forceinline__ void gload_elem(uint32_t (&v)[N], const uint32_t *p) 
 template <int FID>
 __global__ void __launch_bounds__(HASH_THREADS)
 leaf_chunk_kernel(const uint32_t *__restrict__ comm, size_t n_rows, size_t n_cols, size_t row_stride,
-                  uint32_t *__restrict__ out, unsigned n_chunks) {
+                  uint32_t *__restrict__ out, unsigned n_chunks, unsigned k_first) {
   using F = Field<FID>;
   constexpr int N = F::N;
   constexpr int B = F::BYTES;
@@ -49,7 +51,7 @@ leaf_chunk_kernel(const uint32_t *__restrict__ comm, size_t n_rows, size_t n_col
   constexpr int SPB = 64 / B;        // slots per block
   constexpr int PRE = 32 / B;        // zero-prefix slots
   const size_t col = (size_t)blockIdx.x * HASH_THREADS + threadIdx.x;
-  const unsigned k = blockIdx.y;
+  const unsigned k = k_first + blockIdx.y;
   if (col >= n_cols) return;
   const size_t total = 32 + (size_t)B * n_rows;
   const size_t chunk_off = (size_t)k * b3::CHUNK_LEN;
@@ -90,12 +92,12 @@ leaf_chunk_kernel(const uint32_t *__restrict__ comm, size_t n_rows, size_t n_col
 template <int FID>
 __global__ void __launch_bounds__(HASH_THREADS)
 leaf_chunk_kernel_generic(const uint32_t *__restrict__ comm, size_t n_rows, size_t n_cols, size_t row_stride,
-                          uint32_t *__restrict__ out, unsigned n_chunks) {
+                          uint32_t *__restrict__ out, unsigned n_chunks, unsigned k_first) {
   using F = Field<FID>;
   constexpr int N = F::N;
   constexpr int B = F::BYTES;
   const size_t col = (size_t)blockIdx.x * HASH_THREADS + threadIdx.x;
-  const unsigned k = blockIdx.y;
+  const unsigned k = k_first + blockIdx.y;
   if (col >= n_cols) return;
   const size_t total = 32 + (size_t)B * n_rows;
   const size_t chunk_off = (size_t)k * b3::CHUNK_LEN;
@@ -201,32 +203,59 @@ size_t hash_scratch_bytes(int field, size_t n_rows, size_t n_cols) {
   return k > 1 ? (size_t)k * n_cols * 32 : 0;
 }
 
+// rows of comm that chunk k of a leaf input reads: [0, leaf_chunk_rows_end(field, n_rows, k)); a chunk can be
+// hashed as soon as that many rows are encoded (commit() from host memory overlaps hashing with the copy)
+size_t leaf_chunk_rows_end(int field, size_t n_rows, unsigned k) {
+  const size_t B = field_bytes(field), total = 32 + B * n_rows;
+  size_t end = std::min<size_t>((size_t)(k + 1) * b3::CHUNK_LEN, total);  // exclusive byte end of the chunk
+  if (end <= 32) return 0;
+  return std::min(n_rows, (end - 32 + B - 1) / B);
+}
+unsigned leaf_chunk_count(int field, size_t n_rows) { return leaf_chunks(field, n_rows); }
+
+// chunk chaining values (or, for single-chunk leaves, the digests) of chunks [k_first, k_first + k_count)
+cudaError_t launch_leaf_chunks(int field, const uint32_t *comm, size_t n_rows, size_t n_cols, size_t row_stride,
+                               uint8_t *leaves, void *scratch, unsigned k_first, unsigned k_count, cudaStream_t stream) {
+  if (n_cols == 0 || k_count == 0) return cudaSuccess;
+  const unsigned n_chunks = leaf_chunks(field, n_rows);
+  if (n_chunks > 65535u || k_first + k_count > n_chunks) return cudaErrorInvalidValue;
+  uint32_t *out = n_chunks > 1 ? (uint32_t *)scratch : (uint32_t *)leaves;
+  if (n_chunks > 1 && !scratch) return cudaErrorInvalidValue;
+  dim3 grid((unsigned)((n_cols + HASH_THREADS - 1) / HASH_THREADS), k_count);
+  switch (field) {
+    case FT63: leaf_chunk_kernel<FT63><<<grid, HASH_THREADS, 0, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first); break;
+    case FT127: leaf_chunk_kernel<FT127><<<grid, HASH_THREADS, 0, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first); break;
+    case FT191: leaf_chunk_kernel_generic<FT191><<<grid, HASH_THREADS, 0, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first); break;
+    case FT255: leaf_chunk_kernel<FT255><<<grid, HASH_THREADS, 0, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+// BLAKE3 tree over the chunk chaining values of every column (no-op for single-chunk leaves)
+cudaError_t launch_leaf_merge(int field, size_t n_rows, size_t n_cols, uint8_t *leaves, void *scratch, cudaStream_t stream,
+                              int *n_launches) {
+  if (n_launches) *n_launches = 0;
+  const unsigned n_chunks = leaf_chunks(field, n_rows);
+  if (n_chunks <= 1 || n_cols == 0) return cudaSuccess;
+  const unsigned gx = (unsigned)((n_cols + HASH_THREADS - 1) / HASH_THREADS);
+  leaf_merge_kernel<<<gx, HASH_THREADS, 0, stream>>>((const uint32_t *)scratch, n_cols, n_chunks, (uint32_t *)leaves);
+  if (n_launches) *n_launches = 1;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_hash_columns(int field, const uint32_t *comm, size_t n_rows, size_t n_cols, size_t row_stride,
                                 uint8_t *leaves, void *scratch, cudaStream_t stream, int *n_launches) {
   if (n_launches) *n_launches = 0;
   if (n_cols == 0) return cudaSuccess;
   const unsigned n_chunks = leaf_chunks(field, n_rows);
-  if (n_chunks > 65535u) return cudaErrorInvalidValue;
-  uint32_t *out = n_chunks > 1 ? (uint32_t *)scratch : (uint32_t *)leaves;
-  if (n_chunks > 1 && !scratch) return cudaErrorInvalidValue;
-  dim3 grid((unsigned)((n_cols + HASH_THREADS - 1) / HASH_THREADS), n_chunks);
-  switch (field) {
-    case FT63: leaf_chunk_kernel<FT63><<<grid, HASH_THREADS, 0, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks); break;
-    case FT127: leaf_chunk_kernel<FT127><<<grid, HASH_THREADS, 0, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks); break;
-    case FT191: leaf_chunk_kernel_generic<FT191><<<grid, HASH_THREADS, 0, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks); break;
-    case FT255: leaf_chunk_kernel<FT255><<<grid, HASH_THREADS, 0, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks); break;
-    default: return cudaErrorInvalidValue;
-  }
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_leaf_chunks(field, comm, n_rows, n_cols, row_stride, leaves, scratch, 0, n_chunks, stream);
   if (e != cudaSuccess) return e;
   if (n_launches) ++*n_launches;
-  if (n_chunks > 1) {
-    leaf_merge_kernel<<<grid.x, HASH_THREADS, 0, stream>>>((const uint32_t *)scratch, n_cols, n_chunks, (uint32_t *)leaves);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    if (n_launches) ++*n_launches;
-  }
-  return cudaSuccess;
+  int nm = 0;
+  e = launch_leaf_merge(field, n_rows, n_cols, leaves, scratch, stream, &nm);
+  if (n_launches) *n_launches += nm;
+  return e;
 }
 
 // ---- Merkle layers: node = BLAKE3(left || right), a single 64-byte block (lib.rs:768-775) ----

@@ -420,7 +420,7 @@ static cudaError_t ntt_rows_impl(const uint32_t *src, size_t src_stride, size_t 
   using F = Field<FID>;
   static bool attr_set = false;
   constexpr unsigned LOG_TILE = 11;  // 2048 elements: 64 KiB for Ft255
-  constexpr unsigned MAX_S = 9;
+  constexpr unsigned MAX_S = 10;  // stages per pass: 2^19 points are 10 + 9 (two HBM round trips), 2^17 are 9 + 8
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(ntt_pass_kernel<FID>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)SmemLayout<F::N>::bytes(1u << LOG_TILE));

@@ -113,6 +113,19 @@ def test_ligero_encode_vs_oracle(field, log_n):
     assert (enc.encode(dense) == oenc.encode(dense)).all()
 
 
+@pytest.mark.parametrize("field,log_n", [(P.FT255, 19), (P.FT63, 20), (P.FT127, 21)])
+def test_ligero_encode_long_rows(field, log_n):
+    """row lengths of the 2^26..2^28 sweep points: 2^19 and 2^20 points are two passes of 10 + 9 / 10 + 10
+    stages, 2^21 three passes"""
+    n_cols = 1 << log_n
+    n_per_row = n_cols // 2
+    enc = P.LigeroEncoding.new_from_dims(field, n_per_row, n_cols)
+    oenc = O.Encoding.ligero_from_dims(field, n_per_row, n_cols)
+    row = np.zeros((n_cols, enc.L), np.uint64)
+    row[:n_per_row] = O.random_elems(field, n_per_row, seed=log_n)
+    assert (enc.encode(row) == oenc.encode(row)).all()
+
+
 @pytest.mark.parametrize("rho,n_cols", [((1, 4), 1 << 12), ((39, 40), 1 << 13), ((1, 2), 1 << 16)])
 def test_ligero_commit_other_rates(rho, n_cols):
     field = P.FT127
