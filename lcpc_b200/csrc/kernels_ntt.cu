@@ -220,13 +220,21 @@ struct NttPass {
   size_t copy_stride;  // copy_stride apart -- commit()'s own copy of the coefficients for free
 };
 
-constexpr int NTT_THREADS = 256;
+// CTA shape, measured at 2^24 (encode ms): 256 threads x 2048-element tile x 2 CTAs/SM 4.97; 128 x 1024 x 4
+// 4.75; 64 x 512 x 8 4.78; 512 x 4096 x 1 5.89 -- small CTAs hide each other's staging phases and barriers
+#ifndef LCPC_NTT_THREADS
+#define LCPC_NTT_THREADS 128
+#endif
+#ifndef LCPC_NTT_LOG_TILE
+#define LCPC_NTT_LOG_TILE 10
+#endif
+constexpr int NTT_THREADS = LCPC_NTT_THREADS;
 // tuning knobs (A/B builds): largest register round (3 = radix-8) and CTAs per SM the register budget allows
 #ifndef LCPC_NTT_MAX_KL
 #define LCPC_NTT_MAX_KL 3
 #endif
 #ifndef LCPC_NTT_MIN_BLOCKS
-#define LCPC_NTT_MIN_BLOCKS 2
+#define LCPC_NTT_MIN_BLOCKS 4
 #endif
 
 struct NttGeom {
@@ -419,7 +427,7 @@ static cudaError_t ntt_rows_impl(const uint32_t *src, size_t src_stride, size_t 
                                  size_t copy_stride) {
   using F = Field<FID>;
   static bool attr_set = false;
-  constexpr unsigned LOG_TILE = 11;  // 2048 elements: 64 KiB for Ft255
+  constexpr unsigned LOG_TILE = LCPC_NTT_LOG_TILE;  // 1024 elements: 32 KiB for Ft255
   constexpr unsigned MAX_S = 10;  // stages per pass: 2^19 points are 10 + 9 (two HBM round trips), 2^17 are 9 + 8
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(ntt_pass_kernel<FID>, cudaFuncAttributeMaxDynamicSharedMemorySize,
