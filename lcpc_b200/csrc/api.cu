@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -28,6 +29,11 @@ struct lcpc_b200_ctx {
   static constexpr int MAX_CHUNKS = 16;
   cudaEvent_t chunk_ev[MAX_CHUNKS] = {};
   cudaEvent_t begin_ev = nullptr;
+  // side stream: column hashing of already-encoded row chunks runs here next to the encode of later rows
+  // (the transforms saturate the multiplier pipe, BLAKE3 the ALU pipe: they overlap on the same SMs)
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t side_ev[MAX_CHUNKS] = {};
+  cudaEvent_t side_done = nullptr;
   std::mutex mu;
   std::string err;
   uint64_t launches = 0;
@@ -181,8 +187,11 @@ int lcpc_b200_ctx_create(int device, lcpc_b200_ctx **out) {
   bool ok = cudaSetDevice(device) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaEventCreateWithFlags(&ctx->begin_ev, cudaEventDisableTiming) == cudaSuccess;
+            cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->begin_ev, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->side_done, cudaEventDisableTiming) == cudaSuccess;
   for (auto &e : ctx->chunk_ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+  for (auto &e : ctx->side_ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
     lcpc_b200_ctx_destroy(ctx);
     return LCPC_B200_ERR_CUDA;
@@ -202,9 +211,16 @@ void lcpc_b200_ctx_destroy(lcpc_b200_ctx *ctx) {
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamDestroy(ctx->copy_stream);
   }
+  if (ctx->side_stream) {
+    cudaStreamSynchronize(ctx->side_stream);
+    cudaStreamDestroy(ctx->side_stream);
+  }
   for (auto &e : ctx->chunk_ev)
     if (e) cudaEventDestroy(e);
+  for (auto &e : ctx->side_ev)
+    if (e) cudaEventDestroy(e);
   if (ctx->begin_ev) cudaEventDestroy(ctx->begin_ev);
+  if (ctx->side_done) cudaEventDestroy(ctx->side_done);
   if (ctx->scratch) cudaFree(ctx->scratch);
   delete ctx;
 }
@@ -591,13 +607,47 @@ static int commit_run(lcpc_b200_commit *c, const void *src, size_t len, cudaMemc
   } else if (kind == cudaMemcpyDeviceToDevice && enc->kind == LCPC_B200_ENC_LIGERO && padded == len && enc->log_n > 0 &&
              (const void *)c->d_coeffs != src) {
     // pad + copy (:636-645) folded into the first transform pass: it reads the caller's coefficient rows and
-    // stores the commit's own copy on the way
+    // stores the commit's own copy on the way.  Rows can go in chunks (LCPC_B200_DEV_CHUNKS) so that leaf-input
+    // chunks whose rows are done are hashed on the side stream while later rows are transformed; measured at
+    // 2^24: 1/4/8/16 chunks = 5.63/5.72/5.90/6.14 ms -- the transform CTAs hold every register of the SM, so the
+    // hash CTAs cannot co-reside and the extra launch tails cost more than the overlap gains.  Default: 1.
     CU(ctx, cudaEventRecord(c->ev[1], st));
-    int nl = 0;
-    cudaError_t ce = launch_ntt_rows(enc->field, (const uint32_t *)src, c->n_per_row, c->n_per_row, c->d_comm, c->n_cols,
-                                     enc->d_roots, enc->log_n, c->n_rows, st, &nl, nullptr, c->d_coeffs, c->n_per_row);
-    ctx->launches += nl;
-    if (ce != cudaSuccess) return cuda_fail(ctx, ce, "encode");
+    static const size_t want_chunks = [] {
+      const char *e = getenv("LCPC_B200_DEV_CHUNKS");
+      long v = e ? atol(e) : 1;
+      return (size_t)std::min<long>(std::max<long>(v, 1), lcpc_b200_ctx::MAX_CHUNKS);
+    }();
+    const size_t N = B / 4;
+    size_t n_rc = trail.n_chunks > 1 ? std::min(want_chunks, c->n_rows) : 1;
+    while (n_rc > 1 && (c->n_rows / n_rc) * c->n_cols * B < ((size_t)32 << 20)) n_rc--;
+    bool side_used = false;
+    for (size_t k = 0; k < n_rc; k++) {
+      const size_t r0 = k * c->n_rows / n_rc, r1 = (k + 1) * c->n_rows / n_rc;
+      int nl = 0;
+      cudaError_t ce = launch_ntt_rows(enc->field, (const uint32_t *)src + r0 * c->n_per_row * N, c->n_per_row, c->n_per_row,
+                                       c->d_comm + r0 * c->n_cols * N, c->n_cols, enc->d_roots, enc->log_n, r1 - r0, st, &nl,
+                                       nullptr, c->d_coeffs + r0 * c->n_per_row * N, c->n_per_row);
+      ctx->launches += nl;
+      if (ce != cudaSuccess) return cuda_fail(ctx, ce, "encode");
+      if (k + 1 < n_rc) {
+        unsigned ready = trail.next_chunk;
+        while (ready < trail.n_chunks && leaf_chunk_rows_end(enc->field, c->n_rows, ready) <= r1) ready++;
+        if (ready > trail.next_chunk) {
+          CU(ctx, cudaEventRecord(ctx->side_ev[k], st));
+          CU(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->side_ev[k], 0));
+          ce = launch_leaf_chunks(enc->field, c->d_comm, c->n_rows, c->n_cols, c->n_cols, trail.leaves, trail.scratch,
+                                  trail.next_chunk, ready - trail.next_chunk, ctx->side_stream);
+          if (ce != cudaSuccess) return cuda_fail(ctx, ce, "hash_columns");
+          ctx->launches += 1, trail.launches += 1;
+          trail.next_chunk = ready;
+          side_used = true;
+        }
+      }
+    }
+    if (side_used) {
+      CU(ctx, cudaEventRecord(ctx->side_done, ctx->side_stream));
+      CU(ctx, cudaStreamWaitEvent(st, ctx->side_done, 0));
+    }
   } else {
     // pad + copy (lcpc-2d/src/lib.rs:636-645): coeffs = coeffs_in || zeros
     CU(ctx, cudaMemcpyAsync(c->d_coeffs, src, len * B, kind, st));
