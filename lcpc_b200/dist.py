@@ -174,10 +174,16 @@ class DistributedCommit:
                 try:
                     import torch.distributed._symmetric_memory as symm_mem
                     g = group if group is not None else dist.group.WORLD
-                    buf = symm_mem.empty(max(1, n_rows * self.max_cols * L), dtype=i64, device=dev)
+                    # two receive matrices used alternately: a rank can only be two commits ahead of an owner
+                    # after passing the "stores have landed" barrier of the commit in between, which that owner
+                    # reaches after hashing -- so no second barrier is needed before overwriting
+                    half = max(1, n_rows * self.max_cols * L)
+                    buf = symm_mem.empty(2 * half, dtype=i64, device=dev)
                     self.symm = symm_mem.rendezvous(buf, g.group_name)
-                    self.d_recv = buf
-                    self.peer_ptrs = [int(x) for x in self.symm.buffer_ptrs]
+                    self.recv_bufs = [buf[:half], buf[half:]]
+                    self.d_recv = self.recv_bufs[0]
+                    self.peer_ptrs = [[int(x) + b * half * 8 for x in self.symm.buffer_ptrs] for b in (0, 1)]
+                    self.parity = 1
                     self.transport = "p2p"
                 except Exception as e:  # no peer access / allocator unavailable: NCCL moves the tiles instead
                     if want == "p2p":
@@ -204,6 +210,8 @@ class DistributedCommit:
         self.d_my_roots = torch.zeros(max(1, self.max_subs) * 32, dtype=torch.uint8, device=dev)
         self.d_all_roots = torch.zeros(self.world * max(1, self.max_subs) * 32, dtype=torch.uint8, device=dev)
         self.d_top = torch.zeros((2 * p.n_sub - 1) * 32, dtype=torch.uint8, device=dev)
+        self.uniform_subs = self.my_subs > 0 and all(
+            p.sub_lo[g + 1] - p.sub_lo[g] == self.my_subs for g in range(self.world))
         self.zero_root = self._zero_subtree_root()
         if p.n_real_sub < p.n_sub:
             pad = torch.from_numpy(np.tile(np.frombuffer(self.zero_root, np.uint8), p.n_sub - p.n_real_sub).copy()).to(dev)
@@ -251,9 +259,9 @@ class DistributedCommit:
                     ops.pack(self.d_comm_rows, self.my_rows, p.n_cols, self.world, self.d_starts, self.d_send)
             else:
                 if self.transport == "p2p":
-                    # owners must be done reading the previous commit's columns before anyone overwrites them
-                    self.symm.barrier(channel=0)
-                    ptrs, row0 = self.peer_ptrs, p.row_lo[self.rank]
+                    self.parity ^= 1
+                    self.d_recv = self.recv_bufs[self.parity]
+                    ptrs, row0 = self.peer_ptrs[self.parity], p.row_lo[self.rank]
                 else:  # tile h of the send buffer = [my_rows][width_h] at element offset my_rows * col_lo[h]
                     base = self.d_send.data_ptr()
                     ptrs = [base + self.my_rows * p.col_lo[h] * self.L * 8 for h in range(self.world)]
@@ -275,13 +283,19 @@ class DistributedCommit:
                 ops.hash_columns(self.d_recv, p.n_rows, self.my_cols, self.d_forest)
                 if self.sub_layers:
                     ops.merkle_layers(self.d_forest, self.my_subs * p.sub_leaves, self.sub_layers)
-                self.d_my_roots[:self.my_subs * 32] = self.d_forest[self.roots_off:self.roots_off + self.my_subs * 32]
-            dist.all_gather_into_tensor(self.d_all_roots, self.d_my_roots, group=self.group)
-            stride = max(1, self.max_subs) * 32
-            for g in range(self.world):
-                s0, s1 = p.subs(g)
-                if s1 > s0:
-                    self.d_top[s0 * 32:s1 * 32] = self.d_all_roots[g * stride:g * stride + (s1 - s0) * 32]
+            if self.uniform_subs:
+                # every rank owns the same number of subtrees: gather their roots straight into the top tree
+                dist.all_gather_into_tensor(self.d_top[:p.n_real_sub * 32],
+                                            self.d_forest[self.roots_off:self.roots_off + self.my_subs * 32], group=self.group)
+            else:
+                if self.my_cols:
+                    self.d_my_roots[:self.my_subs * 32] = self.d_forest[self.roots_off:self.roots_off + self.my_subs * 32]
+                dist.all_gather_into_tensor(self.d_all_roots, self.d_my_roots, group=self.group)
+                stride = max(1, self.max_subs) * 32
+                for g in range(self.world):
+                    s0, s1 = p.subs(g)
+                    if s1 > s0:
+                        self.d_top[s0 * 32:s1 * 32] = self.d_all_roots[g * stride:g * stride + (s1 - s0) * 32]
             if p.n_sub > 1:
                 ops.merkle_layers(self.d_top, p.n_sub, p.n_sub.bit_length() - 1)
 
@@ -317,9 +331,10 @@ def bench_distributed(args, ctx, enc, field, n, synthetic_coeffs):
     dc = DistributedCommit(enc, n)
     p = dc.plan
     r0, r1 = p.rows(rank)
-    # this rank's rows of the same seeded polynomial every world size would commit
+    # this rank's rows of a synthetic polynomial (uniform field elements, seeded per rank: only the slice a rank
+    # owns is ever materialised, so 2^28 coefficients do not cost every rank 8 GiB of host memory)
     lo, hi = r0 * p.n_per_row, min(r1 * p.n_per_row, n)
-    x = synthetic_coeffs(field, n, seed=0)[lo:hi] if world <= 2 or n <= (1 << 22) else _slice_coeffs(synthetic_coeffs, field, n, lo, hi)
+    x = synthetic_coeffs(field, max(hi - lo, 0), seed=1000 + rank)
     host = torch.from_numpy(np.ascontiguousarray(x).view(np.int64).reshape(-1)).pin_memory()
     dc.load_rows_from_host(host)
     ctx.synchronize()
@@ -368,9 +383,3 @@ def bench_distributed(args, ctx, enc, field, n, synthetic_coeffs):
                 e2e={"value": n / e2e_s, "unit": "field-elts/s", "h2d_bytes_per_step": int(n * 8 * L),
                      "d2h_bytes_per_step": 32 * world, "ms_per_step": e2e_s * 1e3,
                      "mode": "row blocks from pinned host memory on every rank; every rank reads back the LcRoot"})
-
-
-def _slice_coeffs(synthetic_coeffs, field, n, lo, hi):
-    # synthetic_coeffs is a pure function of (field, n, seed): generate once, slice; kept separate so a
-    # future streaming generator can avoid materialising all n elements on every rank
-    return synthetic_coeffs(field, n, seed=0)[lo:hi]
