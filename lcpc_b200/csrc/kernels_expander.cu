@@ -28,6 +28,9 @@
 
 namespace lcpc {
 
+constexpr size_t FUSED_SMEM_BYTES = 40 << 10;  // window + temporary of the fused innermost levels
+constexpr int MAX_FUSED_OPS = 16;
+
 struct DeviceCsr {
   size_t m = 0, n = 0, nnz = 0;
   uint32_t *rowptr = nullptr;  // m + 1
@@ -47,6 +50,9 @@ struct ExpanderCode {
   size_t n_levels = 0, n_in = 0, n_cols = 0, nnz = 0, tmp_len = 0;
   std::vector<DeviceCsr> mats;
   std::vector<ExpanderOp> ops;
+  // ops [fuse_lo, fuse_hi] (the innermost levels around the Reed-Solomon base) touch only the codeword window
+  // [win_lo, win_lo + win_len) and run as ONE kernel with that window in shared memory; fuse_lo > fuse_hi: none
+  size_t fuse_lo = 1, fuse_hi = 0, win_lo = 0, win_len = 0;
 };
 
 size_t expander_n_in(const ExpanderCode *c) { return c->n_in; }
@@ -169,6 +175,20 @@ int expander_build(int field, size_t t, const CscView *pre, const CscView *post,
     return rc;
   }
   for (auto &m : c->mats) c->nnz += m.nnz;
+  // innermost levels: grow the window outwards from the base code while it fits the shared-memory budget
+  {
+    const size_t cap_elems = FUSED_SMEM_BYTES / field_bytes(field);
+    const size_t q = t;  // index of the Reed-Solomon op: ops = pre_0..pre_{t-1}, RS, post_{t-1}..post_0
+    size_t lo = q, hi = q;
+    size_t wlo = c->ops[q].out_off, wend = c->ops[q].out_off + c->ops[q].out_len;
+    while (lo > 0 && hi + 1 < c->ops.size()) {
+      const ExpanderOp &pre_op = c->ops[lo - 1], &post_op = c->ops[hi + 1];
+      const size_t nlo = pre_op.in_off, nend = post_op.out_off + post_op.out_len;
+      if (nend - nlo + c->tmp_len > cap_elems || (hi - lo + 1) + 2 > (size_t)MAX_FUSED_OPS) break;
+      lo--, hi++, wlo = nlo, wend = nend;
+    }
+    if (hi > lo) c->fuse_lo = lo, c->fuse_hi = hi, c->win_lo = wlo, c->win_len = wend - wlo;
+  }
   *out = c;
   return LCPC_B200_OK;
 }
@@ -333,6 +353,76 @@ reed_solomon_kernel(const uint32_t *__restrict__ xin, size_t n_in, uint32_t *__r
   stv<N>(out + (k * n_rows + r) * N, acc.v);
 }
 
+// The innermost levels of the chain for one batch row per CTA, the touched codeword window staged in shared
+// memory: sizes there are a few hundred outputs per level, so separate launches are pure latency.
+struct FusedOp {
+  int kind;  // 0 sparse product, 1 reed-solomon
+  const uint32_t *rowptr, *colidx, *vals;
+  uint32_t in_off, in_len, out_off, out_len;  // offsets relative to the window start
+  int in_tmp, out_tmp;
+};
+struct FusedOps {
+  int n;
+  FusedOp op[MAX_FUSED_OPS];
+};
+
+template <int FID>
+__global__ void __launch_bounds__(256)
+fused_levels_kernel(FusedOps ops, uint32_t *__restrict__ W, size_t n_rows, uint32_t win_lo, uint32_t win_len,
+                    uint32_t first_in_len, uint32_t tmp_len) {
+  using F = Field<FID>;
+  constexpr int N = F::N;
+  extern __shared__ __align__(16) uint32_t fsm[];
+  uint32_t *win = fsm, *tmp = fsm + (size_t)win_len * N;
+  const size_t r = blockIdx.x;
+  // the first op's input (x_i) is the only part of the window computed before this kernel
+  for (uint32_t e = threadIdx.x; e < first_in_len; e += blockDim.x) {
+    uint32_t v[N];
+    ldv<N>(v, W + ((size_t)(win_lo + e) * n_rows + r) * N);
+    stv<N>(win + (size_t)e * N, v);
+  }
+  __syncthreads();
+  typename F::Elem one = F::zero();
+  one.v[0] = 1;
+  for (int i = 0; i < 32 * N; i++) one = F::add(one, one);  // R mod p
+  for (int o = 0; o < ops.n; o++) {
+    const FusedOp &op = ops.op[o];
+    const uint32_t *in = (op.in_tmp ? tmp : win + (size_t)op.in_off * N);
+    uint32_t *out = (op.out_tmp ? tmp : win + (size_t)op.out_off * N);
+    for (uint32_t i = threadIdx.x; i < op.out_len; i += blockDim.x) {
+      typename F::Elem res;
+      if (op.kind == 0) {
+        const uint32_t k0 = __ldg(op.rowptr + i), k1 = __ldg(op.rowptr + i + 1);
+        typename F::Wide acc = F::wide_zero();
+        for (uint32_t k = k0; k < k1; k++) {
+          const uint32_t j = __ldg(op.colidx + k);
+          typename F::Elem a, xv;
+          ldv<N>(a.v, op.vals + (size_t)k * N);
+          ldv<N>(xv.v, in + (size_t)j * N);
+          F::mac_wide(acc, a, xv);
+        }
+        res = F::template redc<2>(acc);
+      } else {  // reed_solomon (encode.rs:97-110): Horner at the point i + 1
+        typename F::Elem pt = one;
+        for (uint32_t q = 0; q < i; q++) pt = F::add(pt, one);
+        res = F::zero();
+        for (uint32_t j = op.in_len; j-- > 0;) {
+          typename F::Elem cf;
+          ldv<N>(cf.v, in + (size_t)j * N);
+          res = F::add(F::mul(res, pt), cf);
+        }
+      }
+      stv<N>(out + (size_t)i * N, res.v);
+    }
+    __syncthreads();
+  }
+  for (uint32_t e = first_in_len + threadIdx.x; e < win_len; e += blockDim.x) {
+    uint32_t v[N];
+    ldv<N>(v, win + (size_t)e * N);
+    stv<N>(W + ((size_t)(win_lo + e) * n_rows + r) * N, v);
+  }
+}
+
 template <int FID> __global__ void one_mont_kernel(uint32_t *out) {
   using F = Field<FID>;
   typename F::Elem one = F::zero();
@@ -362,7 +452,41 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
     transpose_kernel<N><<<grid, 256, 0, st>>>(src, src_stride, W, n_rows, n_rows, c->n_in, none);
     launches++;
   }
-  for (const ExpanderOp &op : c->ops) {
+  for (size_t oi = 0; oi < c->ops.size(); oi++) {
+    const ExpanderOp &op = c->ops[oi];
+    if (oi == c->fuse_lo && c->fuse_hi > c->fuse_lo) {
+      FusedOps fo;
+      fo.n = 0;
+      for (size_t q = c->fuse_lo; q <= c->fuse_hi; q++) {
+        const ExpanderOp &g = c->ops[q];
+        FusedOp &f = fo.op[fo.n++];
+        f.kind = g.kind, f.in_tmp = g.in_tmp, f.out_tmp = g.out_tmp;
+        f.in_len = (uint32_t)g.in_len, f.out_len = (uint32_t)g.out_len;
+        f.in_off = g.in_tmp ? 0 : (uint32_t)(g.in_off - c->win_lo);
+        f.out_off = g.out_tmp ? 0 : (uint32_t)(g.out_off - c->win_lo);
+        if (g.kind == 0) {
+          const DeviceCsr &M = c->mats[g.mat];
+          f.rowptr = M.rowptr, f.colidx = M.colidx, f.vals = M.vals;
+        } else {
+          f.rowptr = f.colidx = f.vals = nullptr;
+        }
+      }
+      const size_t smem = (c->win_len + c->tmp_len) * F::BYTES;
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(fused_levels_kernel<FID>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)FUSED_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+      }
+      fused_levels_kernel<FID><<<(unsigned)n_rows, 256, smem, st>>>(fo, W, n_rows, (uint32_t)c->win_lo, (uint32_t)c->win_len,
+                                                                    (uint32_t)c->ops[c->fuse_lo].in_len, (uint32_t)c->tmp_len);
+      launches++;
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+      oi = c->fuse_hi;
+      continue;
+    }
     if (op.kind == 0) {
       const DeviceCsr &M = c->mats[op.mat];
       const uint32_t *x = W + op.in_off * n_rows * N;

@@ -377,3 +377,57 @@ def test_commit_from_device_memory(kind, field, length):
         oc = oenc.commit(x)
         assert c.get_root().root == oc["root"]
         assert (c.coeffs == oc["coeffs"]).all() and (c.comm == oc["comm"]).all() and (c.hashes == oc["hashes"]).all()
+
+
+@pytest.mark.parametrize("kind,field,n_per_row", [("ligero", P.FT255, 1 << 12), ("ligero", P.FT255, 1 << 14),
+                                                  ("ligero", P.FT127, 1 << 9), ("sdig", P.FT127, 2000)])
+def test_encode_rows_scatter_store(kind, field, n_per_row):
+    """The fused encode + transpose step of the multi-GPU commit on ONE GPU: the last pass stores column block h
+    of every row into its own [total rows][width_h] matrix (here three local buffers with uneven widths and a
+    row offset) instead of row-major comm.  Result == the oracle's row encodes, cut into the same blocks."""
+    import ctypes as C
+
+    import torch
+    from lcpc_b200 import _cabi
+    if kind == "ligero":
+        enc = P.LigeroEncoding.new_from_dims(field, n_per_row, 2 * n_per_row)
+        oenc = O.Encoding.ligero_from_dims(field, n_per_row, 2 * n_per_row)
+    else:
+        enc, oenc = P.SdigEncoding.new_from_dims(field, n_per_row, seed=2), O.Encoding.sdig_from_dims(field, n_per_row, seed=2)
+    n_cols, L = enc.n_cols, enc.L
+    n_rows, row0, total_rows = 5, 2, 9
+    dev = torch.device("cuda", enc.ctx.device)
+    x = O.random_elems(field, n_rows * n_per_row, seed=77).reshape(n_rows, n_per_row, L)
+    d_src = torch.from_numpy(x.view(np.int64).reshape(-1)).to(dev)
+    d_tmp = torch.zeros(n_rows * n_cols * L, dtype=torch.int64, device=dev)
+    starts = np.array([0, n_cols // 3 + 1, n_cols // 3 + 1, n_cols - 5, n_cols], dtype=np.uint64)  # one empty block
+    bufs = [torch.full((total_rows * int(starts[h + 1] - starts[h]) * L + 1,), -1, dtype=torch.int64, device=dev)
+            for h in range(4)]
+    ptrs = np.array([b.data_ptr() for b in bufs], dtype=np.uint64)
+    sc = _cabi.Scatter(4, starts.ctypes.data, ptrs.ctypes.data, row0)
+    lib = _cabi.lib()
+    rc = lib.lcpc_b200_encode_rows_scatter_dev(enc._h, C.c_void_p(d_src.data_ptr()), n_per_row, n_per_row,
+                                               C.c_void_p(d_tmp.data_ptr()), n_rows, C.byref(sc))
+    assert rc == 0, enc.ctx.last_error() if hasattr(enc.ctx, "last_error") else rc
+    enc.ctx.synchronize()
+    want = np.zeros((n_rows, n_cols, L), np.uint64)
+    for r in range(n_rows):
+        row = np.zeros((n_cols, L), np.uint64)
+        row[:n_per_row] = x[r]
+        want[r] = oenc.encode(row)
+    for h in range(4):
+        w = int(starts[h + 1] - starts[h])
+        got = bufs[h].cpu().numpy().view(np.uint64)
+        assert got[-1] == np.uint64(0xffffffffffffffff)  # guard word untouched
+        m = got[:-1].reshape(total_rows, w, L)
+        assert (m[row0:row0 + n_rows] == want[:, int(starts[h]):int(starts[h + 1])]).all(), h
+        rest = np.delete(m, np.s_[row0:row0 + n_rows], axis=0)
+        assert (rest == np.uint64(0xffffffffffffffff)).all()  # rows of other ranks untouched
+    # descriptor validation
+    bad = np.array([0, 10, n_cols - 1], dtype=np.uint64)  # does not end at n_cols
+    sc2 = _cabi.Scatter(2, bad.ctypes.data, ptrs.ctypes.data, 0)
+    assert lib.lcpc_b200_encode_rows_scatter_dev(enc._h, C.c_void_p(d_src.data_ptr()), n_per_row, n_per_row,
+                                                 C.c_void_p(d_tmp.data_ptr()), n_rows, C.byref(sc2)) == _cabi.ERR_BAD_ARG
+    sc3 = _cabi.Scatter(17, starts.ctypes.data, ptrs.ctypes.data, 0)  # more than 16 blocks
+    assert lib.lcpc_b200_encode_rows_scatter_dev(enc._h, C.c_void_p(d_src.data_ptr()), n_per_row, n_per_row,
+                                                 C.c_void_p(d_tmp.data_ptr()), n_rows, C.byref(sc3)) == _cabi.ERR_BAD_ARG
