@@ -343,8 +343,9 @@ def bench_single(args, ctx, enc, field, n, torch, P):
     if enc.__class__.__name__ == "LigeroEncoding":
         per_pass = []
         n_pass = max(1, nl[0])
-        # pass 1 reads the coefficient rows and writes comm; later passes read + write comm
-        per_pass.append(B * n_rows * (n_per_row + n_cols))
+        # pass 1 reads the coefficient rows, writes the commit's own copy of them (the pad/copy of the reference,
+        # folded into the pass) and writes comm; later passes read + write comm
+        per_pass.append(B * n_rows * (2 * n_per_row + n_cols))
         for _ in range(n_pass - 1):
             per_pass.append(2 * B * n_rows * n_cols)
         dominant = dict(kernel="ntt_pass_kernel", launches_per_step=n_pass, ms_per_launch=phases[1] / n_pass,
