@@ -5,11 +5,13 @@
 //   for gap = n/2 .. 1:  (a, b) <- (a + b, (a - b) * w^(idx * n/(2 gap))),  idx = position mod gap.
 // Field arithmetic is exact, so any schedule of those butterflies gives bit-identical limbs.
 //
-// Schedule: the log2(n) stages are cut into passes of S <= 9 consecutive stages.  One CTA owns a tile
+// Schedule: the log2(n) stages are cut into passes of S <= 10 consecutive stages.  One CTA owns a tile
 // of 2^S points along the pass's stride times C adjacent points (C*B contiguous bytes in HBM), stages
-// it in shared memory, runs the S stages there and writes it back: one HBM read + one write per pass.
-// The first pass reads the un-padded coefficient rows directly (implicit zeros beyond n_per_row), so
-// the reference's separate pad/copy (lcpc-2d/src/lib.rs:640-651) costs no extra traffic.
+// it in shared memory, runs the S stages there in radix-8 register rounds and writes it back: one HBM
+// read + one write per pass.  The first pass reads the un-padded coefficient rows directly (implicit zeros
+// beyond n_per_row) and can store the commit's copy of them on the way, so the reference's separate
+// pad/copy (lcpc-2d/src/lib.rs:640-651) costs no extra read; the last pass can store per column block
+// (multi-GPU exchange fused into the transform).
 #include <algorithm>
 
 #include "field.cuh"
@@ -78,35 +80,6 @@ __device__ __forceinline__ void gstore(uint32_t *p, const uint32_t (&v)[N]) {
   } else {
 #pragma unroll
     for (int i = 0; i < N / 2; i++) reinterpret_cast<uint2 *>(p)[i] = make_uint2(v[2 * i], v[2 * i + 1]);
-  }
-}
-
-template <int N>
-__device__ __forceinline__ void sload(uint32_t (&v)[N], const uint32_t *smem, unsigned e, unsigned tile) {
-  constexpr int PW = Planes<N>::PW, NP = Planes<N>::NP;
-#pragma unroll
-  for (int pl = 0; pl < NP; pl++) {
-    const uint32_t *q = smem + ((size_t)pl * tile + e) * PW;
-    if constexpr (PW == 4) {
-      uint4 t = *reinterpret_cast<const uint4 *>(q);
-      v[4 * pl] = t.x, v[4 * pl + 1] = t.y, v[4 * pl + 2] = t.z, v[4 * pl + 3] = t.w;
-    } else {
-      uint2 t = *reinterpret_cast<const uint2 *>(q);
-      v[2 * pl] = t.x, v[2 * pl + 1] = t.y;
-    }
-  }
-}
-
-template <int N>
-__device__ __forceinline__ void sstore(uint32_t *smem, unsigned e, unsigned tile, const uint32_t (&v)[N]) {
-  constexpr int PW = Planes<N>::PW, NP = Planes<N>::NP;
-#pragma unroll
-  for (int pl = 0; pl < NP; pl++) {
-    uint32_t *q = smem + ((size_t)pl * tile + e) * PW;
-    if constexpr (PW == 4)
-      *reinterpret_cast<uint4 *>(q) = make_uint4(v[4 * pl], v[4 * pl + 1], v[4 * pl + 2], v[4 * pl + 3]);
-    else
-      *reinterpret_cast<uint2 *>(q) = make_uint2(v[2 * pl], v[2 * pl + 1]);
   }
 }
 

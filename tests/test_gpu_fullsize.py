@@ -102,3 +102,20 @@ def test_ligero_ragged_length_chunked_host_copy():
     y = O.random_elems(field, length, seed=22)
     c.rerun(y)
     assert oenc.commit(y)["root"] == c.get_root().root
+
+
+def test_ligero_ft255_2_26_sampled():
+    """Beyond the headline size: 512 x 131072 -> 262144 (2^18-point rows, 17-chunk leaves, 2 GiB of coefficients
+    crossing PCIe in 16 row-chunks with hashing trailing the encode)."""
+    field, length = P.FT255, 1 << 26
+    enc, oenc = P.LigeroEncoding(field, length), O.Encoding.ligero(field, length)
+    assert (enc.n_per_row, enc.n_cols) == (131072, 262144)
+    x = O.random_elems(field, length, seed=26)
+    c = P.LcCommit.commit(x, enc)
+    assert c.n_rows == 512
+    check_commit_samples(c, oenc, x, field, rows=[0, 300, 511], cols=[0, 1, 131071, 131072, 262143, 77777])
+    vals, paths = c.open_columns([5, 262143])
+    comm = c.comm.reshape(c.n_rows, c.n_cols, 4)
+    for i, col in enumerate([5, 262143]):
+        assert (vals[i] == comm[:, col]).all()
+        assert O.verify_column_path(field, vals[i], paths[i], col, c.get_root().root)

@@ -431,3 +431,24 @@ def test_encode_rows_scatter_store(kind, field, n_per_row):
     sc3 = _cabi.Scatter(17, starts.ctypes.data, ptrs.ctypes.data, 0)  # more than 16 blocks
     assert lib.lcpc_b200_encode_rows_scatter_dev(enc._h, C.c_void_p(d_src.data_ptr()), n_per_row, n_per_row,
                                                  C.c_void_p(d_tmp.data_ptr()), n_rows, C.byref(sc3)) == _cabi.ERR_BAD_ARG
+
+
+@pytest.mark.parametrize("field", FIELDS)
+@pytest.mark.parametrize("length", [1, 2, 3, 17, 100, 1000])
+def test_commit_tiny_lengths(field, length):
+    """The smallest polynomials `_get_dims` accepts (lcpc-ligero-pc/src/lib.rs:70-112): one or two rows, rows
+    shorter than a warp, a ragged last row."""
+    try:
+        oenc = O.Encoding.ligero(field, length)
+    except Exception:
+        with pytest.raises(P.LcpcError):
+            P.LigeroEncoding(field, length)
+        return
+    enc = P.LigeroEncoding(field, length)
+    assert enc.get_dims(length) == oenc.get_dims(length)
+    x = O.random_elems(field, length, seed=length)
+    c, oc = P.LcCommit.commit(x, enc), oenc.commit(x)
+    assert c.get_root().root == oc["root"]
+    assert (c.comm == oc["comm"]).all() and (c.coeffs == oc["coeffs"]).all() and (c.hashes == oc["hashes"]).all()
+    t = O.random_elems(field, c.n_rows, seed=3)
+    assert (c.collapse(t) == O.collapse(field, oc["coeffs"], t, c.n_rows, c.n_per_row)).all()
