@@ -333,10 +333,18 @@ def bench_single(args, ctx, enc, field, n, torch, P):
     for t in tensors:
         commit.collapse(t)
     t_collapse = time.perf_counter() - t0
+    # the same n_degree_tests combinations with the challenge tensor expanded on the device from a 32-byte key
+    keys = [bytes([i]) * 32 for i in range(max(1, n_comb - 1))]
+    commit.degree_test(keys[0])
+    t0 = time.perf_counter()
+    for k in keys:
+        commit.degree_test(k)
+    t_degree = time.perf_counter() - t0
     t0 = time.perf_counter()
     commit.open_columns(cols)
     t_open = time.perf_counter() - t0
-    prove = {"collapse_ms": t_collapse * 1e3, "n_collapse": n_comb, "open_columns_ms": t_open * 1e3,
+    prove = {"collapse_ms": t_collapse * 1e3, "n_collapse": n_comb, "degree_test_ms": t_degree * 1e3,
+             "n_degree_tests": len(keys), "open_columns_ms": t_open * 1e3,
              "n_col_opens": int(cols.shape[0]), "note": "host API wall time on the device-resident LcCommit"}
     ms_per_step = total_ms / args.steps
     B = 8 * L

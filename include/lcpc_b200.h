@@ -169,6 +169,14 @@ int lcpc_b200_commit_to_host(lcpc_b200_enc *enc, const uint64_t *coeffs_in, size
 /* collapse_columns (lcpc-2d/src/lib.rs:1095-1123; call sites :1034, :1055):
  * poly[c] = sum_r tensor[r] * coeffs[r*n_per_row + c]; tensor: n_rows elements, poly: n_per_row (host) */
 int lcpc_b200_commit_collapse(lcpc_b200_commit *c, const uint64_t *tensor, uint64_t *poly);
+/* One degree test of prove() (lcpc-2d/src/lib.rs:1026-1041) without the tensor crossing PCIe: `key` is the 32
+ * bytes the transcript yields for LABEL_DT (:1026-1027); the device expands ChaCha20Rng::from_seed(key) into
+ * n_rows x F::random (:1028-1032, the step the reference marks "could expand seed in parallel") and collapses
+ * the coefficient matrix with it (:1033-1041).  poly: n_per_row elements; tensor_out (optional): the n_rows
+ * tensor elements, for callers that want to cross-check. */
+int lcpc_b200_commit_degree_test(lcpc_b200_commit *c, const uint8_t key[32], uint64_t *poly, uint64_t *tensor_out);
+/* the expansion alone: out[0..n) = n x F::random from ChaCha20Rng::from_seed(key) (also what verify() draws, :868-877) */
+int lcpc_b200_expand_tensor(lcpc_b200_ctx *ctx, int field, const uint8_t key[32], size_t n, uint64_t *out);
 /* stateless form on host arrays */
 int lcpc_b200_collapse(lcpc_b200_ctx *ctx, int field, const uint64_t *coeffs, const uint64_t *tensor,
                        uint64_t *poly, size_t n_rows, size_t n_per_row);

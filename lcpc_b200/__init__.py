@@ -22,9 +22,9 @@ the C ABI; there is no CPU implementation in this package.
 """
 from .host import (FT63, FT127, FT191, FT255, FIELD_LIMBS, Context, LcCommit, LcEncoding, LcRoot,  # noqa: F401
                    LigeroEncoding, SdigEncoding, default_context, field_op, merkleize, collapse_columns,
-                   ligero_get_dims, n_degree_tests)
+                   ligero_get_dims, n_degree_tests, expand_tensor)
 from ._cabi import LcpcError, LIB_PATH  # noqa: F401
 
 __all__ = ["FT63", "FT127", "FT191", "FT255", "FIELD_LIMBS", "Context", "LcCommit", "LcEncoding", "LcRoot",
            "LigeroEncoding", "SdigEncoding", "LcpcError", "default_context", "field_op", "merkleize",
-           "collapse_columns", "ligero_get_dims", "n_degree_tests"]
+           "collapse_columns", "ligero_get_dims", "n_degree_tests", "expand_tensor"]

@@ -79,6 +79,8 @@ SIGNATURES = {
     "lcpc_b200_commit_device_ptrs": (_i, [_vp, _pvp, _pvp, _pvp]),
     "lcpc_b200_commit_to_host": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "lcpc_b200_commit_collapse": (_i, [_vp, _vp, _vp]),
+    "lcpc_b200_commit_degree_test": (_i, [_vp, _vp, _vp, _vp]),
+    "lcpc_b200_expand_tensor": (_i, [_vp, _i, _vp, _sz, _vp]),
     "lcpc_b200_collapse": (_i, [_vp, _i, _vp, _vp, _vp, _sz, _sz]),
     "lcpc_b200_commit_open_columns": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "lcpc_b200_merkleize": (_i, [_vp, _i, _vp, _sz, _sz, _vp]),

@@ -160,7 +160,7 @@ struct lcpc_b200_commit {
   void *d_hash_scratch = nullptr;
   void *d_enc_scratch = nullptr;
   // prove-side staging
-  uint32_t *d_tensor = nullptr, *d_poly = nullptr;
+  uint32_t *d_tensor = nullptr, *d_poly = nullptr, *d_key = nullptr;
   // phase boundaries of the last run: start | copy+pad | encode | leaf hash | merkle
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   int encode_launches = 0, hash_launches = 0, merkle_launches = 0;
@@ -550,6 +550,7 @@ static void commit_release(lcpc_b200_commit *c) {
   cudaFree(c->d_enc_scratch);
   cudaFree(c->d_tensor);
   cudaFree(c->d_poly);
+  cudaFree(c->d_key);
   for (auto &e : c->ev)
     if (e) cudaEventDestroy(e);
   delete c;
@@ -808,6 +809,54 @@ int lcpc_b200_commit_collapse(lcpc_b200_commit *c, const uint64_t *tensor, uint6
   ctx->launches += nl;
   if (ce != cudaSuccess) return cuda_fail(ctx, ce, "collapse");
   CU(ctx, cudaMemcpyAsync(poly, c->d_poly, c->n_per_row * B, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return LCPC_B200_OK;
+}
+
+// challenge tensor on the device: key -> d_tensor (n_rows elements), enqueue only
+static int expand_tensor_into(lcpc_b200_commit *c, const uint8_t key[32]) {
+  lcpc_b200_ctx *ctx = c->enc->ctx;
+  if (!c->d_key) CU(ctx, cudaMalloc(&c->d_key, 32));
+  CU(ctx, cudaMemcpyAsync(c->d_key, key, 32, cudaMemcpyHostToDevice, ctx->stream));
+  cudaError_t ce = launch_expand_tensor(c->enc->field, c->d_key, 0, c->n_rows, c->d_tensor, ctx->stream);
+  ctx->launches += 1;
+  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "expand_tensor");
+  return LCPC_B200_OK;
+}
+
+int lcpc_b200_commit_degree_test(lcpc_b200_commit *c, const uint8_t key[32], uint64_t *poly, uint64_t *tensor_out) {
+  if (!c || !key || !poly) return LCPC_B200_ERR_BAD_ARG;
+  lcpc_b200_ctx *ctx = c->enc->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (int rc = bind_device(ctx)) return rc;
+  const int field = c->enc->field;
+  const size_t B = field_bytes(field);
+  if (int rc = expand_tensor_into(c, key)) return rc;
+  int nl = 0;
+  cudaError_t ce = launch_collapse(field, c->d_coeffs, c->n_per_row, c->d_tensor, c->d_poly, c->n_rows, c->n_per_row,
+                                   nullptr, ctx->stream, &nl);
+  ctx->launches += nl;
+  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "collapse");
+  CU(ctx, cudaMemcpyAsync(poly, c->d_poly, c->n_per_row * B, cudaMemcpyDeviceToHost, ctx->stream));
+  if (tensor_out) CU(ctx, cudaMemcpyAsync(tensor_out, c->d_tensor, c->n_rows * B, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return LCPC_B200_OK;
+}
+
+int lcpc_b200_expand_tensor(lcpc_b200_ctx *ctx, int field, const uint8_t key[32], size_t n, uint64_t *out) {
+  if (!ctx || !key || (!out && n)) return LCPC_B200_ERR_BAD_ARG;
+  if (field_limbs32(field) < 0) return fail(ctx, LCPC_B200_ERR_BAD_ARG, "unknown field %d", field);
+  if (n == 0) return LCPC_B200_OK;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (int rc = bind_device(ctx)) return rc;
+  const size_t bytes = n * field_bytes(field);
+  if (int rc = ensure_scratch(ctx, 256 + bytes)) return rc;
+  uint8_t *base = (uint8_t *)ctx->scratch;
+  CU(ctx, cudaMemcpyAsync(base, key, 32, cudaMemcpyHostToDevice, ctx->stream));
+  cudaError_t ce = launch_expand_tensor(field, (const uint32_t *)base, 0, n, (uint32_t *)(base + 256), ctx->stream);
+  ctx->launches += 1;
+  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "expand_tensor");
+  CU(ctx, cudaMemcpyAsync(out, base + 256, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   return LCPC_B200_OK;
 }

@@ -77,6 +77,11 @@ cudaError_t launch_collapse(int field, const uint32_t *coeffs, size_t row_stride
                             uint32_t *poly, size_t n_rows, size_t n_per_row, void *scratch, cudaStream_t stream,
                             int *n_launches);
 
+// ---- challenge tensor (lcpc-2d/src/lib.rs:1026-1032): out[0..n) = n x F::random from ChaCha20Rng::from_seed(key)
+// with stream id `stream_id` (0 for from_seed); d_key: the 32-byte key as 8 little-endian words in device memory
+cudaError_t launch_expand_tensor(int field, const uint32_t *d_key, uint64_t stream_id, size_t n, uint32_t *d_out,
+                                 cudaStream_t stream);
+
 // ---- open_column gather (lcpc-2d/src/lib.rs:802-808): out[i][r] = comm[r][cols[i]] ----
 cudaError_t launch_gather_columns(int field, const uint32_t *comm, size_t n_rows, size_t row_stride,
                                   const uint64_t *cols, size_t n_open, uint32_t *out, cudaStream_t stream);

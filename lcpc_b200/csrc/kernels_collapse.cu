@@ -91,6 +91,123 @@ cudaError_t launch_collapse(int field, const uint32_t *coeffs, size_t row_stride
   return e;
 }
 
+// ---- challenge tensor expansion (lcpc-2d/src/lib.rs:1026-1032: ChaCha20Rng::from_seed(key), then n_rows x
+// F::random; the reference notes "could expand seed in parallel instead of in series") ----------------------
+// F::random (ff_derive) draws L u64 words, masks the top limb to NUM_BITS and keeps the candidate iff it is < p,
+// taking the accepted limbs as the Montgomery image.  A u64 is two consecutive u32 words of the ChaCha20
+// stream, so candidate c is exactly words [2L c, 2L (c+1)) of the stream: every thread builds one candidate from
+// the one or two ChaCha20 blocks holding its words, a block-wide scan ranks the accepted ones, and rounds of
+// blockDim candidates repeat until n are out.  One CTA: n is the row count of the commitment (hundreds).
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int n) { return __funnelshift_l(x, x, n); }
+#define LCPC_CHACHA_QR(a, b, c, d)   \
+  do {                              \
+    a += b, d ^= a, d = rotl32(d, 16); \
+    c += d, b ^= c, b = rotl32(b, 12); \
+    a += b, d ^= a, d = rotl32(d, 8);  \
+    c += d, b ^= c, b = rotl32(b, 7);  \
+  } while (0)
+__device__ void chacha20_block(const uint32_t (&key)[8], uint64_t counter, uint64_t stream, uint32_t (&out)[16]) {
+  uint32_t s[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3],
+                    key[4], key[5], key[6], key[7], (uint32_t)counter, (uint32_t)(counter >> 32),
+                    (uint32_t)stream, (uint32_t)(stream >> 32)};
+  uint32_t x[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) x[i] = s[i];
+  for (int r = 0; r < 10; r++) {
+    LCPC_CHACHA_QR(x[0], x[4], x[8], x[12]);
+    LCPC_CHACHA_QR(x[1], x[5], x[9], x[13]);
+    LCPC_CHACHA_QR(x[2], x[6], x[10], x[14]);
+    LCPC_CHACHA_QR(x[3], x[7], x[11], x[15]);
+    LCPC_CHACHA_QR(x[0], x[5], x[10], x[15]);
+    LCPC_CHACHA_QR(x[1], x[6], x[11], x[12]);
+    LCPC_CHACHA_QR(x[2], x[7], x[8], x[13]);
+    LCPC_CHACHA_QR(x[3], x[4], x[9], x[14]);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; i++) out[i] = x[i] + s[i];
+}
+
+constexpr int EXPAND_THREADS = 256;
+template <int FID>
+__global__ void __launch_bounds__(EXPAND_THREADS)
+expand_tensor_kernel(const uint32_t *__restrict__ key_in, uint64_t stream, size_t n, uint32_t num_bits,
+                     uint32_t *__restrict__ out) {
+  using F = Field<FID>;
+  constexpr int N = F::N;
+  __shared__ uint32_t warp_sums[EXPAND_THREADS / 32];
+  __shared__ uint32_t round_total;
+  uint32_t key[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) key[i] = key_in[i];
+  const uint32_t top_mask = (num_bits % 32) ? ((1u << (num_bits % 32)) - 1u) : 0xffffffffu;
+  size_t done = 0;
+  for (uint64_t base = 0; done < n; base += EXPAND_THREADS) {
+    const uint64_t c = base + threadIdx.x;          // candidate index
+    const uint64_t w0 = c * N;                      // its first stream word
+    uint32_t cand[N];
+    {
+      uint32_t blk[16];
+      uint64_t b = w0 / 16;
+      chacha20_block(key, b, stream, blk);
+#pragma unroll
+      for (int l = 0; l < N; l++) {
+        const uint64_t w = w0 + l;
+        if (w / 16 != b) {  // the candidate runs into the next block (Ft191: 6 words per candidate)
+          b = w / 16;
+          chacha20_block(key, b, stream, blk);
+        }
+        uint32_t v = 0;
+#pragma unroll
+        for (int q = 0; q < 16; q++)
+          if (q == (int)(w % 16)) v = blk[q];
+        cand[l] = v;
+      }
+    }
+    cand[N - 1] &= top_mask;
+    // accept iff cand < p
+    bool lt = false, decided = false;
+#pragma unroll
+    for (int l = N - 1; l >= 0; l--) {
+      if (!decided && cand[l] != FieldP<FID>::P(l)) lt = cand[l] < FieldP<FID>::P(l), decided = true;
+    }
+    const uint32_t ok = lt ? 1u : 0u;
+    // rank among the accepted candidates of this round (warp ballot + warp totals)
+    const unsigned lane = threadIdx.x % 32, wid = threadIdx.x / 32;
+    const uint32_t ballot = __ballot_sync(0xffffffffu, ok);
+    const uint32_t before = __popc(ballot & ((1u << lane) - 1u));
+    if (lane == 0) warp_sums[wid] = __popc(ballot);
+    __syncthreads();
+    uint32_t off = 0, tot = 0;
+#pragma unroll
+    for (int q = 0; q < EXPAND_THREADS / 32; q++) {
+      if (q < (int)wid) off += warp_sums[q];
+      tot += warp_sums[q];
+    }
+    const size_t pos = done + off + before;
+    if (ok && pos < n) {
+#pragma unroll
+      for (int l = 0; l < N; l++) out[pos * N + l] = cand[l];
+    }
+    if (threadIdx.x == 0) round_total = tot;
+    __syncthreads();
+    done += round_total;
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_expand_tensor(int field, const uint32_t *d_key, uint64_t stream_id, size_t n, uint32_t *d_out,
+                                 cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  switch (field) {  // NUM_BITS of the fields (lcpc-test-fields/src/lib.rs:13-59)
+    case FT63: expand_tensor_kernel<FT63><<<1, EXPAND_THREADS, 0, stream>>>(d_key, stream_id, n, 63, d_out); break;
+    case FT127: expand_tensor_kernel<FT127><<<1, EXPAND_THREADS, 0, stream>>>(d_key, stream_id, n, 127, d_out); break;
+    case FT191: expand_tensor_kernel<FT191><<<1, EXPAND_THREADS, 0, stream>>>(d_key, stream_id, n, 191, d_out); break;
+    case FT255: expand_tensor_kernel<FT255><<<1, EXPAND_THREADS, 0, stream>>>(d_key, stream_id, n, 255, d_out); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
 // out[i * n_rows + r] = comm[r * row_stride + cols[i]]
 __global__ void gather_columns_kernel(const uint32_t *__restrict__ comm, size_t n_rows, size_t row_stride,
                                       const uint64_t *__restrict__ cols, size_t n_open, uint32_t *__restrict__ out,

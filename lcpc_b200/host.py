@@ -388,6 +388,17 @@ class LcCommit:
         _check(_cabi.lib().lcpc_b200_commit_collapse(self._h, _ptr(t), _ptr(poly)), self.enc.ctx)
         return poly
 
+    def degree_test(self, key: bytes, with_tensor: bool = False):
+        """One degree test of prove() (:1026-1041): the 32-byte transcript challenge `key` is expanded into the
+        random tensor on the device (ChaCha20Rng::from_seed + F::random) and collapsed against the coefficients."""
+        if len(key) != 32:
+            raise LcpcError(_cabi.ERR_BAD_ARG, "degree-test key must be 32 bytes")
+        kb = np.frombuffer(bytes(key), dtype=np.uint8).copy()
+        poly = np.empty((self.n_per_row, self.enc.L), np.uint64)
+        tensor = np.empty((self.n_rows, self.enc.L), np.uint64) if with_tensor else None
+        _check(_cabi.lib().lcpc_b200_commit_degree_test(self._h, _ptr(kb), _ptr(poly), _ptr(tensor)), self.enc.ctx)
+        return (poly, tensor) if with_tensor else poly
+
     def open_columns(self, cols):
         """open_column (:788-825) for every index in ``cols``: (values (n, n_rows, L), paths (n, path_len, 32))."""
         idx = np.ascontiguousarray(cols, dtype=np.uint64)
@@ -418,6 +429,17 @@ def collapse_columns(field: int, coeffs, tensor, n_rows: int, n_per_row: int, ct
     assert a.shape[0] == n_rows * n_per_row and t.shape[0] == n_rows
     out = np.empty((n_per_row, FIELD_LIMBS[field]), np.uint64)
     _check(_cabi.lib().lcpc_b200_collapse(ctx._h, field, _ptr(a), _ptr(t), _ptr(out), n_rows, n_per_row), ctx)
+    return out
+
+
+def expand_tensor(field: int, key: bytes, n: int, ctx: Context | None = None) -> np.ndarray:
+    """n x F::random from ChaCha20Rng::from_seed(key) on the device (lcpc-2d/src/lib.rs:1028-1032, 868-877)."""
+    ctx = ctx or default_context()
+    if len(key) != 32:
+        raise LcpcError(_cabi.ERR_BAD_ARG, "key must be 32 bytes")
+    kb = np.frombuffer(bytes(key), dtype=np.uint8).copy()
+    out = np.empty((n, FIELD_LIMBS[field]), np.uint64)
+    _check(_cabi.lib().lcpc_b200_expand_tensor(ctx._h, field, _ptr(kb), n, _ptr(out)), ctx)
     return out
 
 

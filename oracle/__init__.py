@@ -151,6 +151,15 @@ def random_elems(field, n, seed=0, stream=0) -> np.ndarray:
     return out
 
 
+def random_elems_from_key(field, key: bytes, n) -> np.ndarray:
+    """n x Field::random from ChaCha20Rng::from_seed(key) (lcpc-2d/src/lib.rs:1026-1032)."""
+    assert len(key) == 32
+    out = np.empty((n, FIELD_LIMBS[field]), np.uint64)
+    kb = np.frombuffer(bytes(key), dtype=np.uint8).copy()
+    assert lib().lcpc_oracle_random_elems_from_key(field, _p8(kb), _p64(out), _sz(n)) == 0
+    return out
+
+
 # ----------------------------------------------------------------------------- hash / rng
 def blake3(data: bytes) -> bytes:
     buf = np.frombuffer(bytes(data), dtype=np.uint8) if len(data) else np.zeros(0, np.uint8)

@@ -197,6 +197,18 @@ int lcpc_oracle_random_elems(int field, uint64_t seed, uint64_t stream, uint64_t
   return 0;
 }
 
+/* the prover's / verifier's challenge tensors (lcpc-2d/src/lib.rs:1026-1032, 868-877):
+ * ChaCha20Rng::from_seed(key), then n x Field::random */
+int lcpc_oracle_random_elems_from_key(int field, const uint8_t key[32], uint64_t *out, size_t n) {
+  chacha_rng rng;
+  chacha_from_seed(&rng, key);
+#define CALL(F) \
+  for (size_t i = 0; i < n; i++) F##_random(out + i * NLV, chacha_next_u64, &rng);
+  DISPATCH(field, CALL)
+#undef CALL
+  return 0;
+}
+
 void lcpc_oracle_blake3(const uint8_t *in, size_t len, uint8_t out[32]) { b3_hash(in, len, out); }
 
 void lcpc_oracle_chacha_block(const uint32_t key[8], uint64_t counter, uint64_t stream,

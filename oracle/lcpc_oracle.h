@@ -44,6 +44,9 @@ int lcpc_oracle_to_repr(int field, uint8_t *out, const uint64_t *a, size_t n);
 /* n uniform elements the way `Field::random` draws them from ChaCha20Rng::seed_from_u64(seed)
  * with set_stream(stream) */
 int lcpc_oracle_random_elems(int field, uint64_t seed, uint64_t stream, uint64_t *out, size_t n);
+/* n elements from ChaCha20Rng::from_seed(key): the challenge tensors of prove()/verify()
+ * (lcpc-2d/src/lib.rs:1026-1032, 868-877) */
+int lcpc_oracle_random_elems_from_key(int field, const uint8_t key[32], uint64_t *out, size_t n);
 
 /* ---- hash ---- */
 void lcpc_oracle_blake3(const uint8_t *in, size_t len, uint8_t out[32]);

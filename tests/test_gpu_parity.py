@@ -452,3 +452,29 @@ def test_commit_tiny_lengths(field, length):
     assert (c.comm == oc["comm"]).all() and (c.coeffs == oc["coeffs"]).all() and (c.hashes == oc["hashes"]).all()
     t = O.random_elems(field, c.n_rows, seed=3)
     assert (c.collapse(t) == O.collapse(field, oc["coeffs"], t, c.n_rows, c.n_per_row)).all()
+
+
+# ------------------------------------------------------------------ challenge tensors
+@pytest.mark.parametrize("field", FIELDS)
+@pytest.mark.parametrize("n", [1, 7, 256, 1000, 5000])
+def test_expand_tensor_vs_oracle(field, n):
+    """ChaCha20Rng::from_seed(key) + n x F::random (lcpc-2d/src/lib.rs:1026-1032) expanded in parallel on the
+    device == the oracle's serial draw, for keys that exercise early and late rejections."""
+    for k in range(3):
+        key = O.blake3(bytes([k, n % 251, field]))  # any 32 bytes
+        assert (P.expand_tensor(field, key, n) == O.random_elems_from_key(field, key, n)).all(), k
+
+
+def test_degree_test_matches_collapse_of_oracle_tensor():
+    field, length = P.FT255, 1 << 16
+    enc, oenc = P.LigeroEncoding(field, length), O.Encoding.ligero(field, length)
+    x = O.random_elems(field, length, seed=5)
+    c = P.LcCommit.commit(x, enc)
+    key = bytes(range(32))
+    poly, tensor = c.degree_test(key, with_tensor=True)
+    want_t = O.random_elems_from_key(field, key, c.n_rows)
+    assert (tensor == want_t).all()
+    assert (poly == O.collapse(field, c.coeffs, want_t, c.n_rows, c.n_per_row)).all()
+    assert (c.degree_test(key) == poly).all()
+    with pytest.raises(P.LcpcError):
+        c.degree_test(b"short")

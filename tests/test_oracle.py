@@ -325,3 +325,26 @@ def test_commit_evaluation_property():
     outer = [pow(pt, 32 * r, p) for r in range(4)]
     poly = O.from_mont(f, O.collapse(f, c["coeffs"], O.to_mont(f, outer), 4, 32))
     assert sum(a * b for a, b in zip(poly, inner)) % p == direct
+
+
+def test_random_elems_from_key_is_the_serial_rejection_draw():
+    """from_seed(key) + Field::random restated twice: the C oracle vs a direct Python walk over the ChaCha20
+    word stream (two u32 per u64, low word first; mask the top limb; reject >= p)."""
+    key = bytes((7 * i + 3) % 256 for i in range(32))
+    kw = np.frombuffer(key, dtype="<u4").astype(np.uint32)
+    for field in (O.FT63, O.FT127, O.FT191, O.FT255):
+        info = O.field_info(field)
+        p, nl, bits = info["modulus"], O.FIELD_LIMBS[field], info["num_bits"]
+        words, blk = [], 0
+        while len(words) < 2 * nl * 64:
+            words += [int(w) for w in O.chacha_block(kw, blk, 0)]
+            blk += 1
+        got, pos = [], 0
+        while len(got) < 20:
+            limbs = [words[pos + 2 * i] | (words[pos + 2 * i + 1] << 32) for i in range(nl)]
+            pos += 2 * nl
+            v = sum(l << (64 * i) for i, l in enumerate(limbs)) & ((1 << bits) - 1)
+            if v < p:
+                got.append(v)
+        want = O.random_elems_from_key(field, key, 20)
+        assert [sum(int(want[i, j]) << (64 * j) for j in range(nl)) for i in range(20)] == got
