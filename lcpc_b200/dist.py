@@ -218,6 +218,8 @@ class DistributedCommit:
             with self.ops.on_stream():
                 self.d_top[p.n_real_sub * 32:p.n_sub * 32] = pad
         self.ops.synchronize()
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)  # buffers above were zero-filled on torch's stream, not the engine stream
 
     # root of an all-padding subtree: T zero leaves hashed up (lcpc-2d/src/lib.rs:665,696 leave them zero)
     def _zero_subtree_root(self) -> bytes:

@@ -404,6 +404,7 @@ def test_encode_rows_scatter_store(kind, field, n_per_row):
     bufs = [torch.full((total_rows * int(starts[h + 1] - starts[h]) * L + 1,), -1, dtype=torch.int64, device=dev)
             for h in range(4)]
     ptrs = np.array([b.data_ptr() for b in bufs], dtype=np.uint64)
+    torch.cuda.synchronize()  # torch filled the buffers on its own stream; the engine stream does not wait for it
     sc = _cabi.Scatter(4, starts.ctypes.data, ptrs.ctypes.data, row0)
     lib = _cabi.lib()
     rc = lib.lcpc_b200_encode_rows_scatter_dev(enc._h, C.c_void_p(d_src.data_ptr()), n_per_row, n_per_row,
