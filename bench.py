@@ -249,7 +249,7 @@ def run_ours(args):
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             key = f"{args.workload}_{FIELD_NAMES[field]}_2^{args.lgl}"
-            if key in tr:
+            if key in tr and world == 1:
                 dk["traffic"] = tr[key]["dram_bytes_per_launch"]
         except Exception:
             pass

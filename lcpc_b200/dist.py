@@ -252,7 +252,10 @@ class DistributedCommit:
         start from host memory, its PCIe copy overlapped with the encode; without it the rows loaded by
         `load_rows_from_host` are encoded."""
         dist, p, ops = self.dist, self.plan, self.ops
+        ev = getattr(self, "phase_events", None)  # optional (start, encode done, exchange done, end) CUDA events
         with ops.on_stream():
+            if ev:
+                ev[0].record(ops.stream)
             if self.transport == "staged":
                 if self.my_rows:
                     if host_rows is not None:
@@ -275,12 +278,16 @@ class DistributedCommit:
                     else:
                         ops.encode_rows_scatter(self.d_coeffs, self.my_rows, p.n_per_row, self.d_comm_rows, p.col_lo,
                                                 ptrs, row0)
+            if ev:
+                ev[1].record(ops.stream)
             if self.transport == "p2p":
                 self.symm.barrier(channel=1)  # every rank's stores into this rank's matrix have landed
             else:
                 n_send, n_recv = sum(self.in_splits), sum(self.out_splits)
                 dist.all_to_all_single(self.d_recv[:n_recv], self.d_send[:n_send], self.out_splits, self.in_splits,
                                        group=self.group)
+            if ev:
+                ev[2].record(ops.stream)
             if self.my_cols:
                 ops.hash_columns(self.d_recv, p.n_rows, self.my_cols, self.d_forest)
                 if self.sub_layers:
@@ -300,6 +307,8 @@ class DistributedCommit:
                         self.d_top[s0 * 32:s1 * 32] = self.d_all_roots[g * stride:g * stride + (s1 - s0) * 32]
             if p.n_sub > 1:
                 ops.merkle_layers(self.d_top, p.n_sub, p.n_sub.bit_length() - 1)
+            if ev:
+                ev[3].record(ops.stream)
 
     def get_root(self) -> LcRoot:
         with self.ops.on_stream():
@@ -361,6 +370,18 @@ def bench_distributed(args, ctx, enc, field, n, synthetic_coeffs):
     launches = torch.tensor([ctx.launch_count - launches0], device="cuda")
     dist.all_reduce(launches, op=dist.ReduceOp.SUM)
     assert dc.get_root() == root0
+    # per-phase device times of this rank (separate loop; events on the engine stream)
+    dc.phase_events = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ph = np.zeros(3)
+    for _ in range(args.steps):
+        dc.run()
+        torch.cuda.synchronize()
+        ph += np.array([dc.phase_events[i].elapsed_time(dc.phase_events[i + 1]) for i in range(3)])
+    dc.phase_events = None
+    ph /= args.steps
+    pht = torch.tensor(ph, device="cuda")
+    dist.all_reduce(pht, op=dist.ReduceOp.MAX)
+    ph = pht.cpu().numpy()
     # end to end: pinned host rows -> H2D -> commit -> D2H root, wall clock bracketed by barriers
     for _ in range(2):
         dc.run(host)
@@ -381,7 +402,23 @@ def bench_distributed(args, ctx, enc, field, n, synthetic_coeffs):
     ms_per_step = float(ms.item()) / args.steps
     e2e_s = float(e2e.item())
     return dict(value=n / (ms_per_step * 1e-3), ms_per_step=ms_per_step, gpu_launches=int(launches.item()), clocks=clocks,
-                root=root0.root.hex(), dominant=None, transport=dc.transport,
+                root=root0.root.hex(), transport=dc.transport,
+                phases_ms={"encode_and_scatter": float(ph[0]), "exchange_wait": float(ph[1]), "hash_merkle_root": float(ph[2])},
+                dominant=_dominant_multi(enc, field, p, dc, float(ph[0])),
                 e2e={"value": n / e2e_s, "unit": "field-elts/s", "h2d_bytes_per_step": int(n * 8 * L),
                      "d2h_bytes_per_step": 32 * world, "ms_per_step": e2e_s * 1e3,
                      "mode": "row blocks from pinned host memory on every rank; every rank reads back the LcRoot"})
+
+
+def _dominant_multi(enc, field, p, dc, encode_ms):
+    """Per-GPU roofline entry of the encode step at N > 1 (max over ranks of the event-timed phase): Ligero's two
+    transform passes over this rank's rows; algorithmic bytes as in the single-GPU case, per rank."""
+    if enc.__class__.__name__ != "LigeroEncoding" or dc.my_rows == 0:
+        return None
+    B = 8 * FIELD_LIMBS[field]
+    log_n = p.n_cols.bit_length() - 1
+    n_pass = 1 if log_n <= 10 else -(-log_n // 10)
+    per_pass = [B * dc.my_rows * (p.n_per_row + p.n_cols)] + [2 * B * dc.my_rows * p.n_cols] * (n_pass - 1)
+    return dict(kernel="ntt_pass_kernel (per GPU; last pass stores into the column owners' memory)",
+                launches_per_step=n_pass, ms_per_launch=encode_ms / n_pass, bytes_per_launch=sum(per_pass) / n_pass,
+                traffic=None)
