@@ -239,7 +239,7 @@ def run_ours(args):
                       "l2": "inputs+outputs (>= 1.5 GiB at 2^24) exceed the 126 MB L2; no flush needed",
                       "timing": "CUDA events on the engine stream, max over ranks"},
            "e2e": result["e2e"], "gpu_launches": result["gpu_launches"], "clocks": result["clocks"],
-           "phases_ms": result.get("phases_ms"), "prove": result.get("prove"),
+           "phases_ms": result.get("phases_ms"), "prove": result.get("prove"), "e2e_eager": result.get("e2e_eager"),
            "roofline": None, "cpu_baseline": None}
     # roofline of the dominant kernel (per launch) + of the whole commit
     dk = result.get("dominant")
@@ -340,6 +340,26 @@ def bench_single(args, ctx, enc, field, n, torch, P):
         r = commit.get_root()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     assert r == root0
+    # the eager variant of the same call: every LcCommit field back in (pinned) host memory, as the reference's
+    # commit() returns them -- comm + coeffs + hashes cross PCIe too
+    eager = None
+    if n <= (1 << 24):
+        h_comm = torch.empty((n_rows * n_cols, L), dtype=torch.int64, pin_memory=True)
+        h_coef = torch.empty((n_rows * n_per_row, L), dtype=torch.int64, pin_memory=True)
+        h_hash = torch.empty((commit.n_hashes, 32), dtype=torch.uint8, pin_memory=True)
+        outs = (h_comm.numpy().view(np.uint64), h_coef.numpy().view(np.uint64), h_hash.numpy())
+        commit.rerun(host_np)
+        commit.download_into(*outs)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            commit.rerun(host_np)
+            commit.download_into(*outs)
+        eager_s = (time.perf_counter() - t0) / 3
+        eager = {"value": n / eager_s, "unit": "field-elts/s", "ms_per_step": eager_s * 1e3,
+                 "h2d_bytes_per_step": int(n * 8 * L),
+                 "d2h_bytes_per_step": int(h_comm.numel() * 8 + h_coef.numel() * 8 + h_hash.numel()),
+                 "mode": "host-visible LcCommit: comm, coeffs and hashes downloaded to pinned host memory"}
+        del h_comm, h_coef, h_hash
     clocks = sampler.stop()
     # the prover's device work on the resident commit (lcpc-2d/src/lib.rs:1004-1093 minus transcript): n_degree_tests
     # + 1 row combinations (collapse_columns) and n_col_opens column openings, through the host API (tiny H2D/D2H)
@@ -389,7 +409,7 @@ def bench_single(args, ctx, enc, field, n, torch, P):
                         bytes_per_launch=(B * n_rows * (n_per_row + n_cols) + code_bytes) / max(1, nl[0]), traffic=None)
     return dict(value=n / (ms_per_step * 1e-3), ms_per_step=ms_per_step, gpu_launches=int(launches),
                 clocks=clocks, phases_ms=dict(zip(["pad_copy", "encode", "leaf_hash", "merkle"], phases.tolist())),
-                dominant=dominant, code_bytes=code_bytes, prove=prove,
+                dominant=dominant, code_bytes=code_bytes, prove=prove, e2e_eager=eager,
                 e2e={"value": n / e2e_s, "unit": "field-elts/s", "h2d_bytes_per_step": int(n * B), "d2h_bytes_per_step": 32,
                      "ms_per_step": e2e_s * 1e3, "mode": "device-resident LcCommit; host receives the LcRoot"})
 

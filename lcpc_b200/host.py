@@ -349,6 +349,11 @@ class LcCommit:
         _check(_cabi.lib().lcpc_b200_commit_download(self._h, _ptr(c), _ptr(k), _ptr(h)), self.enc.ctx)
         return c, k, h
 
+    def download_into(self, comm=None, coeffs=None, hashes=None):
+        """Copy the LcCommit fields (lcpc-2d/src/lib.rs:178-183) into caller-owned arrays (any may be None); with
+        page-locked arrays this is the eager host-visible commit() of INTEGRATION.md at full PCIe rate."""
+        _check(_cabi.lib().lcpc_b200_commit_download(self._h, _ptr(comm), _ptr(coeffs), _ptr(hashes)), self.enc.ctx)
+
     @property
     def comm(self) -> np.ndarray:
         if self._comm is None:
