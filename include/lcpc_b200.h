@@ -161,7 +161,14 @@ int lcpc_b200_commit_download(lcpc_b200_commit *c, uint64_t *comm, uint64_t *coe
 int lcpc_b200_commit_phase_times(lcpc_b200_commit *c, float ms[4], int launches[3]);
 /* device pointers of the same three arrays (owned by the commit) */
 int lcpc_b200_commit_device_ptrs(lcpc_b200_commit *c, uint64_t **d_comm, uint64_t **d_coeffs, uint8_t **d_hashes);
-/* one-shot form with host outputs, the exact shape of commit(): new + download + free */
+/* commit into an existing object AND copy the LcCommit fields out (any of comm / coeffs / hashes may be NULL):
+ * row-chunks of comm and coeffs travel back on a second copy stream while later chunks are still being
+ * uploaded and encoded (PCIe is full duplex), so the eager, host-visible commit() costs about max(upload,
+ * download) instead of their sum.  Page-locked buffers (lcpc_b200_host_alloc / _register) are needed for the
+ * overlap; pageable ones work at the driver's staging rate. */
+int lcpc_b200_commit_rerun_to_host(lcpc_b200_commit *c, const uint64_t *coeffs_in, size_t len, uint64_t *comm,
+                                   uint64_t *coeffs, uint8_t *hashes);
+/* one-shot form with host outputs, the exact shape of commit(): allocate + the call above + free */
 int lcpc_b200_commit_to_host(lcpc_b200_enc *enc, const uint64_t *coeffs_in, size_t len, uint64_t *comm,
                              uint64_t *coeffs, uint8_t *hashes);
 

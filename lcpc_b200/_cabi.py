@@ -77,6 +77,7 @@ SIGNATURES = {
     "lcpc_b200_encode_rows_scatter_dev": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, C.POINTER(Scatter)]),
     "lcpc_b200_encode_rows_scatter_h2d": (_i, [_vp, _vp, _sz, _vp, _vp, _sz, C.POINTER(Scatter)]),
     "lcpc_b200_commit_device_ptrs": (_i, [_vp, _pvp, _pvp, _pvp]),
+    "lcpc_b200_commit_rerun_to_host": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "lcpc_b200_commit_to_host": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "lcpc_b200_commit_collapse": (_i, [_vp, _vp, _vp]),
     "lcpc_b200_commit_degree_test": (_i, [_vp, _vp, _vp, _vp]),

@@ -390,9 +390,17 @@ struct HashTrail {
   int launches;
 };
 
+// host destinations of an eager commit: each row-chunk of comm (and of the padded coefficients) goes back over
+// PCIe on the side stream as soon as it is final, while later chunks are still arriving and being encoded
+// (PCIe is full duplex: the download hides behind the upload)
+struct HostOut {
+  uint64_t *comm, *coeffs;
+};
+
 static int encode_rows_from_host(lcpc_b200_enc *enc, const void *src, size_t len, uint32_t *d_coeffs, uint32_t *d_comm,
                                  size_t n_rows, void *enc_scratch, cudaEvent_t first_ev,
-                                 const Scatter *scatter = nullptr, HashTrail *trail = nullptr) {
+                                 const Scatter *scatter = nullptr, HashTrail *trail = nullptr,
+                                 const HostOut *host_out = nullptr) {
   lcpc_b200_ctx *ctx = enc->ctx;
   cudaStream_t st = ctx->stream;
   const size_t B = field_bytes(enc->field), N = B / 4;
@@ -421,6 +429,16 @@ static int encode_rows_from_host(lcpc_b200_enc *enc, const void *src, size_t len
     if (int rc = encode_rows(enc, d_coeffs + r0 * n_per_row * N, n_per_row, n_per_row, d_comm + r0 * enc->n_cols * N,
                              r1 - r0, enc_scratch, scatter ? &sc : nullptr))
       return rc;
+    if (host_out && (host_out->comm || host_out->coeffs)) {
+      CU(ctx, cudaEventRecord(ctx->side_ev[k], st));
+      CU(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->side_ev[k], 0));
+      if (host_out->comm)
+        CU(ctx, cudaMemcpyAsync((uint8_t *)host_out->comm + r0 * enc->n_cols * B, (uint8_t *)d_comm + r0 * enc->n_cols * B,
+                                (r1 - r0) * enc->n_cols * B, cudaMemcpyDeviceToHost, ctx->side_stream));
+      if (host_out->coeffs)
+        CU(ctx, cudaMemcpyAsync((uint8_t *)host_out->coeffs + r0 * n_per_row * B, (uint8_t *)d_coeffs + r0 * n_per_row * B,
+                                (r1 - r0) * n_per_row * B, cudaMemcpyDeviceToHost, ctx->side_stream));
+    }
     if (trail && k + 1 < n_chunks) {  // the chunks still open after the last row-chunk are hashed by the caller
       unsigned ready = trail->next_chunk;
       while (ready < trail->n_chunks && leaf_chunk_rows_end(enc->field, n_rows, ready) <= r1) ready++;
@@ -590,7 +608,8 @@ static int commit_alloc(lcpc_b200_enc *enc, size_t len, lcpc_b200_commit **out) 
 }
 
 // enqueue the whole commit pipeline; src is host or device memory holding `len` elements
-static int commit_run(lcpc_b200_commit *c, const void *src, size_t len, cudaMemcpyKind kind) {
+static int commit_run(lcpc_b200_commit *c, const void *src, size_t len, cudaMemcpyKind kind,
+                      const HostOut *host_out = nullptr) {
   lcpc_b200_enc *enc = c->enc;
   lcpc_b200_ctx *ctx = enc->ctx;
   const size_t B = field_bytes(enc->field);
@@ -603,8 +622,9 @@ static int commit_run(lcpc_b200_commit *c, const void *src, size_t len, cudaMemc
   HashTrail trail{c->d_hashes, c->d_hash_scratch, 0, leaf_chunk_count(enc->field, c->n_rows), 0};
   if (kind == cudaMemcpyHostToDevice && c->n_rows > 1) {
     if (int rc = encode_rows_from_host(enc, src, len, c->d_coeffs, c->d_comm, c->n_rows, c->d_enc_scratch, c->ev[1], nullptr,
-                                       &trail))
+                                       &trail, host_out))
       return rc;
+    if (host_out) host_out = nullptr;  // handled chunk by chunk
   } else if (kind == cudaMemcpyDeviceToDevice && enc->kind == LCPC_B200_ENC_LIGERO && padded == len && enc->log_n > 0 &&
              (const void *)c->d_coeffs != src) {
     // pad + copy (:636-645) folded into the first transform pass: it reads the caller's coefficient rows and
@@ -676,6 +696,12 @@ static int commit_run(lcpc_b200_commit *c, const void *src, size_t len, cudaMemc
   c->merkle_launches = nl;
   if (ce != cudaSuccess) return cuda_fail(ctx, ce, "merkle_tree");
   CU(ctx, cudaEventRecord(c->ev[4], st));
+  if (host_out) {  // routes without row-chunks: whole arrays after the fact
+    if (host_out->comm)
+      CU(ctx, cudaMemcpyAsync(host_out->comm, c->d_comm, c->n_rows * c->n_cols * B, cudaMemcpyDeviceToHost, st));
+    if (host_out->coeffs)
+      CU(ctx, cudaMemcpyAsync(host_out->coeffs, c->d_coeffs, c->n_rows * c->n_per_row * B, cudaMemcpyDeviceToHost, st));
+  }
   return LCPC_B200_OK;
 }
 
@@ -784,12 +810,33 @@ int lcpc_b200_commit_device_ptrs(lcpc_b200_commit *c, uint64_t **d_comm, uint64_
   return LCPC_B200_OK;
 }
 
+// commit + download with the download overlapped: see HostOut
+int lcpc_b200_commit_rerun_to_host(lcpc_b200_commit *c, const uint64_t *coeffs_in, size_t len, uint64_t *comm,
+                                   uint64_t *coeffs, uint8_t *hashes) {
+  if (!c || !coeffs_in) return LCPC_B200_ERR_BAD_ARG;
+  lcpc_b200_ctx *ctx = c->enc->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (int rc = bind_device(ctx)) return rc;
+  HostOut ho{comm, coeffs};
+  if (int rc = commit_run(c, coeffs_in, len, cudaMemcpyHostToDevice, &ho)) return rc;
+  if (hashes)
+    CU(ctx, cudaMemcpyAsync(hashes, c->d_hashes, (2 * c->np2 - 1) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->side_stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return LCPC_B200_OK;
+}
+
 int lcpc_b200_commit_to_host(lcpc_b200_enc *enc, const uint64_t *coeffs_in, size_t len, uint64_t *comm, uint64_t *coeffs,
-                     uint8_t *hashes) {
+                             uint8_t *hashes) {
+  if (!enc || (!coeffs_in && len)) return LCPC_B200_ERR_BAD_ARG;
+  lcpc_b200_ctx *ctx = enc->ctx;
   lcpc_b200_commit *c = nullptr;
-  int rc = lcpc_b200_commit_new(enc, coeffs_in, len, &c);
-  if (rc != LCPC_B200_OK) return rc;
-  rc = lcpc_b200_commit_download(c, comm, coeffs, hashes);
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (int rc = bind_device(ctx)) return rc;
+    if (int rc = commit_alloc(enc, len, &c)) return rc;
+  }
+  int rc = lcpc_b200_commit_rerun_to_host(c, coeffs_in, len, comm, coeffs, hashes);
   lcpc_b200_commit_free(c);
   return rc;
 }

@@ -349,6 +349,14 @@ class LcCommit:
         _check(_cabi.lib().lcpc_b200_commit_download(self._h, _ptr(c), _ptr(k), _ptr(h)), self.enc.ctx)
         return c, k, h
 
+    def rerun_to_host(self, coeffs_in, comm=None, coeffs=None, hashes=None):
+        """commit() into this object with the fields copied out as they become final (download overlapped with
+        the upload and the encode); arrays should be page-locked for the overlap to be real."""
+        a = _elems(coeffs_in, self.enc.field)
+        self._comm = self._coeffs = self._hashes = None
+        _check(_cabi.lib().lcpc_b200_commit_rerun_to_host(self._h, _ptr(a), a.shape[0], _ptr(comm), _ptr(coeffs),
+                                                          _ptr(hashes)), self.enc.ctx)
+
     def download_into(self, comm=None, coeffs=None, hashes=None):
         """Copy the LcCommit fields (lcpc-2d/src/lib.rs:178-183) into caller-owned arrays (any may be None); with
         page-locked arrays this is the eager host-visible commit() of INTEGRATION.md at full PCIe rate."""

@@ -119,3 +119,36 @@ def test_ligero_ft255_2_26_sampled():
     for i, col in enumerate([5, 262143]):
         assert (vals[i] == comm[:, col]).all()
         assert O.verify_column_path(field, vals[i], paths[i], col, c.get_root().root)
+
+
+def test_eager_commit_download_overlapped_with_upload():
+    """commit_rerun_to_host / commit_to_host: comm and coeffs row-chunks come back on a second copy stream while
+    later chunks are uploaded and encoded; the host-visible LcCommit must equal the oracle's (pinned and
+    pageable destinations, chunked and single-chunk sizes, ragged last row)."""
+    import ctypes as C
+
+    import torch
+    from lcpc_b200 import _cabi
+    for field, length, pinned in ((P.FT255, (1 << 20) - 999, True), (P.FT255, 1 << 20, False), (P.FT127, 1 << 12, True),
+                                  (P.FT63, 100, False)):
+        enc, oenc = P.LigeroEncoding(field, length), O.Encoding.ligero(field, length)
+        x = O.random_elems(field, length, seed=length % 1000)
+        oc = oenc.commit(x)
+        n_rows, n_per_row, n_cols = enc.get_dims(length)
+        L = enc.L
+        n_hashes = 2 * (1 << (n_cols - 1).bit_length()) - 1
+        mk = (lambda *shape, dt=torch.int64: torch.empty(shape, dtype=dt, pin_memory=pinned))
+        h_comm, h_coef, h_hash = mk(n_rows * n_cols, L), mk(n_rows * n_per_row, L), mk(n_hashes, 32, dt=torch.uint8)
+        h_comm.fill_(-1), h_coef.fill_(-1)
+        rc = _cabi.lib().lcpc_b200_commit_to_host(enc._h, x.ctypes.data_as(C.c_void_p), length,
+                                                  C.c_void_p(h_comm.data_ptr()), C.c_void_p(h_coef.data_ptr()),
+                                                  C.c_void_p(h_hash.data_ptr()))
+        assert rc == 0
+        assert (h_comm.numpy().view(np.uint64) == oc["comm"]).all()
+        assert (h_coef.numpy().view(np.uint64) == oc["coeffs"]).all()
+        assert (h_hash.numpy() == oc["hashes"]).all()
+        # into an existing object, only comm + hashes requested
+        c = P.LcCommit.commit(O.random_elems(field, length, seed=1), enc)
+        h_comm.fill_(-1)
+        c.rerun_to_host(x, comm=h_comm.numpy().view(np.uint64), hashes=h_hash.numpy())
+        assert (h_comm.numpy().view(np.uint64) == oc["comm"]).all() and c.get_root().root == oc["root"]
