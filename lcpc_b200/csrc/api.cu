@@ -669,6 +669,15 @@ static int commit_run(lcpc_b200_commit *c, const void *src, size_t len, cudaMemc
       CU(ctx, cudaEventRecord(ctx->side_done, ctx->side_stream));
       CU(ctx, cudaStreamWaitEvent(st, ctx->side_done, 0));
     }
+  } else if (kind == cudaMemcpyDeviceToDevice && enc->kind == LCPC_B200_ENC_SDIG && (const void *)c->d_coeffs != src) {
+    // the same for the expander code: the transpose into the work buffer stores the copy and supplies the
+    // zero padding of a short last row
+    CU(ctx, cudaEventRecord(c->ev[1], st));
+    int nl = 0;
+    cudaError_t ce = expander_encode_rows(enc->code, (const uint32_t *)src, c->n_per_row, c->n_per_row, c->d_comm, c->n_cols,
+                                          c->n_rows, c->d_enc_scratch, st, &nl, nullptr, c->d_coeffs, c->n_per_row, len);
+    ctx->launches += nl;
+    if (ce != cudaSuccess) return cuda_fail(ctx, ce, "encode");
   } else {
     // pad + copy (lcpc-2d/src/lib.rs:636-645): coeffs = coeffs_in || zeros
     CU(ctx, cudaMemcpyAsync(c->d_coeffs, src, len * B, kind, st));

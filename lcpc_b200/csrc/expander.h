@@ -27,9 +27,12 @@ size_t expander_codeword_length(const ExpanderCode *code);  // encode.rs:18-33
 size_t expander_nnz(const ExpanderCode *code);
 size_t expander_scratch_bytes(const ExpanderCode *code, size_t n_rows);
 // encode n_rows rows: src row r holds `valid` >= n_in leading elements at src + r*src_stride; dst rows
-// are dst_stride apart and receive the full codeword.  src may equal dst.
+// are dst_stride apart and receive the full codeword.  src may equal dst.  copy_dst (optional): the first
+// n_in elements of every source row are also stored there, rows copy_stride apart.  src_total: elements that
+// exist at src (row-major, src_stride apart); positions beyond it read as zero (the padded last row).
 cudaError_t expander_encode_rows(const ExpanderCode *code, const uint32_t *src, size_t src_stride, size_t valid,
                                  uint32_t *dst, size_t dst_stride, size_t n_rows, void *scratch, cudaStream_t stream,
-                                 int *n_launches, const Scatter *scatter = nullptr);
+                                 int *n_launches, const Scatter *scatter = nullptr, uint32_t *copy_dst = nullptr,
+                                 size_t copy_stride = 0, size_t src_total = ~(size_t)0);
 
 }  // namespace lcpc

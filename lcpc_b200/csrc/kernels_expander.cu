@@ -250,7 +250,7 @@ constexpr int TT = 32;
 template <int N>
 __global__ void __launch_bounds__(256)
 transpose_kernel(const uint32_t *__restrict__ src, size_t src_ld, uint32_t *__restrict__ dst, size_t dst_ld,
-                 size_t n_r, size_t n_c, Scatter sc) {
+                 size_t n_r, size_t n_c, Scatter sc, uint32_t *__restrict__ copy_dst, size_t copy_ld, size_t src_total) {
   __shared__ uint32_t tile[N][TT][TT + 1];
   const size_t c0 = (size_t)blockIdx.x * TT, r0 = (size_t)blockIdx.y * TT;
   const unsigned tx = threadIdx.x % TT, ty = threadIdx.x / TT;  // 32 x 8
@@ -258,7 +258,13 @@ transpose_kernel(const uint32_t *__restrict__ src, size_t src_ld, uint32_t *__re
     size_t r = r0 + rr, cidx = c0 + tx;
     if (r < n_r && cidx < n_c) {
       uint32_t v[N];
-      ldv<N>(v, src + (r * src_ld + cidx) * N);
+      if (r * src_ld + cidx < src_total) {
+        ldv<N>(v, src + (r * src_ld + cidx) * N);
+      } else {  // beyond the caller's coefficients: the zero padding of the last row (lcpc-2d/src/lib.rs:636-645)
+#pragma unroll
+        for (int l = 0; l < N; l++) v[l] = 0;
+      }
+      if (copy_dst) stv<N>(copy_dst + (r * copy_ld + cidx) * N, v);  // commit()'s own copy of the coefficients
 #pragma unroll
       for (int l = 0; l < N; l++) tile[l][rr][tx] = v[l];
     }
@@ -434,7 +440,8 @@ template <int FID> __global__ void one_mont_kernel(uint32_t *out) {
 template <int FID>
 static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_t src_stride, size_t valid,
                                uint32_t *dst, size_t dst_stride, size_t n_rows, void *scratch, cudaStream_t st,
-                               int *n_launches, const Scatter *scatter) {
+                               int *n_launches, const Scatter *scatter, uint32_t *copy_dst, size_t copy_stride,
+                               size_t src_total) {
   using F = Field<FID>;
   constexpr int N = F::N;
   if (n_launches) *n_launches = 0;
@@ -449,7 +456,7 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
     dim3 grid((unsigned)((c->n_in + TT - 1) / TT), (unsigned)((n_rows + TT - 1) / TT));
     Scatter none;
     none.n_blocks = 0;
-    transpose_kernel<N><<<grid, 256, 0, st>>>(src, src_stride, W, n_rows, n_rows, c->n_in, none);
+    transpose_kernel<N><<<grid, 256, 0, st>>>(src, src_stride, W, n_rows, n_rows, c->n_in, none, copy_dst, copy_stride, src_total);
     launches++;
   }
   for (size_t oi = 0; oi < c->ops.size(); oi++) {
@@ -526,7 +533,7 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
     Scatter sc;
     sc.n_blocks = 0;
     if (scatter && scatter->n_blocks) sc = *scatter;
-    transpose_kernel<N><<<grid, 256, 0, st>>>(W, n_rows, dst, dst_stride, c->n_cols, n_rows, sc);
+    transpose_kernel<N><<<grid, 256, 0, st>>>(W, n_rows, dst, dst_stride, c->n_cols, n_rows, sc, nullptr, 0, ~(size_t)0);
     launches++;
   }
   if (n_launches) *n_launches = launches;
@@ -535,12 +542,13 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
 
 cudaError_t expander_encode_rows(const ExpanderCode *c, const uint32_t *src, size_t src_stride, size_t valid,
                                  uint32_t *dst, size_t dst_stride, size_t n_rows, void *scratch, cudaStream_t st,
-                                 int *n_launches, const Scatter *scatter) {
+                                 int *n_launches, const Scatter *scatter, uint32_t *copy_dst, size_t copy_stride,
+                                 size_t src_total) {
   switch (c->field) {
-    case FT63: return encode_impl<FT63>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches, scatter);
-    case FT127: return encode_impl<FT127>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches, scatter);
-    case FT191: return encode_impl<FT191>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches, scatter);
-    case FT255: return encode_impl<FT255>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches, scatter);
+    case FT63: return encode_impl<FT63>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches, scatter, copy_dst, copy_stride, src_total);
+    case FT127: return encode_impl<FT127>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches, scatter, copy_dst, copy_stride, src_total);
+    case FT191: return encode_impl<FT191>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches, scatter, copy_dst, copy_stride, src_total);
+    case FT255: return encode_impl<FT255>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches, scatter, copy_dst, copy_stride, src_total);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -354,7 +354,8 @@ def test_rerun_and_launch_counter():
 
 @pytest.mark.parametrize("kind,field,length", [("ligero", P.FT255, 1 << 16), ("ligero", P.FT255, 1 << 20),
                                                ("ligero", P.FT127, (1 << 15) - 77), ("ligero", P.FT63, 1 << 13),
-                                               ("sdig", P.FT127, 1 << 14)])
+                                               ("sdig", P.FT127, 1 << 14), ("sdig_exact", P.FT127, 1 << 14),
+                                               ("sdig_exact", P.FT255, 1 << 13)])
 def test_commit_from_device_memory(kind, field, length):
     """commit_new_dev / commit_rerun_dev (coefficients already in HBM: the roofline-timed region of bench.py).
     For Ligero with a full last row the commit's own copy of the coefficients is written by the first
@@ -364,6 +365,8 @@ def test_commit_from_device_memory(kind, field, length):
         enc, oenc = P.LigeroEncoding(field, length), O.Encoding.ligero(field, length)
     else:
         enc, oenc = P.SdigEncoding(field, length, seed=4), O.Encoding.sdig(field, length, seed=4)
+        if kind == "sdig_exact":  # a length that fills the last row: the copy rides on the transpose into the work buffer
+            length = enc.get_dims(length)[0] * enc.n_per_row
     x0, x1 = O.random_elems(field, length, seed=31), O.random_elems(field, length, seed=32)
     dev = torch.device("cuda", enc.ctx.device)
     d0 = torch.from_numpy(x0.view(np.int64)).to(dev)
