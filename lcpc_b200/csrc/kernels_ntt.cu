@@ -259,9 +259,10 @@ __device__ __forceinline__ void sstore2(uint32_t *smem, unsigned slot, unsigned 
 }
 
 // KL stages (t-bits lg_top .. lg_top-KL+1) on 2^KL elements per work item, in registers
-template <int FID, int KL, bool FINAL>
+// `tws` (last pass only): the pass's 2^(S-1) twiddles w^(k * n / 2^S) in shared memory, element k at tws + k*N
+template <int FID, int KL, bool FINAL, bool SMEM_TW>
 __device__ __forceinline__ void ntt_round(uint32_t *smem, const uint32_t *__restrict__ roots, const NttGeom &g,
-                                          unsigned lg_top) {
+                                          unsigned lg_top, const uint32_t *tws) {
   using F = Field<FID>;
   constexpr int N = F::N;
   constexpr int K = 1 << KL;
@@ -287,8 +288,22 @@ __device__ __forceinline__ void ntt_round(uint32_t *smem, const uint32_t *__rest
         const bool unit = FINAL && r == 0;  // exponent r * n/(2 gap) = 0
         typename F::Elem wv;
         if (!unit) {
-          const size_t tw = ((j0 + ((size_t)r << log_h)) & (((size_t)1 << logG) - 1)) << twshift;
-          gload_ro<N>(wv.v, roots + tw * N);
+          const size_t k = (j0 + ((size_t)r << log_h)) & (((size_t)1 << logG) - 1);
+          if (SMEM_TW) {  // exponent k * n / 2^(logG+1) = (k << (S-1-logG)) * n / 2^S
+            const uint32_t *q = tws + ((k << (g.S - 1 - logG)) * N);
+#pragma unroll
+            for (int l = 0; l < N; l += Planes<N>::PW) {
+              if constexpr (Planes<N>::PW == 4) {
+                uint4 t = *reinterpret_cast<const uint4 *>(q + l);
+                wv.v[l] = t.x, wv.v[l + 1] = t.y, wv.v[l + 2] = t.z, wv.v[l + 3] = t.w;
+              } else {
+                uint2 t = *reinterpret_cast<const uint2 *>(q + l);
+                wv.v[l] = t.x, wv.v[l + 1] = t.y;
+              }
+            }
+          } else {
+            gload_ro<N>(wv.v, roots + (k << twshift) * N);
+          }
         }
 #pragma unroll
         for (int blk = 0; blk < K; blk += 2 * gq) {
@@ -356,21 +371,36 @@ ntt_pass_kernel(const uint32_t *__restrict__ src, uint32_t *dst, const uint32_t 
       *reinterpret_cast<uint2 *>(q) = v;
     }
   }
+  // last pass: its stages only ever use the 2^(S-1) twiddles w^(k n / 2^S); keep them in shared memory behind the
+  // tile instead of paying an L2 round trip per butterfly
+  uint32_t *tws = smem + SmemLayout<N>::bytes(g.tile) / 4;
+  if (g.last) {
+    const unsigned n_tw = p.S ? 1u << (p.S - 1) : 0;
+    const unsigned step_log = p.log_n - p.S;
+    for (unsigned gi = threadIdx.x; gi < n_tw * NP; gi += NTT_THREADS) {
+      const unsigned k = gi / NP, pl = gi % NP;
+      const uint32_t *src_tw = roots + ((size_t)k << step_log) * N + pl * PW;
+      if constexpr (PW == 4) *reinterpret_cast<uint4 *>(tws + k * N + pl * PW) = __ldg(reinterpret_cast<const uint4 *>(src_tw));
+      else *reinterpret_cast<uint2 *>(tws + k * N + pl * PW) = __ldg(reinterpret_cast<const uint2 *>(src_tw));
+    }
+  }
   __syncthreads();
 
   unsigned rem = p.S, lg_top = p.S - 1;
   while (rem > 0) {
     if (LCPC_NTT_MAX_KL >= 3 && rem >= 3) {
-      if (g.last && rem == 3) ntt_round<FID, 3, true>(smem, roots, g, lg_top);
-      else ntt_round<FID, 3, false>(smem, roots, g, lg_top);
+      if (g.last && rem == 3) ntt_round<FID, 3, true, true>(smem, roots, g, lg_top, tws);
+      else if (g.last) ntt_round<FID, 3, false, true>(smem, roots, g, lg_top, tws);
+      else ntt_round<FID, 3, false, false>(smem, roots, g, lg_top, tws);
       rem -= 3, lg_top -= 3;
     } else if (rem >= 2) {
-      if (g.last && rem == 2) ntt_round<FID, 2, true>(smem, roots, g, lg_top);
-      else ntt_round<FID, 2, false>(smem, roots, g, lg_top);
+      if (g.last && rem == 2) ntt_round<FID, 2, true, true>(smem, roots, g, lg_top, tws);
+      else if (g.last) ntt_round<FID, 2, false, true>(smem, roots, g, lg_top, tws);
+      else ntt_round<FID, 2, false, false>(smem, roots, g, lg_top, tws);
       rem -= 2, lg_top -= 2;
     } else {
-      if (g.last) ntt_round<FID, 1, true>(smem, roots, g, lg_top);
-      else ntt_round<FID, 1, false>(smem, roots, g, lg_top);
+      if (g.last) ntt_round<FID, 1, true, true>(smem, roots, g, lg_top, tws);
+      else ntt_round<FID, 1, false, false>(smem, roots, g, lg_top, tws);
       rem = 0;
     }
     __syncthreads();
@@ -403,8 +433,9 @@ static cudaError_t ntt_rows_impl(const uint32_t *src, size_t src_stride, size_t 
   constexpr unsigned LOG_TILE = LCPC_NTT_LOG_TILE;  // 1024 elements: 32 KiB for Ft255
   constexpr unsigned MAX_S = 10;  // stages per pass: 2^19 points are 10 + 9 (two HBM round trips), 2^17 are 9 + 8
   if (!attr_set) {
+    // tile + (last pass) up to 2^(LOG_TILE-1) twiddles
     cudaError_t e = cudaFuncSetAttribute(ntt_pass_kernel<FID>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)SmemLayout<F::N>::bytes(1u << LOG_TILE));
+                                         (int)(SmemLayout<F::N>::bytes(1u << LOG_TILE) + ((size_t)1 << (LOG_TILE - 1)) * F::BYTES));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -440,7 +471,7 @@ static cudaError_t ntt_rows_impl(const uint32_t *src, size_t src_stride, size_t 
     p.copy_dst = ip == 0 ? copy_dst : nullptr, p.copy_stride = copy_stride;
     size_t grid = n_rows << p.tiles_per_row_log;
     if (grid > 0x7fffffffu) return cudaErrorInvalidValue;
-    size_t smem = SmemLayout<F::N>::bytes(1u << (S + logC));
+    size_t smem = SmemLayout<F::N>::bytes(1u << (S + logC)) + (last ? ((size_t)1 << (S - 1)) * F::BYTES : 0);
     ntt_pass_kernel<FID><<<(unsigned)grid, NTT_THREADS, smem, stream>>>(cur_src, dst, roots, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
