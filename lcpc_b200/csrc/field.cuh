@@ -347,16 +347,30 @@ template <int FID> struct Field {
   // acc += t, then acc -= p * 2^(32N) if that leaves acc >= 2^(64N - 1).  Invariant: acc < 2^(64N-1)
   // before and after (every product is < p^2 < 0.19 * 2^(64N), and 0.27 <= p / 2^(32N) < 0.44 for the
   // four moduli); subtracting a multiple of p * R does not change REDC's result mod p.
-  LCPC_DEV static void wide_add_fold(Wide &acc, const Wide &t) {
-    add_cc(acc.v[0], acc.v[0], t.v[0]);
-#pragma unroll
-    for (int i = 1; i < 2 * N - 1; i++) addc_cc(acc.v[i], acc.v[i], t.v[i]);
-    addc(acc.v[2 * N - 1], acc.v[2 * N - 1], t.v[2 * N - 1]);
+  // acc -= p * 2^(32N) if acc >= 2^(64N - 1)
+  LCPC_DEV static void wide_fold(Wide &acc) {
     const uint32_t mask = (uint32_t)((int32_t)acc.v[2 * N - 1] >> 31);
     sub_cc(acc.v[N], acc.v[N], FP::P(0) & mask);
 #pragma unroll
     for (int i = 1; i < N - 1; i++) subc_cc(acc.v[N + i], acc.v[N + i], FP::P(i) & mask);
     subc(acc.v[2 * N - 1], acc.v[2 * N - 1], FP::P(N - 1) & mask);
+  }
+  LCPC_DEV static void wide_add(Wide &acc, const Wide &t) {
+    add_cc(acc.v[0], acc.v[0], t.v[0]);
+#pragma unroll
+    for (int i = 1; i < 2 * N - 1; i++) addc_cc(acc.v[i], acc.v[i], t.v[i]);
+    addc(acc.v[2 * N - 1], acc.v[2 * N - 1], t.v[2 * N - 1]);
+  }
+  LCPC_DEV static void wide_add_fold(Wide &acc, const Wide &t) {
+    wide_add(acc, t);
+    wide_fold(acc);
+  }
+  // merge two folded partial sums (both < 2^(64N-1)): the sum is < 2^(64N) and two folds bring it back under
+  // 2^(64N-1) for every modulus here (0.27 <= p / 2^(32N) < 0.44)
+  LCPC_DEV static void wide_merge(Wide &acc, const Wide &t) {
+    wide_add(acc, t);
+    wide_fold(acc);
+    wide_fold(acc);
   }
   LCPC_DEV static void mac_wide(Wide &acc, const Elem &a, const Elem &b) { wide_add_fold(acc, mul_full(a, b)); }
 

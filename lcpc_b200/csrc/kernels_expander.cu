@@ -366,14 +366,16 @@ struct FusedOp {
   const uint32_t *rowptr, *colidx, *vals;
   uint32_t in_off, in_len, out_off, out_len;  // offsets relative to the window start
   int in_tmp, out_tmp;
+  uint32_t group;  // sparse product: lanes sharing one output (power of two <= 32), so that short levels use the CTA
 };
 struct FusedOps {
   int n;
   FusedOp op[MAX_FUSED_OPS];
 };
 
+constexpr int FUSED_THREADS = 1024;
 template <int FID>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(FUSED_THREADS)
 fused_levels_kernel(FusedOps ops, uint32_t *__restrict__ W, size_t n_rows, uint32_t win_lo, uint32_t win_len,
                     uint32_t first_in_len, uint32_t tmp_len) {
   using F = Field<FID>;
@@ -395,30 +397,47 @@ fused_levels_kernel(FusedOps ops, uint32_t *__restrict__ W, size_t n_rows, uint3
     const FusedOp &op = ops.op[o];
     const uint32_t *in = (op.in_tmp ? tmp : win + (size_t)op.in_off * N);
     uint32_t *out = (op.out_tmp ? tmp : win + (size_t)op.out_off * N);
-    for (uint32_t i = threadIdx.x; i < op.out_len; i += blockDim.x) {
-      typename F::Elem res;
-      if (op.kind == 0) {
-        const uint32_t k0 = __ldg(op.rowptr + i), k1 = __ldg(op.rowptr + i + 1);
+    if (op.kind == 0) {
+      // `group` lanes split the non-zeros of one output and merge their double-width partial sums with shuffles:
+      // these levels have tens to hundreds of outputs, far fewer than the CTA has threads
+      const unsigned G = op.group, gl = threadIdx.x & (G - 1), per_pass = blockDim.x / G;
+      for (uint32_t base = 0; base < op.out_len; base += per_pass) {  // same trip count for every thread
+        const uint32_t i = base + threadIdx.x / G;
+        const bool act = i < op.out_len;
         typename F::Wide acc = F::wide_zero();
-        for (uint32_t k = k0; k < k1; k++) {
-          const uint32_t j = __ldg(op.colidx + k);
-          typename F::Elem a, xv;
-          ldv<N>(a.v, op.vals + (size_t)k * N);
-          ldv<N>(xv.v, in + (size_t)j * N);
-          F::mac_wide(acc, a, xv);
+        if (act) {
+          const uint32_t k0 = __ldg(op.rowptr + i), k1 = __ldg(op.rowptr + i + 1);
+          for (uint32_t k = k0 + gl; k < k1; k += G) {
+            const uint32_t j = __ldg(op.colidx + k);
+            typename F::Elem a, xv;
+            ldv<N>(a.v, op.vals + (size_t)k * N);
+            ldv<N>(xv.v, in + (size_t)j * N);
+            F::mac_wide(acc, a, xv);
+          }
         }
-        res = F::template redc<2>(acc);
-      } else {  // reed_solomon (encode.rs:97-110): Horner at the point i + 1
+        for (unsigned d = G >> 1; d >= 1; d >>= 1) {
+          typename F::Wide other;
+#pragma unroll
+          for (int l = 0; l < 2 * N; l++) other.v[l] = __shfl_down_sync(0xffffffffu, acc.v[l], d, G);
+          F::wide_merge(acc, other);
+        }
+        if (act && gl == 0) {
+          typename F::Elem res = F::template redc<2>(acc);
+          stv<N>(out + (size_t)i * N, res.v);
+        }
+      }
+    } else {  // reed_solomon (encode.rs:97-110): Horner at the point i + 1
+      for (uint32_t i = threadIdx.x; i < op.out_len; i += blockDim.x) {
         typename F::Elem pt = one;
         for (uint32_t q = 0; q < i; q++) pt = F::add(pt, one);
-        res = F::zero();
+        typename F::Elem res = F::zero();
         for (uint32_t j = op.in_len; j-- > 0;) {
           typename F::Elem cf;
           ldv<N>(cf.v, in + (size_t)j * N);
           res = F::add(F::mul(res, pt), cf);
         }
+        stv<N>(out + (size_t)i * N, res.v);
       }
-      stv<N>(out + (size_t)i * N, res.v);
     }
     __syncthreads();
   }
@@ -471,6 +490,8 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
         f.in_len = (uint32_t)g.in_len, f.out_len = (uint32_t)g.out_len;
         f.in_off = g.in_tmp ? 0 : (uint32_t)(g.in_off - c->win_lo);
         f.out_off = g.out_tmp ? 0 : (uint32_t)(g.out_off - c->win_lo);
+        f.group = 1;
+        while (f.group < 32 && (size_t)f.out_len * (f.group * 2) <= (size_t)FUSED_THREADS) f.group *= 2;
         if (g.kind == 0) {
           const DeviceCsr &M = c->mats[g.mat];
           f.rowptr = M.rowptr, f.colidx = M.colidx, f.vals = M.vals;
@@ -486,7 +507,7 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
         if (e != cudaSuccess) return e;
         attr_set = true;
       }
-      fused_levels_kernel<FID><<<(unsigned)n_rows, 256, smem, st>>>(fo, W, n_rows, (uint32_t)c->win_lo, (uint32_t)c->win_len,
+      fused_levels_kernel<FID><<<(unsigned)n_rows, FUSED_THREADS, smem, st>>>(fo, W, n_rows, (uint32_t)c->win_lo, (uint32_t)c->win_len,
                                                                     (uint32_t)c->ops[c->fuse_lo].in_len, (uint32_t)c->tmp_len);
       launches++;
       cudaError_t e = cudaGetLastError();
