@@ -297,13 +297,14 @@ transpose_kernel(const uint32_t *__restrict__ src, size_t src_ld, uint32_t *__re
 // __launch_bounds__(256, 4) is what makes ptxas keep all eight 16-byte loads of a batch in front of the first
 // product (64 registers); left to itself it settles on 48 registers and sinks each load next to its use, which
 // measured 6 % slower on the 2^24 chain.
-constexpr int SPMM_UNROLL = 4;
+// Wider elements (Ft191, Ft255) batch two deep under a 128-register budget instead.
 template <int FID>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, (Field<FID>::N <= 4 ? 4 : 2))
 spmm_kernel(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ colidx, const uint32_t *__restrict__ vals,
             const uint32_t *__restrict__ x, uint32_t *__restrict__ y, size_t m, size_t n_rows, unsigned r0, unsigned rg) {
   using F = Field<FID>;
   constexpr int N = F::N;
+  constexpr int SPMM_UNROLL = N <= 4 ? 4 : 2;
   const size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= m * rg) return;
   const size_t i = item / rg, r = r0 + item % rg;
