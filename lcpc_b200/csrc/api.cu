@@ -161,12 +161,15 @@ struct lcpc_b200_commit {
   void *d_enc_scratch = nullptr;
   // prove-side staging
   uint32_t *d_tensor = nullptr, *d_poly = nullptr, *d_key = nullptr;
+  void *h_poly = nullptr;  // page-locked landing buffer for collapse results (pageable destinations copy from it)
   // phase boundaries of the last run: start | copy+pad | encode | leaf hash | merkle
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   int encode_launches = 0, hash_launches = 0, merkle_launches = 0;
 };
 
 extern "C" {
+
+static int return_poly(lcpc_b200_commit *c, uint64_t *poly);
 
 const char *lcpc_b200_version(void) { return "lcpc_b200 0.1 (sm_100a)"; }
 
@@ -569,6 +572,7 @@ static void commit_release(lcpc_b200_commit *c) {
   cudaFree(c->d_tensor);
   cudaFree(c->d_poly);
   cudaFree(c->d_key);
+  if (c->h_poly) cudaFreeHost(c->h_poly);
   for (auto &e : c->ev)
     if (e) cudaEventDestroy(e);
   delete c;
@@ -864,8 +868,24 @@ int lcpc_b200_commit_collapse(lcpc_b200_commit *c, const uint64_t *tensor, uint6
                                    nullptr, ctx->stream, &nl);
   ctx->launches += nl;
   if (ce != cudaSuccess) return cuda_fail(ctx, ce, "collapse");
-  CU(ctx, cudaMemcpyAsync(poly, c->d_poly, c->n_per_row * B, cudaMemcpyDeviceToHost, ctx->stream));
+  return return_poly(c, poly);
+}
+
+// d_poly -> caller memory through the page-locked landing buffer (a direct copy into pageable memory is staged by
+// the driver at a fraction of the PCIe rate); synchronises the engine stream
+static int return_poly(lcpc_b200_commit *c, uint64_t *poly) {
+  lcpc_b200_ctx *ctx = c->enc->ctx;
+  const size_t bytes = c->n_per_row * field_bytes(c->enc->field);
+  if (!c->h_poly && cudaHostAlloc(&c->h_poly, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    c->h_poly = nullptr;
+    cudaGetLastError();
+    CU(ctx, cudaMemcpyAsync(poly, c->d_poly, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return LCPC_B200_OK;
+  }
+  CU(ctx, cudaMemcpyAsync(c->h_poly, c->d_poly, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(poly, c->h_poly, bytes);
   return LCPC_B200_OK;
 }
 
@@ -893,10 +913,8 @@ int lcpc_b200_commit_degree_test(lcpc_b200_commit *c, const uint8_t key[32], uin
                                    nullptr, ctx->stream, &nl);
   ctx->launches += nl;
   if (ce != cudaSuccess) return cuda_fail(ctx, ce, "collapse");
-  CU(ctx, cudaMemcpyAsync(poly, c->d_poly, c->n_per_row * B, cudaMemcpyDeviceToHost, ctx->stream));
   if (tensor_out) CU(ctx, cudaMemcpyAsync(tensor_out, c->d_tensor, c->n_rows * B, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
-  return LCPC_B200_OK;
+  return return_poly(c, poly);
 }
 
 int lcpc_b200_expand_tensor(lcpc_b200_ctx *ctx, int field, const uint8_t key[32], size_t n, uint64_t *out) {
