@@ -504,7 +504,10 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
         }
       }
       const size_t smem = (c->win_len + c->tmp_len) * F::BYTES;
-      static bool attr_set = false;
+      static bool attr_set_dev[64] = {};  // per device
+      int dev_id = 0;
+      cudaGetDevice(&dev_id);
+      bool &attr_set = attr_set_dev[dev_id & 63];
       if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(fused_levels_kernel<FID>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)FUSED_SMEM_BYTES);

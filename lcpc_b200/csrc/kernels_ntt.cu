@@ -429,7 +429,10 @@ static cudaError_t ntt_rows_impl(const uint32_t *src, size_t src_stride, size_t 
                                  cudaStream_t stream, int *n_launches, const Scatter *scatter, uint32_t *copy_dst,
                                  size_t copy_stride) {
   using F = Field<FID>;
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};  // the attribute is per device: one process may hold contexts on several
+  int dev_id = 0;
+  cudaGetDevice(&dev_id);
+  bool &attr_set = attr_set_dev[dev_id & 63];
   constexpr unsigned LOG_TILE = LCPC_NTT_LOG_TILE;  // 1024 elements: 32 KiB for Ft255
   constexpr unsigned MAX_S = 10;  // stages per pass: 2^19 points are 10 + 9 (two HBM round trips), 2^17 are 9 + 8
   if (!attr_set) {

@@ -482,3 +482,58 @@ def test_degree_test_matches_collapse_of_oracle_tensor():
     assert (c.degree_test(key) == poly).all()
     with pytest.raises(P.LcpcError):
         c.degree_test(b"short")
+
+
+def test_contexts_are_thread_safe():
+    """A context serialises its calls (one stream, one mutex); separate contexts run concurrently.  Reference:
+    `LcEncoding: Sync` because rayon workers call encode concurrently (lcpc-2d/src/lib.rs:74, 648-653)."""
+    import threading
+    field, length = P.FT127, 1 << 14
+    oenc = O.Encoding.ligero(field, length)
+    xs = [O.random_elems(field, length, seed=200 + i) for i in range(6)]
+    want = [oenc.commit(x)["root"] for x in xs]
+    shared = P.LigeroEncoding(field, length)                      # three threads share one context/encoding
+    own = [P.LigeroEncoding(field, length, ctx=P.Context(0)) for _ in range(3)]  # three have their own
+    got, errs = [None] * 6, []
+
+    def work(i, enc):
+        try:
+            for _ in range(3):
+                c = P.LcCommit.commit(xs[i], enc)
+                t = O.random_elems(field, c.n_rows, seed=i)
+                c.collapse(t)
+                got[i] = c.get_root().root
+        except Exception as e:  # pragma: no cover
+            errs.append(repr(e))
+
+    ts = [threading.Thread(target=work, args=(i, shared if i < 3 else own[i - 3])) for i in range(6)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    assert got == want
+
+
+def test_row_block_entry_points_reject_bad_shapes():
+    import ctypes as C
+
+    import torch
+    from lcpc_b200 import _cabi
+    field = P.FT127
+    enc = P.LigeroEncoding.new_from_dims(field, 256, 512)
+    dev = torch.device("cuda", enc.ctx.device)
+    d_a = torch.zeros(4 * 512 * 2, dtype=torch.int64, device=dev)
+    d_b = torch.zeros(4 * 512 * 2, dtype=torch.int64, device=dev)
+    host = np.zeros((4 * 256, 2), np.uint64)
+    torch.cuda.synchronize()
+    lib = _cabi.lib()
+    # len must fill exactly n_rows rows (last one possibly short): 4 rows need 769..1024 elements
+    for bad_len in (768, 1025, 0):
+        assert lib.lcpc_b200_encode_rows_h2d(enc._h, host.ctypes.data_as(C.c_void_p), bad_len, C.c_void_p(d_a.data_ptr()),
+                                             C.c_void_p(d_b.data_ptr()), 4) == _cabi.ERR_BAD_ARG
+    assert lib.lcpc_b200_encode_rows_h2d(enc._h, host.ctypes.data_as(C.c_void_p), 1000, C.c_void_p(d_a.data_ptr()),
+                                         C.c_void_p(d_b.data_ptr()), 4) == 0
+    # valid > n_cols / > stride
+    assert lib.lcpc_b200_encode_rows_dev(enc._h, C.c_void_p(d_a.data_ptr()), 256, 600, C.c_void_p(d_b.data_ptr()), 2) \
+        == _cabi.ERR_BAD_ARG
+    assert lib.lcpc_b200_encode_dev(enc._h, C.c_void_p(d_a.data_ptr()), 2, 513) == _cabi.ERR_BAD_ARG
+    enc.ctx.synchronize()
