@@ -537,3 +537,20 @@ def test_row_block_entry_points_reject_bad_shapes():
         == _cabi.ERR_BAD_ARG
     assert lib.lcpc_b200_encode_dev(enc._h, C.c_void_p(d_a.data_ptr()), 2, 513) == _cabi.ERR_BAD_ARG
     enc.ctx.synchronize()
+
+
+def test_contexts_on_two_devices_in_one_process():
+    """One process may hold contexts on several GPUs (the multi-GPU commit uses one process per GPU, but the ABI
+    does not require it): kernels with opted-in shared memory must work on every device."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    field, length = P.FT255, 1 << 14
+    x = O.random_elems(field, length, seed=9)
+    want = O.Encoding.ligero(field, length).commit(x)["root"]
+    for dev in (1, 0, 1):
+        enc = P.LigeroEncoding(field, length, ctx=P.Context(dev))
+        assert P.LcCommit.commit(x, enc).get_root().root == want
+    enc2 = P.SdigEncoding(P.FT127, 1 << 12, seed=0, ctx=P.Context(1))
+    x2 = O.random_elems(P.FT127, 1 << 12, seed=10)
+    assert P.LcCommit.commit(x2, enc2).get_root().root == O.Encoding.sdig(P.FT127, 1 << 12, seed=0).commit(x2)["root"]
