@@ -236,6 +236,7 @@ def run_ours(args):
            "config": {"workload": wl["name"], "n_rows": n_rows, "n_per_row": n_per_row, "n_cols": n_cols,
                       "parallelism": (f"row-block x{world}, exchange={result.get('transport')}, column-block hash"
                                       if world > 1 else "1 GPU"),
+                      "root_check": result.get("root_check"),
                       "l2": "inputs+outputs (>= 1.5 GiB at 2^24) exceed the 126 MB L2; no flush needed",
                       "timing": "CUDA events on the engine stream, max over ranks"},
            "e2e": result["e2e"], "gpu_launches": result["gpu_launches"], "clocks": result["clocks"],

@@ -401,7 +401,22 @@ def bench_distributed(args, ctx, enc, field, n, synthetic_coeffs):
     assert r == root0
     ms_per_step = float(ms.item()) / args.steps
     e2e_s = float(e2e.item())
-    return dict(value=n / (ms_per_step * 1e-3), ms_per_step=ms_per_step, gpu_launches=int(launches.item()), clocks=clocks,
+    # parity at the benchmarked size: the sharded commit's LcRoot == the single-GPU commit of the same polynomial
+    # (which the parity tests hold to the oracle).  Rank 0 rebuilds every rank's slice; skipped beyond 2^24.
+    root_check = "skipped (size)"
+    if n <= (1 << 24):
+        if rank == 0:
+            from .host import LcCommit
+            parts = []
+            for g in range(world):
+                g0, g1 = p.rows(g)
+                parts.append(synthetic_coeffs(field, max(min(g1 * p.n_per_row, n) - g0 * p.n_per_row, 0), seed=1000 + g))
+            single = LcCommit.commit(np.concatenate(parts), enc)
+            root_check = "equals the single-GPU commit" if single.get_root() == root0 else "MISMATCH"
+            single.close()
+            assert root_check != "MISMATCH", "distributed LcRoot differs from the single-GPU commit"
+        dist.barrier()
+    return dict(value=n / (ms_per_step * 1e-3), root_check=root_check, ms_per_step=ms_per_step, gpu_launches=int(launches.item()), clocks=clocks,
                 root=root0.root.hex(), transport=dc.transport,
                 phases_ms={"encode_and_scatter": float(ph[0]), "exchange_wait": float(ph[1]), "hash_merkle_root": float(ph[2])},
                 dominant=_dominant_multi(enc, field, p, dc, float(ph[0])),
