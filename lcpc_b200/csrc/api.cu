@@ -34,6 +34,7 @@ struct lcpc_b200_ctx {
   cudaStream_t side_stream = nullptr;
   cudaEvent_t side_ev[MAX_CHUNKS] = {};
   cudaEvent_t side_done = nullptr;
+  cudaEvent_t lane_fork = nullptr, lane_join = nullptr;  // lent to the expander encode in scatter mode
   std::mutex mu;
   std::string err;
   uint64_t launches = 0;
@@ -192,7 +193,9 @@ int lcpc_b200_ctx_create(int device, lcpc_b200_ctx **out) {
             cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&ctx->begin_ev, cudaEventDisableTiming) == cudaSuccess &&
-            cudaEventCreateWithFlags(&ctx->side_done, cudaEventDisableTiming) == cudaSuccess;
+            cudaEventCreateWithFlags(&ctx->side_done, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->lane_fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->lane_join, cudaEventDisableTiming) == cudaSuccess;
   for (auto &e : ctx->chunk_ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
   for (auto &e : ctx->side_ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
@@ -224,6 +227,8 @@ void lcpc_b200_ctx_destroy(lcpc_b200_ctx *ctx) {
     if (e) cudaEventDestroy(e);
   if (ctx->begin_ev) cudaEventDestroy(ctx->begin_ev);
   if (ctx->side_done) cudaEventDestroy(ctx->side_done);
+  if (ctx->lane_fork) cudaEventDestroy(ctx->lane_fork);
+  if (ctx->lane_join) cudaEventDestroy(ctx->lane_join);
   if (ctx->scratch) cudaFree(ctx->scratch);
   delete ctx;
 }
@@ -367,8 +372,9 @@ static int encode_rows(lcpc_b200_enc *enc, const uint32_t *src, size_t src_strid
     ce = launch_ntt_rows(enc->field, src, src_stride, valid, dst, enc->n_cols, enc->d_roots, enc->log_n, n_rows,
                          ctx->stream, &nl, scatter);
   } else {
+    SideLane lane{ctx->side_stream, ctx->lane_fork, ctx->lane_join};
     ce = expander_encode_rows(enc->code, src, src_stride, valid, dst, enc->n_cols, n_rows, enc_scratch, ctx->stream, &nl,
-                              scatter);
+                              scatter, nullptr, 0, ~(size_t)0, scatter ? &lane : nullptr);
   }
   ctx->launches += nl;
   if (ce != cudaSuccess) return cuda_fail(ctx, ce, "encode");

@@ -18,6 +18,12 @@ struct CscView {
 
 struct ExpanderCode;
 
+// a second stream + two events the caller lends for work that may run beside the chain (scatter mode only)
+struct SideLane {
+  cudaStream_t stream;
+  cudaEvent_t fork, join;
+};
+
 // uploads the code in gather (row-compressed) form; returns an LCPC_B200_* status
 int expander_build(int field, size_t n_levels, const CscView *pre, const CscView *post, cudaStream_t stream,
                    ExpanderCode **out, std::string *err);
@@ -33,6 +39,6 @@ size_t expander_scratch_bytes(const ExpanderCode *code, size_t n_rows);
 cudaError_t expander_encode_rows(const ExpanderCode *code, const uint32_t *src, size_t src_stride, size_t valid,
                                  uint32_t *dst, size_t dst_stride, size_t n_rows, void *scratch, cudaStream_t stream,
                                  int *n_launches, const Scatter *scatter = nullptr, uint32_t *copy_dst = nullptr,
-                                 size_t copy_stride = 0, size_t src_total = ~(size_t)0);
+                                 size_t copy_stride = 0, size_t src_total = ~(size_t)0, const SideLane *side = nullptr);
 
 }  // namespace lcpc

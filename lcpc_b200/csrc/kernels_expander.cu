@@ -250,7 +250,8 @@ constexpr int TT = 32;
 template <int N>
 __global__ void __launch_bounds__(256)
 transpose_kernel(const uint32_t *__restrict__ src, size_t src_ld, uint32_t *__restrict__ dst, size_t dst_ld,
-                 size_t n_r, size_t n_c, Scatter sc, uint32_t *__restrict__ copy_dst, size_t copy_ld, size_t src_total) {
+                 size_t n_r, size_t n_c, Scatter sc, uint32_t *__restrict__ copy_dst, size_t copy_ld, size_t src_total,
+                 size_t pos0) {
   __shared__ uint32_t tile[N][TT][TT + 1];
   const size_t c0 = (size_t)blockIdx.x * TT, r0 = (size_t)blockIdx.y * TT;
   const unsigned tx = threadIdx.x % TT, ty = threadIdx.x / TT;  // 32 x 8
@@ -276,15 +277,40 @@ transpose_kernel(const uint32_t *__restrict__ src, size_t src_ld, uint32_t *__re
       uint32_t v[N];
 #pragma unroll
       for (int l = 0; l < N; l++) v[l] = tile[l][tx][cc];
-      uint32_t *out = dst + (cidx * dst_ld + r) * N;
+      const size_t pos = pos0 + r;  // destination position (pos0 > 0: the source starts at work-buffer position pos0)
+      uint32_t *out = dst + (cidx * dst_ld + pos) * N;
       if (sc.n_blocks) {
         unsigned h = 0;
-        while (h + 1 < sc.n_blocks && r >= sc.starts[h + 1]) h++;
+        while (h + 1 < sc.n_blocks && pos >= sc.starts[h + 1]) h++;
         const size_t start = sc.starts[h], width = sc.starts[h + 1] - start;
-        out = sc.dst[h] + ((sc.row0 + cidx) * width + (r - start)) * N;
+        out = sc.dst[h] + ((sc.row0 + cidx) * width + (pos - start)) * N;
       }
       stv<N>(out, v);
     }
+  }
+}
+
+// The systematic part of the codeword (positions [0, n_in) = the coefficients themselves, two thirds of it) is
+// final before the chain starts: in the multi-GPU commit it leaves for its column owners on a side stream while
+// the sparse products run, straight from the row-major source rows (no transpose involved).
+template <int N>
+__global__ void __launch_bounds__(256)
+scatter_rows_kernel(const uint32_t *__restrict__ src, size_t src_ld, size_t src_total, size_t n_rows, size_t n_in,
+                    Scatter sc) {
+  const size_t total = n_rows * n_in;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = idx / n_in, pos = idx % n_in;
+    uint32_t v[N];
+    if (r * src_ld + pos < src_total) {
+      ldv<N>(v, src + (r * src_ld + pos) * N);
+    } else {
+#pragma unroll
+      for (int l = 0; l < N; l++) v[l] = 0;
+    }
+    unsigned h = 0;
+    while (h + 1 < sc.n_blocks && pos >= sc.starts[h + 1]) h++;
+    const size_t start = sc.starts[h], width = sc.starts[h + 1] - start;
+    stv<N>(sc.dst[h] + ((sc.row0 + r) * width + (pos - start)) * N, v);
   }
 }
 
@@ -464,7 +490,7 @@ template <int FID>
 static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_t src_stride, size_t valid,
                                uint32_t *dst, size_t dst_stride, size_t n_rows, void *scratch, cudaStream_t st,
                                int *n_launches, const Scatter *scatter, uint32_t *copy_dst, size_t copy_stride,
-                               size_t src_total) {
+                               size_t src_total, const SideLane *side) {
   using F = Field<FID>;
   constexpr int N = F::N;
   if (n_launches) *n_launches = 0;
@@ -474,12 +500,24 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
   uint32_t *W = (uint32_t *)scratch;                       // [n_cols][n_rows]
   uint32_t *T = W + c->n_cols * n_rows * N;                // [tmp_len][n_rows]
   int launches = 0;
+  const bool early = scatter && scatter->n_blocks && side && side->stream;
+  if (early) {  // systematic positions leave now, on the side stream, overlapped with the chain below
+    cudaError_t e = cudaEventRecord(side->fork, st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(side->stream, side->fork, 0);
+    if (e != cudaSuccess) return e;
+    const size_t total = n_rows * c->n_in;
+    const unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+    scatter_rows_kernel<N><<<grid, 256, 0, side->stream>>>(src, src_stride, src_total, n_rows, c->n_in, *scatter);
+    launches++;
+    e = cudaEventRecord(side->join, side->stream);
+    if (e != cudaSuccess) return e;
+  }
   // coefficients -> W[0 .. n_in)
   {
     dim3 grid((unsigned)((c->n_in + TT - 1) / TT), (unsigned)((n_rows + TT - 1) / TT));
     Scatter none;
     none.n_blocks = 0;
-    transpose_kernel<N><<<grid, 256, 0, st>>>(src, src_stride, W, n_rows, n_rows, c->n_in, none, copy_dst, copy_stride, src_total);
+    transpose_kernel<N><<<grid, 256, 0, st>>>(src, src_stride, W, n_rows, n_rows, c->n_in, none, copy_dst, copy_stride, src_total, 0);
     launches++;
   }
   for (size_t oi = 0; oi < c->ops.size(); oi++) {
@@ -555,14 +593,20 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
-  // W -> row-major codewords
+  // W -> row-major codewords (or per-column-block matrices); positions [0, n_in) are skipped if they already left
   {
-    dim3 grid((unsigned)((n_rows + TT - 1) / TT), (unsigned)((c->n_cols + TT - 1) / TT));
+    const size_t pos0 = early ? c->n_in : 0, n_pos = c->n_cols - pos0;
+    dim3 grid((unsigned)((n_rows + TT - 1) / TT), (unsigned)((n_pos + TT - 1) / TT));
     Scatter sc;
     sc.n_blocks = 0;
     if (scatter && scatter->n_blocks) sc = *scatter;
-    transpose_kernel<N><<<grid, 256, 0, st>>>(W, n_rows, dst, dst_stride, c->n_cols, n_rows, sc, nullptr, 0, ~(size_t)0);
+    transpose_kernel<N><<<grid, 256, 0, st>>>(W + pos0 * n_rows * N, n_rows, dst, dst_stride, n_pos, n_rows, sc, nullptr, 0,
+                                              ~(size_t)0, pos0);
     launches++;
+    if (early) {
+      cudaError_t e = cudaStreamWaitEvent(st, side->join, 0);
+      if (e != cudaSuccess) return e;
+    }
   }
   if (n_launches) *n_launches = launches;
   return cudaGetLastError();
@@ -571,12 +615,12 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
 cudaError_t expander_encode_rows(const ExpanderCode *c, const uint32_t *src, size_t src_stride, size_t valid,
                                  uint32_t *dst, size_t dst_stride, size_t n_rows, void *scratch, cudaStream_t st,
                                  int *n_launches, const Scatter *scatter, uint32_t *copy_dst, size_t copy_stride,
-                                 size_t src_total) {
+                                 size_t src_total, const SideLane *side) {
   switch (c->field) {
-    case FT63: return encode_impl<FT63>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches, scatter, copy_dst, copy_stride, src_total);
-    case FT127: return encode_impl<FT127>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches, scatter, copy_dst, copy_stride, src_total);
-    case FT191: return encode_impl<FT191>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches, scatter, copy_dst, copy_stride, src_total);
-    case FT255: return encode_impl<FT255>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches, scatter, copy_dst, copy_stride, src_total);
+    case FT63: return encode_impl<FT63>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches, scatter, copy_dst, copy_stride, src_total, side);
+    case FT127: return encode_impl<FT127>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches, scatter, copy_dst, copy_stride, src_total, side);
+    case FT191: return encode_impl<FT191>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches, scatter, copy_dst, copy_stride, src_total, side);
+    case FT255: return encode_impl<FT255>(c, src, src_stride, valid, dst, dst_stride, n_rows, scratch, st, n_launches, scatter, copy_dst, copy_stride, src_total, side);
     default: return cudaErrorInvalidValue;
   }
 }
