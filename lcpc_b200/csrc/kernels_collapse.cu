@@ -4,10 +4,12 @@
 // collapse_columns (reference: lcpc-2d/src/lib.rs:1095-1123, call sites :1034,:1055):
 //     poly[c] = sum_r tensor[r] * coeffs[r * n_per_row + c]
 // The reference reduces every product mod p and adds; here each thread keeps the UNREDUCED
-// double-width sum of its products (a 2N+1-limb accumulator), and one Montgomery reduction is done
-// per output element -- half the multiplier work of reduce-per-product.  The result is the same
-// canonical residue: REDC is linear mod p and the final value is brought into [0, p).
-// open_column's strided gather (lcpc-2d/src/lib.rs:802-808) is gather_columns_kernel.
+// double-width sum of its products (a 2N-limb accumulator kept below 2^(64N-1) by subtracting p*R when it
+// grows past that, field.cuh mac_wide), and one Montgomery reduction is done per output element -- half the
+// multiplier work of reduce-per-product.  The result is the same canonical residue: REDC is linear mod p
+// and the final value is brought into [0, p).
+// open_column's strided gather (lcpc-2d/src/lib.rs:802-808) is gather_columns_kernel; the challenge tensors
+// of the degree tests (:1026-1032) are expanded on the device by expand_tensor_kernel.
 #include <algorithm>
 
 #include "field.cuh"

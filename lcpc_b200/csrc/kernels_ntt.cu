@@ -1,4 +1,4 @@
-// lcpc_b200/csrc/kernels_ntt.cu -- Ligero row encoding: batched radix-2 NTT over shared memory.
+// lcpc_b200/csrc/kernels_ntt.cu -- Ligero row encoding: batched NTT (radix-2 DIF semantics, radix-8 register rounds).
 //
 // Replaces LigeroEncoding::encode (reference: lcpc-ligero-pc/src/lib.rs:162-164), which delegates to
 // fffft 0.4 `fft_io_pc`: in-order input, bit-reversed output, decimation in frequency,
