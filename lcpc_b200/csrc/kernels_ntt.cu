@@ -459,7 +459,9 @@ static cudaError_t ntt_rows_impl(const uint32_t *src, size_t src_stride, size_t 
   size_t cur_stride = src_stride, cur_valid = src_valid;
   for (unsigned ip = 0; ip < n_pass; ip++) {
     unsigned remaining = n_pass - ip;
-    unsigned S = (hi + remaining - 1) / remaining;  // balanced split, larger passes first
+    // balanced split, larger passes first (2^17: 9 + 8 measured 4.75 ms; 8 + 9, which would save 1.6 % of the
+    // products in the final round, measured 4.78 ms)
+    unsigned S = (hi + remaining - 1) / remaining;
     NttPass p;
     p.log_n = log_n, p.hi = hi, p.S = S;
     unsigned logC = S >= LOG_TILE ? 0 : LOG_TILE - S;
