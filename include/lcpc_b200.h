@@ -38,6 +38,15 @@ extern "C" {
 #define LCPC_B200_ERR_OOM (-5)         /* device or pinned-host allocation failed */
 #define LCPC_B200_ERR_COLUMN (-6)      /* ProverError::ColumnNumber (:797-799) */
 #define LCPC_B200_ERR_UNSUPPORTED (-7) /* valid request this build does not implement */
+#define LCPC_B200_ERR_OUTER_TENSOR (-8) /* ProverError::OuterTensor (:1016-1018) */
+/* VerifierError (lcpc-2d/src/lib.rs:141-170); VerifierError::Encode is LCPC_B200_ERR_ENCODE */
+#define LCPC_B200_VERR_NUM_COL_OPENS (-20) /* :845-847 */
+#define LCPC_B200_VERR_COLUMN_PATH (-21)   /* :940 */
+#define LCPC_B200_VERR_COLUMN_EVAL (-22)   /* :939 */
+#define LCPC_B200_VERR_COLUMN_DEGREE (-23) /* :938 */
+#define LCPC_B200_VERR_OUTER_TENSOR (-24)  /* :854-856 */
+#define LCPC_B200_VERR_INNER_TENSOR (-25)  /* :851-853 */
+#define LCPC_B200_VERR_ENCODING_DIMS (-26) /* :857-859 */
 
 /* field ids: lcpc-test-fields/src/lib.rs:13-59 */
 enum { LCPC_B200_FT63 = 1, LCPC_B200_FT127 = 2, LCPC_B200_FT191 = 3, LCPC_B200_FT255 = 4 };
@@ -193,6 +202,50 @@ int lcpc_b200_collapse(lcpc_b200_ctx *ctx, int field, const uint64_t *coeffs, co
 int lcpc_b200_commit_open_columns(lcpc_b200_commit *c, const uint64_t *cols, size_t n, uint64_t *cols_out,
                                   uint8_t *paths_out);
 
+/* ---- whole prove() / verify() (lcpc-2d/src/lib.rs:1004-1093, :832-952) ----
+ * The Fiat-Shamir transcript (merlin::Transcript) is sequential host work and lives on the host side of the
+ * boundary (include/lcpc_b200_host.h: lcpc_b200_transcript_*); a Rust host passes challenges itself through the
+ * piecewise entry points above, a host without merlin hands a transcript handle to the two calls below. */
+typedef struct lcpc_b200_transcript lcpc_b200_transcript;
+/* domain-separation labels (LcEncoding::LABEL_DT/PR/PE/CO, :78-85).  NULL selects what def_labels! actually
+ * produces for every encoding of the reference, the literal byte strings "$l//DT", "$l//PR", "$l//PE", "$l//CO"
+ * (lcpc-2d/src/macros.rs:28-36: `$l` inside a byte-string literal is not substituted). */
+typedef struct {
+  const uint8_t *dt, *pr, *pe, *co;
+  size_t dt_len, pr_len, pe_len, co_len;
+} lcpc_b200_labels;
+/* prove (:1004-1093): n_degree_tests x { key <- tr.challenge(LABEL_DT); tensor <- ChaCha20(key) on the device;
+ * p_random[i] = collapse(coeffs, tensor); tr <- p_random[i] }, p_eval = collapse(coeffs, outer_tensor), tr <- p_eval,
+ * key <- tr.challenge(LABEL_CO), n_col_opens column numbers <- Uniform(0, n_cols) over ChaCha20(key), open_column each.
+ * Outputs (host): p_eval n_per_row elements; p_random n_degree_tests x n_per_row; col_idx (optional) the opened column
+ * numbers; cols_out n_col_opens x n_rows elements; paths_out n_col_opens x path_len x 32 bytes.
+ * ERR_OUTER_TENSOR when outer_len != n_rows. */
+int lcpc_b200_commit_prove(lcpc_b200_commit *c, lcpc_b200_transcript *tr, const lcpc_b200_labels *labels,
+                           const uint64_t *outer_tensor, size_t outer_len, size_t n_degree_tests, size_t n_col_opens,
+                           uint64_t *p_eval, uint64_t *p_random, uint64_t *col_idx, uint64_t *cols_out,
+                           uint8_t *paths_out);
+/* the fields of an LcEvalProof (:490-500) as flat host arrays */
+typedef struct {
+  size_t n_cols;            /* LcEvalProof::n_cols */
+  size_t n_per_row;         /* p_eval.len() */
+  size_t n_degree_tests;    /* p_random_vec.len() */
+  size_t n_columns;         /* columns.len() */
+  size_t n_rows;            /* columns[0].col.len() */
+  size_t path_len;          /* columns[i].path.len() */
+  const uint64_t *p_eval;   /* n_per_row elements */
+  const uint64_t *p_random; /* n_degree_tests x n_per_row */
+  const uint64_t *cols;     /* n_columns x n_rows (each LcColumn::col contiguous) */
+  const uint8_t *paths;     /* n_columns x path_len x 32 */
+} lcpc_b200_proof;
+/* verify (:832-952): argument checks (:845-859), challenges re-derived from `tr` (:866-911), p_random / p_eval
+ * rows encoded on the device (:883-888, :914-921), every opened column checked in one batch (:926-942: dot
+ * products against all tensors, leaf digest, Merkle path), then <inner_tensor, p_eval> (:944-951) -> eval_out.
+ * Returns LCPC_B200_OK, an LCPC_B200_VERR_* code, or LCPC_B200_ERR_*. */
+int lcpc_b200_verify(lcpc_b200_enc *enc, lcpc_b200_transcript *tr, const lcpc_b200_labels *labels,
+                     const uint8_t root[32], const uint64_t *outer_tensor, size_t outer_len,
+                     const uint64_t *inner_tensor, size_t inner_len, size_t n_col_opens, size_t n_degree_tests,
+                     const lcpc_b200_proof *proof, uint64_t *eval_out);
+
 /* ---- standalone pieces (tests, verifier-side use, multi-GPU pipeline) ---- */
 /* merkleize (lcpc-2d/src/lib.rs:690-704) of a host row-major comm into host hashes[2*np2-1][32] */
 int lcpc_b200_merkleize(lcpc_b200_ctx *ctx, int field, const uint64_t *comm, size_t n_rows, size_t n_cols,
@@ -216,7 +269,8 @@ int lcpc_b200_collapse_dev(lcpc_b200_ctx *ctx, int field, const uint64_t *d_coef
                            const uint64_t *d_tensor, uint64_t *d_poly, size_t n_rows, size_t n_per_row);
 /* element-wise field arithmetic on host arrays (parity tests of the device arithmetic):
  * op 0 add, 1 sub, 2 mul, 4 from_mont (b ignored), 5 mul as full product + separate reduction,
- * 6 r[i] = sum_{k<37} a[(i+k)%n] * b[(7i+k)%n] accumulated double-width and reduced once */
+ * 6 r[i] = sum_{k<37} a[(i+k)%n] * b[(7i+k)%n] accumulated double-width and reduced once,
+ * 7 mul as a one-level Karatsuba product + reduction (fields with 2 or 4 u64 limbs; plain mul otherwise) */
 int lcpc_b200_field_op(lcpc_b200_ctx *ctx, int field, int op, uint64_t *r, const uint64_t *a,
                        const uint64_t *b, size_t n);
 

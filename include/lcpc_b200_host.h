@@ -38,6 +38,24 @@ int lcpc_b200_sdig_code_matrix(const lcpc_b200_sdig_code *c, size_t level, int i
 /* convenience: lcpc_b200_sdig_new on every matrix of a generated code */
 int lcpc_b200_sdig_new_from_code(lcpc_b200_ctx *ctx, const lcpc_b200_sdig_code *c, lcpc_b200_enc **out);
 
+/* merlin::Transcript (merlin 2.0: STROBE-128 over Keccak-f[1600]), the Fiat-Shamir transcript of prove()/verify()
+ * (lcpc-2d/src/lib.rs:16, :304-311, :518-527).  Sequential host work; in a Rust integration this stays merlin. */
+int lcpc_b200_transcript_new(const uint8_t *label, size_t n, lcpc_b200_transcript **out); /* Transcript::new */
+int lcpc_b200_transcript_clone(const lcpc_b200_transcript *tr, lcpc_b200_transcript **out);
+void lcpc_b200_transcript_free(lcpc_b200_transcript *tr);
+int lcpc_b200_transcript_append_message(lcpc_b200_transcript *tr, const uint8_t *label, size_t nl, const uint8_t *msg,
+                                        size_t n);
+int lcpc_b200_transcript_append_u64(lcpc_b200_transcript *tr, const uint8_t *label, size_t nl, uint64_t x);
+int lcpc_b200_transcript_challenge_bytes(lcpc_b200_transcript *tr, const uint8_t *label, size_t nl, uint8_t *out,
+                                         size_t n);
+/* FieldHash::transcript_update (lcpc-2d/src/lib.rs:46-49) for `count` elements: one append_message(label, repr_i)
+ * per element; repr = canonical little-endian bytes (to_repr), elem_bytes each */
+int lcpc_b200_transcript_append_reprs(lcpc_b200_transcript *tr, const uint8_t *label, size_t nl, const uint8_t *repr,
+                                      size_t elem_bytes, size_t count);
+/* the column challenge of prove()/verify() (:1073-1080, :903-911): n draws of Uniform::new(0usize, n_cols) from
+ * ChaCha20Rng::from_seed(key) */
+int lcpc_b200_sample_columns(const uint8_t key[32], size_t n_cols, size_t n, uint64_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,10 @@ reference (Rust)                       here
 ``LcCommit::commit / get_root /        ``LcCommit.commit(coeffs, enc)``, ``.get_root()``,
 prove`` (lib.rs:276-311)               ``.collapse(tensor)``, ``.open_columns(cols)``
 ``LcRoot`` (lib.rs:315-323)            ``LcRoot`` (32-byte digest)
+``LcCommit::prove`` (lib.rs:304-311)   ``LcCommit.prove(outer_tensor, enc, tr)`` -> ``LcEvalProof``
+``LcEvalProof::verify`` (:518-527)     ``LcEvalProof.verify(root, outer, inner, enc, tr)``
+``merlin::Transcript``                 ``Transcript(label)``
+serde / bincode of the three types     ``serialize_*`` / ``deserialize_*`` (``lcpc_b200.proof``)
 =====================================  ==========================================================
 
 Field elements are ``numpy.uint64`` arrays of shape ``(n, L)``: the in-memory image of the reference's
@@ -24,7 +28,11 @@ from .host import (FT63, FT127, FT191, FT255, FIELD_LIMBS, Context, LcCommit, Lc
                    LigeroEncoding, SdigEncoding, default_context, field_op, merkleize, collapse_columns,
                    ligero_get_dims, n_degree_tests, expand_tensor)
 from ._cabi import LcpcError, LIB_PATH  # noqa: F401
+from .proof import (LcEvalProof, Transcript, prove, sample_columns, serialize_root, serialize_commit,  # noqa: F401
+                    serialize_proof, deserialize_root, deserialize_commit_fields, deserialize_proof)
 
 __all__ = ["FT63", "FT127", "FT191", "FT255", "FIELD_LIMBS", "Context", "LcCommit", "LcEncoding", "LcRoot",
            "LigeroEncoding", "SdigEncoding", "LcpcError", "default_context", "field_op", "merkleize",
-           "collapse_columns", "ligero_get_dims", "n_degree_tests", "expand_tensor"]
+           "collapse_columns", "ligero_get_dims", "n_degree_tests", "expand_tensor", "LcEvalProof", "Transcript", "prove",
+           "sample_columns", "serialize_root", "serialize_commit", "serialize_proof", "deserialize_root",
+           "deserialize_commit_fields", "deserialize_proof"]

@@ -15,8 +15,16 @@ LIB_PATH = os.environ.get("LCPC_B200_LIB") or os.path.join(_HERE, "lib", "liblcp
 
 OK = 0
 ERR_BAD_ARG, ERR_TOO_BIG, ERR_ENCODE, ERR_CUDA, ERR_OOM, ERR_COLUMN, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6, -7
+ERR_OUTER_TENSOR = -8
+# VerifierError (lcpc-2d/src/lib.rs:141-170)
+(VERR_NUM_COL_OPENS, VERR_COLUMN_PATH, VERR_COLUMN_EVAL, VERR_COLUMN_DEGREE, VERR_OUTER_TENSOR, VERR_INNER_TENSOR,
+ VERR_ENCODING_DIMS) = -20, -21, -22, -23, -24, -25, -26
 _ERR_NAMES = {ERR_BAD_ARG: "BAD_ARG", ERR_TOO_BIG: "TOO_BIG", ERR_ENCODE: "ENCODE", ERR_CUDA: "CUDA",
-              ERR_OOM: "OOM", ERR_COLUMN: "COLUMN", ERR_UNSUPPORTED: "UNSUPPORTED"}
+              ERR_OOM: "OOM", ERR_COLUMN: "COLUMN", ERR_UNSUPPORTED: "UNSUPPORTED", ERR_OUTER_TENSOR: "OUTER_TENSOR",
+              VERR_NUM_COL_OPENS: "VerifierError::NumColOpens", VERR_COLUMN_PATH: "VerifierError::ColumnPath",
+              VERR_COLUMN_EVAL: "VerifierError::ColumnEval", VERR_COLUMN_DEGREE: "VerifierError::ColumnDegree",
+              VERR_OUTER_TENSOR: "VerifierError::OuterTensor", VERR_INNER_TENSOR: "VerifierError::InnerTensor",
+              VERR_ENCODING_DIMS: "VerifierError::EncodingDims"}
 
 
 class LcpcError(RuntimeError):
@@ -34,6 +42,17 @@ class Csc(C.Structure):
 
 class Scatter(C.Structure):
     _fields_ = [("n_blocks", C.c_size_t), ("starts", C.c_void_p), ("dst", C.c_void_p), ("row0", C.c_size_t)]
+
+
+class Labels(C.Structure):
+    _fields_ = [("dt", C.c_char_p), ("pr", C.c_char_p), ("pe", C.c_char_p), ("co", C.c_char_p),
+                ("dt_len", C.c_size_t), ("pr_len", C.c_size_t), ("pe_len", C.c_size_t), ("co_len", C.c_size_t)]
+
+
+class Proof(C.Structure):
+    _fields_ = [("n_cols", C.c_size_t), ("n_per_row", C.c_size_t), ("n_degree_tests", C.c_size_t),
+                ("n_columns", C.c_size_t), ("n_rows", C.c_size_t), ("path_len", C.c_size_t),
+                ("p_eval", C.c_void_p), ("p_random", C.c_void_p), ("cols", C.c_void_p), ("paths", C.c_void_p)]
 
 
 _vp, _sz, _i, _u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64
@@ -84,6 +103,8 @@ SIGNATURES = {
     "lcpc_b200_expand_tensor": (_i, [_vp, _i, _vp, _sz, _vp]),
     "lcpc_b200_collapse": (_i, [_vp, _i, _vp, _vp, _vp, _sz, _sz]),
     "lcpc_b200_commit_open_columns": (_i, [_vp, _vp, _sz, _vp, _vp]),
+    "lcpc_b200_commit_prove": (_i, [_vp, _vp, C.POINTER(Labels), _vp, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "lcpc_b200_verify": (_i, [_vp, _vp, C.POINTER(Labels), _vp, _vp, _sz, _vp, _sz, _sz, _sz, C.POINTER(Proof), _vp]),
     "lcpc_b200_merkleize": (_i, [_vp, _i, _vp, _sz, _sz, _vp]),
     "lcpc_b200_hash_columns_dev": (_i, [_vp, _i, _vp, _sz, _sz, _sz, _vp]),
     "lcpc_b200_merkle_tree_dev": (_i, [_vp, _vp, _sz]),
@@ -105,6 +126,14 @@ SIGNATURES = {
     "lcpc_b200_sdig_code_codeword_length": (_sz, [_vp]),
     "lcpc_b200_sdig_code_matrix": (_i, [_vp, _sz, _i, C.POINTER(Csc)]),
     "lcpc_b200_sdig_new_from_code": (_i, [_vp, _vp, _pvp]),
+    "lcpc_b200_transcript_new": (_i, [C.c_char_p, _sz, _pvp]),
+    "lcpc_b200_transcript_clone": (_i, [_vp, _pvp]),
+    "lcpc_b200_transcript_free": (None, [_vp]),
+    "lcpc_b200_transcript_append_message": (_i, [_vp, C.c_char_p, _sz, C.c_char_p, _sz]),
+    "lcpc_b200_transcript_append_u64": (_i, [_vp, C.c_char_p, _sz, _u64]),
+    "lcpc_b200_transcript_challenge_bytes": (_i, [_vp, C.c_char_p, _sz, _vp, _sz]),
+    "lcpc_b200_transcript_append_reprs": (_i, [_vp, C.c_char_p, _sz, _vp, _sz, _sz]),
+    "lcpc_b200_sample_columns": (_i, [_vp, _sz, _sz, _vp]),
 }
 
 _lib = None

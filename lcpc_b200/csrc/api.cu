@@ -13,8 +13,11 @@
 #include <vector>
 
 #include "../../include/lcpc_b200.h"
+#include "../../include/lcpc_b200_host.h"
 #include "expander.h"
 #include "field.cuh"
+#include "host_chacha.h"
+#include "host_transcript.h"
 #include "kernels.h"
 
 using namespace lcpc;
@@ -980,11 +983,10 @@ int lcpc_b200_collapse(lcpc_b200_ctx *ctx, int field, const uint64_t *coeffs, co
   return LCPC_B200_OK;
 }
 
-int lcpc_b200_commit_open_columns(lcpc_b200_commit *c, const uint64_t *cols, size_t n, uint64_t *cols_out,
-                                  uint8_t *paths_out) {
-  if (!c || (n && (!cols || !cols_out || !paths_out))) return LCPC_B200_ERR_BAD_ARG;
+// open_column for n columns; the context's mutex is held by the caller
+static int open_columns_locked(lcpc_b200_commit *c, const uint64_t *cols, size_t n, uint64_t *cols_out,
+                               uint8_t *paths_out) {
   lcpc_b200_ctx *ctx = c->enc->ctx;
-  std::lock_guard<std::mutex> g(ctx->mu);
   for (size_t i = 0; i < n; i++)
     if (cols[i] >= c->n_cols) return fail(ctx, LCPC_B200_ERR_COLUMN, "column %llu >= n_cols %zu", (unsigned long long)cols[i], c->n_cols);
   if (n == 0) return LCPC_B200_OK;
@@ -1008,6 +1010,226 @@ int lcpc_b200_commit_open_columns(lcpc_b200_commit *c, const uint64_t *cols, siz
   CU(ctx, cudaMemcpyAsync(cols_out, base + off_vals, n * c->n_rows * B, cudaMemcpyDeviceToHost, ctx->stream));
   if (path_len) CU(ctx, cudaMemcpyAsync(paths_out, base + off_paths, n * (size_t)path_len * 32, cudaMemcpyDeviceToHost, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return LCPC_B200_OK;
+}
+
+int lcpc_b200_commit_open_columns(lcpc_b200_commit *c, const uint64_t *cols, size_t n, uint64_t *cols_out,
+                                  uint8_t *paths_out) {
+  if (!c || (n && (!cols || !cols_out || !paths_out))) return LCPC_B200_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> g(c->enc->ctx->mu);
+  return open_columns_locked(c, cols, n, cols_out, paths_out);
+}
+
+
+// ------------------------------------------------------------------------------- prove() / verify()
+namespace {
+
+struct Labels {
+  const uint8_t *dt, *pr, *pe, *co;
+  size_t dt_len, pr_len, pe_len, co_len;
+};
+// def_labels! (lcpc-2d/src/macros.rs:28-36) leaves `$l` unsubstituted inside the byte-string literals
+const uint8_t kLabelDT[] = "$l//DT", kLabelPR[] = "$l//PR", kLabelPE[] = "$l//PE", kLabelCO[] = "$l//CO";
+Labels resolve_labels(const lcpc_b200_labels *in) {
+  if (!in) return Labels{kLabelDT, kLabelPR, kLabelPE, kLabelCO, 6, 6, 6, 6};
+  return Labels{in->dt, in->pr, in->pe, in->co, in->dt_len, in->pr_len, in->pe_len, in->co_len};
+}
+
+// a device allocation that lives for one call
+struct DeviceBlock {
+  uint8_t *base = nullptr;
+  size_t used = 0, cap = 0;
+  ~DeviceBlock() {
+    if (base) cudaFree(base);
+  }
+  size_t reserve(size_t bytes) {  // returns the offset of a 256-byte aligned region
+    size_t off = (used + 255) & ~(size_t)255;
+    used = off + bytes;
+    return off;
+  }
+  cudaError_t commit() {
+    cap = used ? used : 256;
+    return cudaMalloc(&base, cap);
+  }
+};
+
+// ChaCha20Rng::from_seed(key) -> n x Uniform::new(0usize, n_cols) (lcpc-2d/src/lib.rs:1073-1080, :903-911)
+void sample_columns(const uint8_t key[32], size_t n_cols, size_t n, uint64_t *out) {
+  host::ChaCha20Stream rng = host::ChaCha20Stream::from_seed(key);
+  for (size_t i = 0; i < n; i++) out[i] = rng.below(n_cols);
+}
+
+}  // namespace
+
+int lcpc_b200_sample_columns(const uint8_t key[32], size_t n_cols, size_t n, uint64_t *out) {
+  if (!key || n_cols == 0 || (!out && n)) return LCPC_B200_ERR_BAD_ARG;
+  sample_columns(key, n_cols, n, out);
+  return LCPC_B200_OK;
+}
+
+int lcpc_b200_commit_prove(lcpc_b200_commit *c, lcpc_b200_transcript *tr, const lcpc_b200_labels *labels,
+                           const uint64_t *outer_tensor, size_t outer_len, size_t n_degree_tests, size_t n_col_opens,
+                           uint64_t *p_eval, uint64_t *p_random, uint64_t *col_idx, uint64_t *cols_out,
+                           uint8_t *paths_out) {
+  if (!c || !tr || !outer_tensor || !p_eval || (n_degree_tests && !p_random) || (n_col_opens && (!cols_out || !paths_out)))
+    return LCPC_B200_ERR_BAD_ARG;
+  lcpc_b200_ctx *ctx = c->enc->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (outer_len != c->n_rows)  // ProverError::OuterTensor (:1016-1018)
+    return fail(ctx, LCPC_B200_ERR_OUTER_TENSOR, "outer tensor has %zu entries, the commitment %zu rows", outer_len, c->n_rows);
+  if (int rc = bind_device(ctx)) return rc;
+  const Labels lb = resolve_labels(labels);
+  const int field = c->enc->field;
+  const size_t B = field_bytes(field), L = B / 8, pbytes = c->n_per_row * B;
+  uint32_t *d_repr = nullptr;
+  CU(ctx, cudaMalloc(&d_repr, pbytes));
+  std::vector<uint8_t> repr(pbytes);
+  int rc = LCPC_B200_OK;
+  // one collapse against the tensor in c->d_tensor: Montgomery limbs to `dst`, canonical bytes into the transcript
+  auto collapse_and_absorb = [&](uint64_t *dst, const uint8_t *label, size_t label_len) -> int {
+    int nl = 0;
+    cudaError_t ce = launch_collapse(field, c->d_coeffs, c->n_per_row, c->d_tensor, c->d_poly, c->n_rows, c->n_per_row,
+                                     nullptr, ctx->stream, &nl);
+    if (ce == cudaSuccess) ce = launch_field_op(field, 4, d_repr, c->d_poly, nullptr, c->n_per_row, ctx->stream);
+    ctx->launches += nl + 1;
+    if (ce != cudaSuccess) return cuda_fail(ctx, ce, "prove: collapse");
+    CU(ctx, cudaMemcpyAsync(dst, c->d_poly, pbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(repr.data(), d_repr, pbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    tr->tr.append_elems(label, label_len, repr.data(), B, c->n_per_row);  // transcript_update per coefficient (:1043-1045)
+    return LCPC_B200_OK;
+  };
+  for (size_t i = 0; i < n_degree_tests && rc == LCPC_B200_OK; i++) {  // :1025-1048
+    uint8_t key[32];
+    tr->tr.challenge_bytes(lb.dt, lb.dt_len, key, 32);
+    rc = expand_tensor_into(c, key);
+    if (rc == LCPC_B200_OK) rc = collapse_and_absorb(p_random + i * c->n_per_row * L, lb.pr, lb.pr_len);
+  }
+  if (rc == LCPC_B200_OK) {  // :1051-1063
+    cudaError_t ce = cudaMemcpyAsync(c->d_tensor, outer_tensor, c->n_rows * B, cudaMemcpyHostToDevice, ctx->stream);
+    if (ce != cudaSuccess) rc = cuda_fail(ctx, ce, "prove: outer tensor");
+    else rc = collapse_and_absorb(p_eval, lb.pe, lb.pe_len);
+  }
+  cudaFree(d_repr);
+  if (rc != LCPC_B200_OK) return rc;
+  // :1066-1085
+  uint8_t key[32];
+  tr->tr.challenge_bytes(lb.co, lb.co_len, key, 32);
+  std::vector<uint64_t> cols(n_col_opens);
+  sample_columns(key, c->n_cols, n_col_opens, cols.data());
+  if (col_idx) memcpy(col_idx, cols.data(), n_col_opens * 8);
+  return open_columns_locked(c, cols.data(), n_col_opens, cols_out, paths_out);
+}
+
+int lcpc_b200_verify(lcpc_b200_enc *enc, lcpc_b200_transcript *tr, const lcpc_b200_labels *labels,
+                     const uint8_t root[32], const uint64_t *outer_tensor, size_t outer_len,
+                     const uint64_t *inner_tensor, size_t inner_len, size_t n_col_opens, size_t n_degree_tests,
+                     const lcpc_b200_proof *proof, uint64_t *eval_out) {
+  if (!enc || !tr || !root || !proof || !eval_out) return LCPC_B200_ERR_BAD_ARG;
+  lcpc_b200_ctx *ctx = enc->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  // argument checks in the reference's order (:845-859)
+  if (n_col_opens != proof->n_columns || n_col_opens == 0)
+    return fail(ctx, LCPC_B200_VERR_NUM_COL_OPENS, "proof opens %zu columns, the encoding asks for %zu", proof->n_columns, n_col_opens);
+  const size_t n_rows = proof->n_rows, n_cols = proof->n_cols, n_per_row = proof->n_per_row, n_open = proof->n_columns;
+  if (inner_len != n_per_row) return fail(ctx, LCPC_B200_VERR_INNER_TENSOR, "inner tensor: %zu != n_per_row %zu", inner_len, n_per_row);
+  if (outer_len != n_rows) return fail(ctx, LCPC_B200_VERR_OUTER_TENSOR, "outer tensor: %zu != n_rows %zu", outer_len, n_rows);
+  if (!lcpc_b200_enc_dims_ok(enc, n_per_row, n_cols)) return fail(ctx, LCPC_B200_VERR_ENCODING_DIMS, "encoding dimension mismatch");
+  // the reference indexes p_random_vec[i] for i < n_degree_tests (:883) and panics when the proof is short
+  if (proof->n_degree_tests != n_degree_tests || n_rows == 0 || !outer_tensor || !inner_tensor || !proof->p_eval ||
+      (n_degree_tests && !proof->p_random) || !proof->cols || (proof->path_len && !proof->paths) || proof->path_len > 64)
+    return fail(ctx, LCPC_B200_ERR_BAD_ARG, "verify: malformed proof");
+  if (int rc = bind_device(ctx)) return rc;
+  const Labels lb = resolve_labels(labels);
+  const int field = enc->field;
+  const size_t B = field_bytes(field), T = n_degree_tests + 1;
+  const unsigned path_len = (unsigned)proof->path_len;
+
+  DeviceBlock blk;
+  const size_t o_in = blk.reserve(T * n_per_row * B), o_repr = blk.reserve(T * n_per_row * B);
+  const size_t o_rows = blk.reserve(T * n_cols * B), o_tensors = blk.reserve(T * n_rows * B);
+  const size_t o_keys = blk.reserve(T * 32), o_cols = blk.reserve(n_open * n_rows * B);
+  const size_t o_colsT = blk.reserve(n_open * n_rows * B), o_idx = blk.reserve(n_open * 8);
+  const size_t o_leaves = blk.reserve(n_open * 32), o_paths = blk.reserve(n_open * (size_t)path_len * 32 + 32);
+  const size_t o_root = blk.reserve(32), o_evals = blk.reserve(T * n_open * B), o_flags = blk.reserve(n_open * 4);
+  const size_t o_hs = blk.reserve(hash_scratch_bytes(field, n_rows, n_open) + 32);
+  const size_t o_es = blk.reserve(enc_scratch_bytes(enc, T) + 32);
+  const size_t o_inner = blk.reserve(n_per_row * B), o_part = blk.reserve((DOT_PARTIALS + 1) * B);
+  CU(ctx, blk.commit());
+  uint8_t *d = blk.base;
+  auto w32 = [&](size_t off) { return (uint32_t *)(d + off); };
+  cudaStream_t st = ctx->stream;
+
+  // p_random rows and p_eval: to the device once; canonical bytes back for the transcript, rows on to the encode
+  if (n_degree_tests)
+    CU(ctx, cudaMemcpyAsync(d + o_in, proof->p_random, n_degree_tests * n_per_row * B, cudaMemcpyHostToDevice, st));
+  CU(ctx, cudaMemcpyAsync(d + o_in + n_degree_tests * n_per_row * B, proof->p_eval, n_per_row * B, cudaMemcpyHostToDevice, st));
+  cudaError_t ce = launch_field_op(field, 4, w32(o_repr), w32(o_in), nullptr, T * n_per_row, st);
+  ctx->launches += 1;
+  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "verify: from_mont");
+  std::vector<uint8_t> repr(T * n_per_row * B);
+  CU(ctx, cudaMemcpyAsync(repr.data(), d + o_repr, repr.size(), cudaMemcpyDeviceToHost, st));
+  CU(ctx, cudaEventRecord(ctx->begin_ev, st));
+  // step 1b / step 2 (:883-888, :914-921): every row zero-extended to n_cols and encoded, in one batch
+  if (int rc = encode_rows(enc, w32(o_in), n_per_row, n_per_row, w32(o_rows), T, d + o_es)) return rc;
+  CU(ctx, cudaEventSynchronize(ctx->begin_ev));
+
+  // host: replay the transcript while the device encodes (:866-911)
+  std::vector<uint8_t> keys(T * 32);
+  for (size_t i = 0; i < n_degree_tests; i++) {
+    tr->tr.challenge_bytes(lb.dt, lb.dt_len, keys.data() + 32 * i, 32);
+    tr->tr.append_elems(lb.pr, lb.pr_len, repr.data() + i * n_per_row * B, B, n_per_row);
+  }
+  tr->tr.append_elems(lb.pe, lb.pe_len, repr.data() + n_degree_tests * n_per_row * B, B, n_per_row);
+  uint8_t key_co[32];
+  tr->tr.challenge_bytes(lb.co, lb.co_len, key_co, 32);
+  std::vector<uint64_t> cols(n_open);
+  sample_columns(key_co, n_cols, n_open, cols.data());
+
+  // tensors: the degree-test ones expanded from their keys on the device, then the outer tensor
+  if (n_degree_tests) CU(ctx, cudaMemcpyAsync(d + o_keys, keys.data(), n_degree_tests * 32, cudaMemcpyHostToDevice, st));
+  for (size_t i = 0; i < n_degree_tests; i++) {
+    ce = launch_expand_tensor(field, w32(o_keys + 32 * i), 0, n_rows, w32(o_tensors + i * n_rows * B), st);
+    ctx->launches += 1;
+    if (ce != cudaSuccess) return cuda_fail(ctx, ce, "verify: expand_tensor");
+  }
+  CU(ctx, cudaMemcpyAsync(d + o_tensors + n_degree_tests * n_rows * B, outer_tensor, n_rows * B, cudaMemcpyHostToDevice, st));
+  CU(ctx, cudaMemcpyAsync(d + o_cols, proof->cols, n_open * n_rows * B, cudaMemcpyHostToDevice, st));
+  CU(ctx, cudaMemcpyAsync(d + o_idx, cols.data(), n_open * 8, cudaMemcpyHostToDevice, st));
+  if (path_len) CU(ctx, cudaMemcpyAsync(d + o_paths, proof->paths, n_open * (size_t)path_len * 32, cudaMemcpyHostToDevice, st));
+  CU(ctx, cudaMemcpyAsync(d + o_root, root, 32, cudaMemcpyHostToDevice, st));
+  CU(ctx, cudaMemcpyAsync(d + o_inner, inner_tensor, n_per_row * B, cudaMemcpyHostToDevice, st));
+
+  // step 3 (:926-942), batched: columns -> row-major [n_rows][n_open]; leaf digests with the commit's kernels;
+  // <tensor_k, column_j> for all j with collapse_kernel; comparisons and Merkle walks in check_columns_kernel
+  ce = launch_transpose_columns(field, w32(o_cols), w32(o_colsT), n_open, n_rows, st);
+  ctx->launches += 1;
+  int nl = 0;
+  if (ce == cudaSuccess) ce = launch_hash_columns(field, w32(o_colsT), n_rows, n_open, n_open, d + o_leaves, d + o_hs, st, &nl);
+  ctx->launches += nl;
+  for (size_t k = 0; k < T && ce == cudaSuccess; k++) {
+    ce = launch_collapse(field, w32(o_colsT), n_open, w32(o_tensors + k * n_rows * B), w32(o_evals + k * n_open * B), n_rows,
+                         n_open, nullptr, st, &nl);
+    ctx->launches += nl;
+  }
+  if (ce == cudaSuccess)
+    ce = launch_check_columns(field, w32(o_evals), w32(o_rows), n_cols, (unsigned)T, (const uint64_t *)(d + o_idx), n_open,
+                              d + o_leaves, d + o_paths, path_len, d + o_root, w32(o_flags), st);
+  ctx->launches += 1;
+  // step 4 (:944-951)
+  if (ce == cudaSuccess)
+    ce = launch_dot(field, w32(o_inner), w32(o_in + n_degree_tests * n_per_row * B), n_per_row, w32(o_part + B), w32(o_part), st, &nl);
+  ctx->launches += nl;
+  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "verify: column checks");
+  std::vector<uint32_t> flags(n_open);
+  CU(ctx, cudaMemcpyAsync(flags.data(), d + o_flags, n_open * 4, cudaMemcpyDeviceToHost, st));
+  CU(ctx, cudaMemcpyAsync(eval_out, d + o_part, B, cudaMemcpyDeviceToHost, st));
+  CU(ctx, cudaStreamSynchronize(st));
+  for (size_t j = 0; j < n_open; j++) {  // the match at :937-942
+    if (!(flags[j] & 1u)) return fail(ctx, LCPC_B200_VERR_COLUMN_DEGREE, "column %zu (#%llu): degree test dot product failed", j, (unsigned long long)cols[j]);
+    if (!(flags[j] & 2u)) return fail(ctx, LCPC_B200_VERR_COLUMN_EVAL, "column %zu (#%llu): eval dot product failed", j, (unsigned long long)cols[j]);
+    if (!(flags[j] & 4u)) return fail(ctx, LCPC_B200_VERR_COLUMN_PATH, "column %zu (#%llu): merkle path failed", j, (unsigned long long)cols[j]);
+  }
   return LCPC_B200_OK;
 }
 
@@ -1095,7 +1317,7 @@ int lcpc_b200_merkleize(lcpc_b200_ctx *ctx, int field, const uint64_t *comm, siz
 
 int lcpc_b200_field_op(lcpc_b200_ctx *ctx, int field, int op, uint64_t *r, const uint64_t *a, const uint64_t *b, size_t n) {
   if (!ctx || !r || !a) return LCPC_B200_ERR_BAD_ARG;
-  if (field_limbs32(field) < 0 || !(op == 0 || op == 1 || op == 2 || op == 4 || op == 5 || op == 6))
+  if (field_limbs32(field) < 0 || !(op == 0 || op == 1 || op == 2 || op == 4 || op == 5 || op == 6 || op == 7))
     return fail(ctx, LCPC_B200_ERR_BAD_ARG, "bad field/op %d/%d", field, op);
   const bool two = op != 4;
   if (two && !b) return LCPC_B200_ERR_BAD_ARG;

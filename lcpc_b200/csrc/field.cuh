@@ -136,6 +136,16 @@ inline void mul_wide(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b) {
 }
 #endif
 
+// the zero operand of carry-only adds: with LCPC_OPAQUE_ZERO a constant-bank load ptxas cannot fold, which keeps
+// `x + 0 + carry` an IADD3.X on the ALU pipe instead of an IMAD.X on the multiplier pipe
+LCPC_DEV uint32_t zero_operand() {
+#if defined(__CUDA_ARCH__) && defined(LCPC_OPAQUE_ZERO)
+  return kZero32;
+#else
+  return 0u;
+#endif
+}
+
 template <int FID> struct Field {
   using FP = FieldP<FID>;
   static constexpr int N = FP::N;  // 32-bit limbs
@@ -266,6 +276,9 @@ template <int FID> struct Field {
   }
 
   LCPC_DEV static Elem mul(const Elem &a, const Elem &b) {
+#if defined(LCPC_KARATSUBA)
+    if constexpr (N >= LCPC_KARATSUBA) return mul_karatsuba(a, b);
+#endif
     uint32_t E[N], O[N];
     step<true, true>(E, O, a.v, b.v[0]);
 #pragma unroll
@@ -422,6 +435,62 @@ template <int FID> struct Field {
     for (int s = 0; s < SUBS; s++) r = cond_sub_p(r);
     return r;
   }
+
+  // ---- one-level subtractive Karatsuba product (N a multiple of 4) ----
+  // a = a0 + a1 W, b = b0 + b1 W, W = 2^(16N):  a b = z0 + (z0 + z2 + (a0 - a1)(b1 - b0)) W + z2 W^2 with
+  // z0 = a0 b0, z2 = a1 b1: three half-size schoolbook products (3 N^2/4 wide IMADs instead of N^2) paid for
+  // with ~9N adds/logic ops on the ALU pipe, which the multiplier-bound kernels leave mostly idle.
+  // The middle term is formed from |a0 - a1| |b1 - b0| and the product's sign; it is non-negative and
+  // < 2^(32N+1), so the (N+1)-limb two's-complement sum below is exact.
+  LCPC_DEV static Wide mul_full_karatsuba(const Elem &a, const Elem &b) {
+    static_assert(N % 4 == 0, "Karatsuba split needs an even number of limbs per half");
+    constexpr int H = N / 2;
+    Wide t;
+    const uint32_t Z = zero_operand();
+    mul_full_n<H>(t.v, a.v, b.v);              // z0 at limbs 0..N-1
+    mul_full_n<H>(t.v + N, a.v + H, b.v + H);  // z2 at limbs N..2N-1
+    uint32_t da[H], db[H], z1[N], sa, sb;
+    sub_cc(da[0], a.v[0], a.v[H]);
+#pragma unroll
+    for (int i = 1; i < H; i++) subc_cc(da[i], a.v[i], a.v[H + i]);
+    subc(sa, Z, Z);  // all ones iff a0 < a1
+    sub_cc(db[0], b.v[H], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < H; i++) subc_cc(db[i], b.v[H + i], b.v[i]);
+    subc(sb, Z, Z);  // all ones iff b1 < b0
+    // |x| = (x ^ s) - s over H limbs (s = 0 or -1)
+    sub_cc(da[0], da[0] ^ sa, sa);
+#pragma unroll
+    for (int i = 1; i < H - 1; i++) subc_cc(da[i], da[i] ^ sa, sa);
+    subc(da[H - 1], da[H - 1] ^ sa, sa);
+    sub_cc(db[0], db[0] ^ sb, sb);
+#pragma unroll
+    for (int i = 1; i < H - 1; i++) subc_cc(db[i], db[i] ^ sb, sb);
+    subc(db[H - 1], db[H - 1] ^ sb, sb);
+    mul_full_n<H>(z1, da, db);
+    const uint32_t neg = sa ^ sb;  // all ones iff (a0 - a1)(b1 - b0) < 0
+    uint32_t mid[N + 1];
+    add_cc(mid[0], t.v[0], t.v[N]);
+#pragma unroll
+    for (int i = 1; i < N; i++) addc_cc(mid[i], t.v[i], t.v[N + i]);
+    addc(mid[N], Z, Z);
+    // mid += neg ? -z1 : z1   (two's complement over N+1 limbs: ~z1 + 1 with the sign limb -1)
+    uint32_t dummy;
+    add_cc(dummy, neg, neg);  // carry flag <- neg & 1
+    (void)dummy;
+#pragma unroll
+    for (int i = 0; i < N; i++) addc_cc(mid[i], mid[i], z1[i] ^ neg);
+    addc(mid[N], mid[N], neg);
+    // t += mid * 2^(32H)
+    add_cc(t.v[H], t.v[H], mid[0]);
+#pragma unroll
+    for (int i = 1; i <= N; i++) addc_cc(t.v[H + i], t.v[H + i], mid[i]);
+#pragma unroll
+    for (int i = H + N + 1; i < 2 * N - 1; i++) addc_cc(t.v[i], t.v[i], Z);
+    if (H + N + 1 <= 2 * N - 1) addc(t.v[2 * N - 1], t.v[2 * N - 1], Z);
+    return t;
+  }
+  LCPC_DEV static Elem mul_karatsuba(const Elem &a, const Elem &b) { return redc<1>(mul_full_karatsuba(a, b)); }
 
   // canonical integer of a Montgomery-form element: a * R^{-1} mod p  (what to_repr serialises,
   // reference: FieldHash::digest_update, lcpc-2d/src/lib.rs:42-57)

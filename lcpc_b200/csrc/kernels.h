@@ -12,7 +12,8 @@ namespace lcpc {
 int field_limbs32(int field);  // 2/4/6/8, or -1
 inline size_t field_bytes(int field) { return 4 * (size_t)field_limbs32(field); }
 
-// element-wise field ops (test hook): op 0 add, 1 sub, 2 mul, 4 from_mont, 5 mul_full+redc, 6 lazy 37-term sums
+// element-wise field ops (test hook): op 0 add, 1 sub, 2 mul, 4 from_mont, 5 mul_full+redc, 6 lazy 37-term sums,
+// 7 Karatsuba product + redc
 cudaError_t launch_field_op(int field, int op, uint32_t *r, const uint32_t *a, const uint32_t *b, size_t n,
                             cudaStream_t stream);
 
@@ -89,5 +90,20 @@ cudaError_t launch_gather_columns(int field, const uint32_t *comm, size_t n_rows
 // Merkle paths (lcpc-2d/src/lib.rs:811-821): out[i][l] = sibling of column cols[i]'s ancestor on layer l
 cudaError_t launch_gather_paths(const uint8_t *hashes, size_t np2, const uint64_t *cols, size_t n_open,
                                 unsigned path_len, uint8_t *out, cudaStream_t stream);
+
+// ---- verifier side (lcpc-2d/src/lib.rs:926-951), kernels_verify.cu ----
+// opened columns in[j][r] (each LcColumn::col contiguous) -> row-major out[r][j]
+cudaError_t launch_transpose_columns(int field, const uint32_t *in, uint32_t *out, size_t n_open, size_t n_rows,
+                                     cudaStream_t stream);
+// flags[j]: bit 0 degree-test values match (evals[k][j] == rows[k][cols[j]] for k < n_tensors - 1), bit 1 the
+// evaluation value matches (k = n_tensors - 1), bit 2 leaves[j] + paths[j][0..path_len) hash up to root
+cudaError_t launch_check_columns(int field, const uint32_t *evals, const uint32_t *rows, size_t row_stride,
+                                 unsigned n_tensors, const uint64_t *cols, size_t n_open, const uint8_t *leaves,
+                                 const uint8_t *paths, unsigned path_len, const uint8_t *root, uint32_t *flags,
+                                 cudaStream_t stream);
+// out[0] = sum_i a[i] * b[i]; partials: DOT_PARTIALS elements of scratch
+constexpr unsigned DOT_PARTIALS = 592;
+cudaError_t launch_dot(int field, const uint32_t *a, const uint32_t *b, size_t n, uint32_t *partials, uint32_t *out,
+                       cudaStream_t stream, int *n_launches);
 
 }  // namespace lcpc

@@ -109,6 +109,10 @@ __global__ void field_op_kernel(int op, uint32_t *r, const uint32_t *a, const ui
       z = F::template redc<2>(acc);
       break;
     }
+    case 7:
+      if constexpr (F::N % 4 == 0) z = F::mul_karatsuba(x, y);
+      else z = F::mul(x, y);
+      break;
     default: z = F::from_mont(x); break;
   }
   gstore<F::N>(r + i * F::N, z.v);

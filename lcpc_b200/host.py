@@ -412,6 +412,11 @@ class LcCommit:
         _check(_cabi.lib().lcpc_b200_commit_degree_test(self._h, _ptr(kb), _ptr(poly), _ptr(tensor)), self.enc.ctx)
         return (poly, tensor) if with_tensor else poly
 
+    def prove(self, outer_tensor, enc: "LcEncoding", tr):
+        """LcCommit::prove (:304-311): the evaluation proof for ``outer_tensor`` under transcript ``tr``."""
+        from .proof import prove
+        return prove(self, outer_tensor, enc, tr)
+
     def open_columns(self, cols):
         """open_column (:788-825) for every index in ``cols``: (values (n, n_rows, L), paths (n, path_len, 32))."""
         idx = np.ascontiguousarray(cols, dtype=np.uint64)
@@ -456,7 +461,7 @@ def expand_tensor(field: int, key: bytes, n: int, ctx: Context | None = None) ->
     return out
 
 
-_OPS = {"add": 0, "sub": 1, "mul": 2, "from_mont": 4, "mul_sos": 5, "lazy_sum37": 6}
+_OPS = {"add": 0, "sub": 1, "mul": 2, "from_mont": 4, "mul_sos": 5, "lazy_sum37": 6, "mul_karatsuba": 7}
 
 
 def field_op(field: int, op: str, a, b=None, ctx: Context | None = None) -> np.ndarray:

@@ -34,6 +34,10 @@ static int run(int op, uint64_t *r, const uint64_t *a, const uint64_t *b, size_t
         z = F::template redc<2>(acc);
         break;
       }
+      case 7:  // Karatsuba product (fields with a multiple of 4 limbs; others fall back to mul)
+        if constexpr (F::N % 4 == 0) z = F::mul_karatsuba(x, y);
+        else z = F::mul(x, y);
+        break;
       default: return -1;
     }
     memcpy(r + i * (F::N / 2), z.v, F::BYTES);

@@ -40,6 +40,7 @@ def test_field_ops(field):
     assert (P.field_op(field, "from_mont", a) == O.field_op(field, "from_mont", a)).all()
     # full product + separate reduction, and double-width sums of 37 products reduced once
     assert (P.field_op(field, "mul_sos", a, b) == O.field_op(field, "mul", a, b)).all()
+    assert (P.field_op(field, "mul_karatsuba", a, b) == O.field_op(field, "mul", a, b)).all()
     m = 5000
     a2, b2 = a[:m].copy(), b[:m].copy()
     a2[100:164] = O.ints_to_elems([p - 1] * 64, field)   # runs of (p-1)^2 terms: worst case of the fold bound

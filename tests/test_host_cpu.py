@@ -152,6 +152,11 @@ def test_field_carry_chains_on_host_emulation(hostcheck, field):
     assert hostcheck.hostcheck_field_op(field, 5, r.ctypes.data_as(C.c_void_p), a.ctypes.data_as(C.c_void_p),
                                         b.ctypes.data_as(C.c_void_p), C.c_size_t(n)) == 0
     assert (r == O.field_op(field, "mul", a, b)).all()
+    # one-level subtractive Karatsuba product + reduction == the interleaved product
+    r = np.empty_like(a)
+    assert hostcheck.hostcheck_field_op(field, 7, r.ctypes.data_as(C.c_void_p), a.ctypes.data_as(C.c_void_p),
+                                        b.ctypes.data_as(C.c_void_p), C.c_size_t(n)) == 0
+    assert (r == O.field_op(field, "mul", a, b)).all()
     # 37-term sums of products accumulated double-width and reduced once == reduce-every-product
     m = 3000
     r = np.empty_like(a[:m])

@@ -1,0 +1,211 @@
+"""CPU tests of the host-side protocol layer: the Fiat-Shamir transcript, the column challenge, the oracle's
+prove/verify restatement and the bincode wire format.  Nothing here needs a GPU (no compute entry point of the C ABI
+is called); the GPU side of prove/verify is in tests/test_gpu_protocol.py.
+"""
+import hashlib
+import os
+import random
+
+import numpy as np
+import pytest
+
+import oracle as O
+import lcpc_b200 as P
+from oracle import protocol as PR
+from oracle import transcript as T
+
+# merlin's conformance vector (merlin/src/transcript.rs tests; the same constant is used by its Go/JS/C ports):
+#   Transcript::new(b"test protocol"); append_message(b"some label", b"some data"); challenge_bytes(b"challenge", 32)
+MERLIN_VECTOR = "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
+
+
+def test_keccak_permutation_matches_hashlib_sha3():
+    rng = random.Random(7)
+    for n in (0, 1, 55, 135, 136, 137, 167, 168, 169, 1000):
+        d = bytes(rng.getrandbits(8) for _ in range(n))
+        assert T.sponge(136, 0x06, d, 32) == hashlib.sha3_256(d).digest()
+        assert T.sponge(168, 0x1F, d, 400) == hashlib.shake_128(d).digest(400)
+
+
+def test_oracle_transcript_reproduces_merlin_vector():
+    t = T.Transcript(b"test protocol")
+    t.append_message(b"some label", b"some data")
+    assert t.challenge_bytes(b"challenge", 32).hex() == MERLIN_VECTOR
+
+
+def test_product_transcript_reproduces_merlin_vector():
+    t = P.Transcript(b"test protocol")
+    t.append_message(b"some label", b"some data")
+    assert t.challenge_bytes(b"challenge", 32).hex() == MERLIN_VECTOR
+
+
+def test_product_transcript_equals_oracle_on_random_operation_sequences():
+    rng = random.Random(11)
+    for trial in range(4):
+        label = bytes(rng.getrandbits(8) for _ in range(rng.randint(0, 20)))
+        a, b = P.Transcript(label), T.Transcript(label)
+        for _ in range(250):
+            lab = bytes(rng.getrandbits(8) for _ in range(rng.randint(0, 12)))
+            kind = rng.random()
+            if kind < 0.55:  # message sizes around the STROBE rate (166) exercise the mid-operation permutation
+                m = os.urandom(rng.choice([0, 1, 8, 31, 32, 160, 163, 164, 165, 166, 167, 332, 1000]))
+                a.append_message(lab, m)
+                b.append_message(lab, m)
+            elif kind < 0.7:
+                x = rng.getrandbits(64)
+                a.append_u64(lab, x)
+                b.append_u64(lab, x)
+            else:
+                n = rng.choice([0, 1, 32, 64, 165, 166, 167, 500])
+                assert a.challenge_bytes(lab, n) == b.challenge_bytes(lab, n)
+        assert a.challenge_bytes(b"end", 32) == b.challenge_bytes(b"end", 32)
+
+
+def test_transcript_clone_and_batched_reprs():
+    a = P.Transcript(b"x")
+    reprs = np.frombuffer(os.urandom(32 * 50), dtype=np.uint8).reshape(50, 32)
+    b = a.clone()
+    a.append_reprs(b"$l//PR", reprs)
+    for r in reprs:
+        b.append_message(b"$l//PR", r.tobytes())
+    assert a.challenge_bytes(b"c", 32) == b.challenge_bytes(b"c", 32)
+    c = a.clone()
+    assert a.challenge_bytes(b"d", 16) == c.challenge_bytes(b"d", 16)
+
+
+@pytest.mark.parametrize("n_cols", [1, 2, 3, 1000, 1024, 131072, 357699, (1 << 40) + 7, (1 << 63) + 1])
+def test_sample_columns_matches_oracle(n_cols):
+    """ChaCha20Rng::from_seed(key) + Uniform::new(0usize, n_cols): product C++ vs the oracle's restatement."""
+    for key in (bytes(32), bytes(range(32)), hashlib.sha256(b"k").digest()):
+        got = [int(v) for v in P.sample_columns(key, n_cols, 700)]
+        assert got == PR.sample_columns(key, n_cols, 700)
+        assert all(0 <= v < n_cols for v in got)
+
+
+def test_sample_columns_rejects_bad_arguments():
+    with pytest.raises(P.LcpcError):
+        P.sample_columns(bytes(31), 10, 5)
+    with pytest.raises(P.LcpcError):
+        P.sample_columns(bytes(32), 0, 5)
+
+
+# ------------------------------------------------------------------ oracle prove / verify (the checker itself)
+def _oracle_case(field, enc, length, seed):
+    x = O.random_elems(field, length, seed=seed)
+    c = enc.commit(x)
+    outer = O.random_elems(field, c["n_rows"], seed=seed + 1)
+    inner = O.random_elems(field, c["n_per_row"], seed=seed + 2)
+    proof = PR.prove(field, c, outer, enc.get_n_degree_tests(), enc.get_n_col_opens(), T.Transcript(b"test transcript"))
+    return c, outer, inner, proof
+
+
+@pytest.mark.parametrize("kind,field,length", [("ligero", O.FT255, 1 << 10), ("ligero", O.FT63, 3000),
+                                               ("sdig", O.FT127, 1 << 12)])
+def test_oracle_prove_verify_round_trip(kind, field, length):
+    """The reference's own end-to-end property (lcpc-2d/src/tests.rs `end_to_end`, `end_to_end_two_proofs`): a proof
+    verifies against the root and yields the evaluation <outer (x) inner, coeffs>."""
+    enc = O.Encoding.ligero(field, length) if kind == "ligero" else O.Encoding.sdig(field, length, seed=0)
+    c, outer, inner, proof = _oracle_case(field, enc, length, seed=3)
+    ev = PR.verify(field, enc, c["root"], outer, inner, proof, T.Transcript(b"test transcript"))
+    want = O.dot(field, inner, O.collapse(field, c["coeffs"], outer, c["n_rows"], c["n_per_row"]))
+    assert (ev == want).all()
+    # a different transcript label changes every challenge: the proof must not verify
+    with pytest.raises(PR.VerifierError):
+        PR.verify(field, enc, c["root"], outer, inner, proof, T.Transcript(b"another transcript"))
+
+
+def test_oracle_verify_rejects_tampering():
+    field, length = O.FT127, 1 << 11
+    enc = O.Encoding.ligero(field, length)
+    c, outer, inner, proof = _oracle_case(field, enc, length, seed=9)
+    one = O.to_mont(field, [1])[0]
+
+    def run(p, root=c["root"], o=outer, i=inner):
+        return PR.verify(field, enc, root, o, i, p, T.Transcript(b"test transcript"))
+
+    bad = dict(proof, columns=proof["columns"][:-1])
+    with pytest.raises(PR.VerifierError) as e:
+        run(bad)
+    assert e.value.kind == "NumColOpens"
+    with pytest.raises(PR.VerifierError) as e:
+        run(proof, i=inner[:-1])
+    assert e.value.kind == "InnerTensor"
+    with pytest.raises(PR.VerifierError) as e:
+        run(proof, o=np.concatenate([outer, outer[:1]]))
+    assert e.value.kind == "OuterTensor"
+    cols = [(col.copy(), path.copy()) for col, path in proof["columns"]]
+    cols[5][0][0] = O.field_op(field, "add", cols[5][0][:1], one[None, :])[0]
+    with pytest.raises(PR.VerifierError) as e:
+        run(dict(proof, columns=cols))
+    assert e.value.kind in ("ColumnDegree", "ColumnEval")
+    cols = [(col.copy(), path.copy()) for col, path in proof["columns"]]
+    cols[7][1][2, 3] ^= 1
+    with pytest.raises(PR.VerifierError) as e:
+        run(dict(proof, columns=cols))
+    assert e.value.kind == "ColumnPath"
+    with pytest.raises(PR.VerifierError) as e:
+        run(proof, root=bytes(32))
+    assert e.value.kind == "ColumnPath"
+
+
+# ------------------------------------------------------------------ wire format
+def _as_product_proof(field, proof):
+    cols = np.stack([c for c, _ in proof["columns"]])
+    paths = np.stack([p for _, p in proof["columns"]])
+    return P.LcEvalProof(field, proof["n_cols"], proof["p_eval"], np.stack(proof["p_random_vec"]), cols, paths)
+
+
+@pytest.mark.parametrize("kind,field,length", [("ligero", O.FT255, 1 << 10), ("sdig", O.FT127, 1 << 12),
+                                               ("ligero", O.FT191, 700), ("ligero", O.FT63, 2000)])
+def test_wire_proof_matches_oracle_writer_and_round_trips(kind, field, length):
+    enc = O.Encoding.ligero(field, length) if kind == "ligero" else O.Encoding.sdig(field, length, seed=0)
+    c, outer, inner, proof = _oracle_case(field, enc, length, seed=21)
+    pp = _as_product_proof(field, proof)
+    blob = P.serialize_proof(pp)
+    assert blob == PR.wire_proof(proof)
+    back = P.deserialize_proof(blob, field)
+    assert back.n_cols == pp.n_cols and (back.p_eval == pp.p_eval).all() and (back.p_random_vec == pp.p_random_vec).all()
+    assert (back.cols == pp.cols).all() and (back.paths == pp.paths).all()
+    assert P.serialize_proof(back) == blob
+    # size formula of the bincode layout: every Vec costs 8 bytes of length, every digest 8 + 32
+    L, ndt = O.FIELD_LIMBS[field], len(proof["p_random_vec"])
+    n_open, n_rows, plen = pp.cols.shape[0], pp.cols.shape[1], pp.paths.shape[1]
+    want = 8 + (8 + pp.p_eval.shape[0] * 8 * L) * (1 + ndt) + 8 + 8 + n_open * (8 + n_rows * 8 * L + 8 + plen * 40)
+    assert len(blob) == want
+
+
+def test_wire_root_and_commit_fields():
+    field, length = O.FT255, 1 << 10
+    enc = O.Encoding.ligero(field, length)
+    c = enc.commit(O.random_elems(field, length, seed=1))
+    assert P.serialize_root(P.LcRoot(c["root"])) == PR.wire_root(c["root"]) == (32).to_bytes(8, "little") + c["root"]
+    assert P.deserialize_root(PR.wire_root(c["root"])).root == c["root"]
+    blob = PR.wire_commit(c)
+
+    class HostCommit:  # the attributes serialize_commit reads from an LcCommit
+        comm, coeffs, hashes = c["comm"], c["coeffs"], c["hashes"]
+        n_rows, n_cols, n_per_row = c["n_rows"], c["n_cols"], c["n_per_row"]
+
+    assert P.serialize_commit(HostCommit) == blob
+    f = P.deserialize_commit_fields(blob, field)
+    assert (f["comm"] == c["comm"]).all() and (f["coeffs"] == c["coeffs"]).all() and (f["hashes"] == c["hashes"]).all()
+    assert (f["n_rows"], f["n_cols"], f["n_per_row"]) == (c["n_rows"], c["n_cols"], c["n_per_row"])
+
+
+def test_wire_rejects_malformed_input():
+    field = O.FT63
+    with pytest.raises(P.LcpcError):
+        P.deserialize_root(b"\x20" + bytes(7) + bytes(31))  # truncated digest
+    with pytest.raises(P.LcpcError):
+        P.deserialize_root((31).to_bytes(8, "little") + bytes(31))  # wrong digest length
+    with pytest.raises(P.LcpcError):
+        P.deserialize_root((32).to_bytes(8, "little") + bytes(33))  # trailing bytes
+    with pytest.raises(P.LcpcError):
+        P.deserialize_proof((1024).to_bytes(8, "little") + (1 << 60).to_bytes(8, "little"), field)  # absurd length
+    enc = O.Encoding.ligero(field, 512)
+    c = enc.commit(O.random_elems(field, 512, seed=1))
+    blob = bytearray(PR.wire_commit(c))
+    off = 8 + c["comm"].nbytes + 8 + c["coeffs"].nbytes
+    blob[off:off + 8] = (c["n_rows"] + 1).to_bytes(8, "little")  # n_rows inconsistent with comm.len()
+    with pytest.raises(P.LcpcError):
+        P.deserialize_commit_fields(bytes(blob), field)
