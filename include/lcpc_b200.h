@@ -15,6 +15,10 @@
  * There is NO CPU fallback: without a CUDA device every compute entry point fails with
  * LCPC_B200_ERR_CUDA.
  *
+ * Lifetimes: an encoding holds a reference on its context and a commit on its encoding, so lcpc_b200_ctx_destroy /
+ * lcpc_b200_enc_free / lcpc_b200_commit_free may be called in any order (the object is released when its last
+ * dependant is); a handle must not be USED after its own free call.
+ *
  * Threading: a context serialises its calls internally (one stream, one mutex); use one context per
  * host thread for concurrency.  `LcEncoding::encode` is called from many rayon workers in the
  * reference (lcpc-2d/src/lib.rs:648-653); the batched entry points here replace that loop.

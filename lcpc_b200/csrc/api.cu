@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -23,7 +24,11 @@
 using namespace lcpc;
 
 // ------------------------------------------------------------------------------------------------
+// Lifetimes: an encoding keeps its context alive and a commit keeps its encoding alive (reference counts), so the
+// three `*_destroy` / `*_free` calls may come in any order -- a garbage-collected host (the Python layer here, a
+// Drop order a Rust shim does not control) cannot turn the order of finalisers into a use-after-free.
 struct lcpc_b200_ctx {
+  std::atomic<int> refs{1};
   int device = 0;
   cudaStream_t stream = nullptr;
   // host->device staging stream + events: commit() from host memory copies the coefficient rows in
@@ -146,6 +151,7 @@ static void host_root(int field, unsigned log_len, uint32_t *w, uint32_t *one) {
 
 // ------------------------------------------------------------------------------------------------
 struct lcpc_b200_enc {
+  std::atomic<int> refs{1};
   lcpc_b200_ctx *ctx = nullptr;
   int kind = 0, field = 0;
   size_t n_per_row = 0, n_cols = 0;
@@ -209,8 +215,8 @@ int lcpc_b200_ctx_create(int device, lcpc_b200_ctx **out) {
   return LCPC_B200_OK;
 }
 
-void lcpc_b200_ctx_destroy(lcpc_b200_ctx *ctx) {
-  if (!ctx) return;
+static void ctx_unref(lcpc_b200_ctx *ctx) {
+  if (ctx->refs.fetch_sub(1) != 1) return;  // encodings of this context are still alive
   cudaSetDevice(ctx->device);
   if (ctx->stream) {
     cudaStreamSynchronize(ctx->stream);
@@ -234,6 +240,10 @@ void lcpc_b200_ctx_destroy(lcpc_b200_ctx *ctx) {
   if (ctx->lane_join) cudaEventDestroy(ctx->lane_join);
   if (ctx->scratch) cudaFree(ctx->scratch);
   delete ctx;
+}
+
+void lcpc_b200_ctx_destroy(lcpc_b200_ctx *ctx) {
+  if (ctx) ctx_unref(ctx);
 }
 
 const char *lcpc_b200_last_error(const lcpc_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -304,6 +314,7 @@ int lcpc_b200_ligero_new(lcpc_b200_ctx *ctx, int field, size_t n_per_row, size_t
     return cuda_fail(ctx, ce, "ligero_new");
   }
   ctx->launches += half ? 1 : 0;
+  ctx->refs.fetch_add(1);
   *out = e;
   return LCPC_B200_OK;
 }
@@ -333,18 +344,27 @@ int lcpc_b200_sdig_new(lcpc_b200_ctx *ctx, int field, size_t n_levels, const lcp
   e->ctx = ctx, e->kind = LCPC_B200_ENC_SDIG, e->field = field;
   e->n_per_row = expander_n_in(code), e->n_cols = expander_codeword_length(code);
   e->code = code;
+  ctx->refs.fetch_add(1);
   *out = e;
   return LCPC_B200_OK;
 }
 
+static void enc_unref(lcpc_b200_enc *enc) {
+  if (enc->refs.fetch_sub(1) != 1) return;  // commits made with this encoding are still alive
+  lcpc_b200_ctx *ctx = enc->ctx;
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (enc->d_roots) cudaFree(enc->d_roots);
+    if (enc->code) expander_free(enc->code);
+    delete enc;
+  }
+  ctx_unref(ctx);
+}
+
 void lcpc_b200_enc_free(lcpc_b200_enc *enc) {
-  if (!enc) return;
-  std::lock_guard<std::mutex> g(enc->ctx->mu);
-  cudaSetDevice(enc->ctx->device);
-  cudaStreamSynchronize(enc->ctx->stream);
-  if (enc->d_roots) cudaFree(enc->d_roots);
-  if (enc->code) expander_free(enc->code);
-  delete enc;
+  if (enc) enc_unref(enc);
 }
 
 int lcpc_b200_enc_kind(const lcpc_b200_enc *enc) { return enc ? enc->kind : LCPC_B200_ERR_BAD_ARG; }
@@ -616,6 +636,7 @@ static int commit_alloc(lcpc_b200_enc *enc, size_t len, lcpc_b200_commit **out) 
     commit_release(c);
     return cuda_fail(ctx, ce, "commit: cudaMalloc");
   }
+  enc->refs.fetch_add(1);
   *out = c;
   return LCPC_B200_OK;
 }
@@ -742,6 +763,7 @@ static int commit_new_impl(lcpc_b200_enc *enc, const void *src, size_t len, cuda
   }
   if (rc != LCPC_B200_OK) {
     commit_release(c);
+    enc->refs.fetch_sub(1);  // the caller's own reference keeps enc alive
     return rc;
   }
   *out = c;
@@ -774,11 +796,15 @@ int lcpc_b200_commit_rerun(lcpc_b200_commit *c, const uint64_t *coeffs_in, size_
 
 void lcpc_b200_commit_free(lcpc_b200_commit *c) {
   if (!c) return;
-  lcpc_b200_ctx *ctx = c->enc->ctx;
-  std::lock_guard<std::mutex> g(ctx->mu);
-  cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
-  commit_release(c);
+  lcpc_b200_enc *enc = c->enc;
+  {
+    lcpc_b200_ctx *ctx = enc->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    commit_release(c);
+  }
+  enc_unref(enc);
 }
 
 int lcpc_b200_commit_dims(const lcpc_b200_commit *c, size_t *n_rows, size_t *n_per_row, size_t *n_cols, size_t *n_hashes) {

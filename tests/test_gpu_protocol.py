@@ -167,3 +167,21 @@ def test_wire_commit_from_device_resident_commit():
     again = P.LcCommit.commit(f["coeffs"][:length], enc)  # a device-resident commit is rebuilt from its coefficients
     assert again.get_root().root == oc["root"] and (again.hashes == f["hashes"]).all()
     assert P.serialize_root(c.get_root()) == PR.wire_root(oc["root"])
+
+
+def test_handles_may_be_freed_in_any_order():
+    """An encoding outlives its Python wrapper while commits made with it are alive (reference counts in the C
+    ABI): finalisers of a garbage-collected cycle run in arbitrary order."""
+    ctx = P.Context(0)
+    field, length = P.FT63, 1 << 10
+    enc = P.LigeroEncoding(field, length, ctx=ctx)
+    oenc = O.Encoding.ligero(field, length)
+    x = O.random_elems(field, length, seed=8)
+    c = P.LcCommit.commit(x, enc)
+    want = oenc.commit(x)
+    enc.close()   # encoding handle released first ...
+    ctx.close()   # ... and the context too
+    assert c.get_root().root == want["root"]          # the commit still works
+    t = O.random_elems(field, c.n_rows, seed=9)
+    assert (c.collapse(t) == O.collapse(field, want["coeffs"], t, c.n_rows, c.n_per_row)).all()
+    c.close()
