@@ -65,6 +65,8 @@ typedef struct lcpc_b200_commit lcpc_b200_commit; /* device-resident LcCommit (l
 const char *lcpc_b200_version(void);
 /* number of u64 limbs of a field (1,2,3,4) or -1 */
 int lcpc_b200_field_limbs(int field);
+/* Field::one() as stored: R mod p, L u64 limbs (ff_derive's R constant); host-only, no device needed */
+int lcpc_b200_field_one(int field, uint64_t *out);
 int lcpc_b200_ctx_create(int device, lcpc_b200_ctx **out);
 void lcpc_b200_ctx_destroy(lcpc_b200_ctx *ctx);
 const char *lcpc_b200_last_error(const lcpc_b200_ctx *ctx);

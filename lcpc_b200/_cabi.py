@@ -62,6 +62,7 @@ _pvp, _psz = C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)
 SIGNATURES = {
     "lcpc_b200_version": (C.c_char_p, []),
     "lcpc_b200_field_limbs": (_i, [_i]),
+    "lcpc_b200_field_one": (_i, [_i, _vp]),
     "lcpc_b200_ctx_create": (_i, [_i, _pvp]),
     "lcpc_b200_ctx_destroy": (None, [_vp]),
     "lcpc_b200_last_error": (C.c_char_p, [_vp]),

@@ -188,6 +188,15 @@ int lcpc_b200_field_limbs(int field) {
   return n < 0 ? -1 : n / 2;
 }
 
+int lcpc_b200_field_one(int field, uint64_t *out) {
+  FieldHostInfo fi;
+  if (!out || !field_host_info(field, &fi)) return LCPC_B200_ERR_BAD_ARG;
+  uint32_t w[8], one[8];
+  host_root(field, 1, w, one);
+  memcpy(out, one, field_bytes(field));
+  return LCPC_B200_OK;
+}
+
 int lcpc_b200_ctx_create(int device, lcpc_b200_ctx **out) {
   if (!out) return LCPC_B200_ERR_BAD_ARG;
   *out = nullptr;

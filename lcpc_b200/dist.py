@@ -126,6 +126,26 @@ class CudaOps:
     def merkle_layers(self, nodes, n_leaves, n_layers):
         _check(_cabi.lib().lcpc_b200_merkle_layers_dev(self.ctx._h, C.c_void_p(nodes.data_ptr()), _sz(n_leaves), n_layers), self.ctx)
 
+    # ---- prove side ----
+    def collapse_rows(self, coeffs, row_stride, tensor, poly, n_rows, n_per_row):
+        """poly[c] = sum_r tensor[r] * coeffs[r][c] over device tensors (collapse_columns, lcpc-2d/src/lib.rs:1095-1123)."""
+        _check(_cabi.lib().lcpc_b200_collapse_dev(self.ctx._h, self.field, C.c_void_p(coeffs.data_ptr()), _sz(row_stride),
+                                                  C.c_void_p(tensor.data_ptr()), C.c_void_p(poly.data_ptr()), _sz(n_rows),
+                                                  _sz(n_per_row)), self.ctx)
+
+    def expand_tensor(self, key: bytes, n: int) -> np.ndarray:
+        from .host import expand_tensor
+        return expand_tensor(self.field, key, n, ctx=self.ctx)
+
+    def to_repr(self, elems: np.ndarray) -> np.ndarray:
+        """Canonical little-endian bytes of Montgomery-form elements (to_repr): (n, L) u64 -> (n, 8L) u8."""
+        from .host import field_op
+        return field_op(self.field, "from_mont", elems, ctx=self.ctx).view(np.uint8).reshape(elems.shape[0], -1)
+
+    def one(self) -> np.ndarray:
+        from .host import field_one
+        return field_one(self.field)
+
 
 class DistributedCommit:
     """Device-resident, column-sharded LcCommit over a torch.distributed process group.
@@ -316,6 +336,94 @@ class DistributedCommit:
         self.ops.synchronize()
         return LcRoot(root.numpy().tobytes())
 
+    # ---- prove() over the sharded commit (row-sharded coeffs, column-sharded comm) ----
+    def collapse(self, tensor) -> np.ndarray:
+        """collapse_columns (lcpc-2d/src/lib.rs:1095-1123) with the coefficient rows sharded by row block: every rank
+        combines its own rows with its slice of `tensor`, the partial vectors are all-gathered (world x n_per_row
+        elements) and summed on the device.  Every rank returns the same (n_per_row, L) array."""
+        torch, dist, p, ops, L = self.torch, self.dist, self.plan, self.ops, self.L
+        dev = ops.device
+        t = np.ascontiguousarray(tensor, dtype=np.uint64).reshape(-1, L)
+        if t.shape[0] != p.n_rows:
+            raise _cabi.LcpcError(_cabi.ERR_OUTER_TENSOR, "tensor length != n_rows")
+        if not hasattr(self, "d_part"):
+            i64 = torch.int64
+            self.d_part = torch.zeros(p.n_per_row * L, dtype=i64, device=dev)
+            self.d_all_parts = torch.zeros(self.world * p.n_per_row * L, dtype=i64, device=dev)
+            self.d_poly = torch.zeros(p.n_per_row * L, dtype=i64, device=dev)
+            self.d_tensor = torch.zeros(p.n_rows * L, dtype=i64, device=dev)
+            ones = np.tile(ops.one().reshape(1, L), (self.world, 1))
+            self.d_ones = torch.from_numpy(ones.view(np.int64).reshape(-1).copy()).to(dev)
+            if dev.type == "cuda":
+                torch.cuda.synchronize(dev)  # filled on torch's stream, read on the engine stream
+        r0, r1 = p.rows(self.rank)
+        with ops.on_stream():
+            self.d_tensor.copy_(torch.from_numpy(t.view(np.int64).reshape(-1)))
+            if self.my_rows:
+                ops.collapse_rows(self.d_coeffs, p.n_per_row, self.d_tensor[r0 * L:r1 * L], self.d_part, self.my_rows,
+                                  p.n_per_row)
+            else:
+                self.d_part.zero_()  # the zero element is all-zero limbs
+            dist.all_gather_into_tensor(self.d_all_parts, self.d_part, group=self.group)
+            ops.collapse_rows(self.d_all_parts, p.n_per_row, self.d_ones, self.d_poly, self.world, p.n_per_row)
+            out = self.d_poly.cpu()
+        ops.synchronize()
+        return out.numpy().view(np.uint64).reshape(p.n_per_row, L).copy()
+
+    def open_columns(self, cols):
+        """open_column (lcpc-2d/src/lib.rs:788-825) for every index in `cols` over the column-sharded commit: the
+        owner of a column gathers its values and the siblings inside its own subtrees, the siblings above come from
+        the top tree; one all-reduce over disjoint supports hands every rank all openings.  Pure data movement."""
+        torch, dist, p, L = self.torch, self.dist, self.plan, self.L
+        dev = self.ops.device
+        cols = np.ascontiguousarray(cols, dtype=np.uint64).astype(np.int64)
+        if cols.size and (cols.min() < 0 or cols.max() >= p.n_cols):
+            raise _cabi.LcpcError(_cabi.ERR_COLUMN, "bad column number")  # ProverError::ColumnNumber (:797-799)
+        n, path_len = cols.shape[0], (p.np2 - 1).bit_length()
+        c0, c1 = p.cols(self.rank)
+        with self.ops.on_stream():
+            vals = torch.zeros((n, p.n_rows, L), dtype=torch.int64, device=dev)
+            paths = torch.zeros((n, path_len, 32), dtype=torch.uint8, device=dev)
+            mine = np.nonzero((cols >= c0) & (cols < c1))[0]
+            if mine.size:
+                where = torch.from_numpy(mine).to(dev)
+                local = torch.from_numpy(cols[mine] - c0).to(dev)
+                recv = self.d_recv[:p.n_rows * self.my_cols * L].view(p.n_rows, self.my_cols, L)
+                vals[where] = recv[:, local, :].permute(1, 0, 2)
+                forest, off, ln = self.d_forest.view(-1, 32), 0, self.my_subs * p.sub_leaves
+                for l in range(self.sub_layers):  # siblings inside this rank's aligned subtrees
+                    paths[where, l] = forest[off + ((local >> l) ^ 1)]
+                    off, ln = off + ln, ln >> 1
+                top, off, ln = self.d_top.view(-1, 32), 0, p.n_sub
+                sub = torch.from_numpy(cols[mine] // p.sub_leaves).to(dev)
+                for t in range(p.n_sub.bit_length() - 1):  # siblings in the tree over the subtree roots
+                    paths[where, self.sub_layers + t] = top[off + ((sub >> t) ^ 1)]
+                    off, ln = off + ln, ln >> 1
+            dist.all_reduce(vals, group=self.group)
+            dist.all_reduce(paths, group=self.group)
+            vals_h, paths_h = vals.cpu(), paths.cpu()
+        self.ops.synchronize()
+        return vals_h.numpy().view(np.uint64), paths_h.numpy()
+
+    def prove(self, outer_tensor, tr):
+        """LcCommit::prove (lcpc-2d/src/lib.rs:1004-1093) on the sharded commit; every rank drives an identical
+        transcript `tr` (lcpc_b200.Transcript) and returns the same LcEvalProof."""
+        from .proof import LcEvalProof, sample_columns
+        enc, p, ops = self.enc, self.plan, self.ops
+        p_random = []
+        for _ in range(enc.get_n_degree_tests()):
+            key = tr.challenge_bytes(enc.LABEL_DT, 32)
+            pr = self.collapse(ops.expand_tensor(key, p.n_rows))
+            tr.append_reprs(enc.LABEL_PR, ops.to_repr(pr))
+            p_random.append(pr)
+        p_eval = self.collapse(outer_tensor)
+        tr.append_reprs(enc.LABEL_PE, ops.to_repr(p_eval))
+        key = tr.challenge_bytes(enc.LABEL_CO, 32)
+        cols = sample_columns(key, p.n_cols, enc.get_n_col_opens())
+        vals, paths = self.open_columns(cols)
+        p_rand = np.stack(p_random) if p_random else np.empty((0, p.n_per_row, self.L), np.uint64)
+        return LcEvalProof(self.field, p.n_cols, p_eval, p_rand, vals, paths, col_idx=cols)
+
     # ---- inspection helpers (tests) ----
     def local_columns(self) -> np.ndarray:
         """This rank's column block of comm as (n_rows, my_cols, L)."""
@@ -416,7 +524,27 @@ def bench_distributed(args, ctx, enc, field, n, synthetic_coeffs):
             single.close()
             assert root_check != "MISMATCH", "distributed LcRoot differs from the single-GPU commit"
         dist.barrier()
-    return dict(value=n / (ms_per_step * 1e-3), root_check=root_check, ms_per_step=ms_per_step, gpu_launches=int(launches.item()), clocks=clocks,
+    # prove() over the sharded commit (config 4 of BASELINE.json is commit + prove): wall clock, max over ranks;
+    # rank 0 then verifies the proof on its own GPU against the sharded commit's root
+    from .proof import Transcript
+    outer = synthetic_coeffs(field, p.n_rows, seed=7)
+    dc.prove(outer, Transcript(b"bench"))
+    dist.barrier()
+    t0 = time.perf_counter()
+    proof = dc.prove(outer, Transcript(b"bench"))
+    t_prove = torch.tensor([time.perf_counter() - t0], device="cuda")
+    dist.all_reduce(t_prove, op=dist.ReduceOp.MAX)
+    prove = {"prove_ms": float(t_prove.item()) * 1e3, "n_degree_tests": int(proof.p_random_vec.shape[0]),
+             "n_col_opens": int(proof.cols.shape[0]),
+             "note": "LcCommit::prove over row-sharded coefficients and column-sharded comm: per-rank partial row "
+                     "combinations all-gathered and summed on the device, openings gathered from the column owners"}
+    if rank == 0:
+        inner = synthetic_coeffs(field, p.n_per_row, seed=8)
+        t0 = time.perf_counter()
+        proof.verify(root0, outer, inner, enc, Transcript(b"bench"))
+        prove["verify_ms_rank0"] = (time.perf_counter() - t0) * 1e3
+    dist.barrier()
+    return dict(value=n / (ms_per_step * 1e-3), root_check=root_check, prove=prove, ms_per_step=ms_per_step, gpu_launches=int(launches.item()), clocks=clocks,
                 root=root0.root.hex(), transport=dc.transport,
                 phases_ms={"encode_and_scatter": float(ph[0]), "exchange_wait": float(ph[1]), "hash_merkle_root": float(ph[2])},
                 dominant=_dominant_multi(enc, field, p, dc, float(ph[0])),

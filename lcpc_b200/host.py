@@ -461,6 +461,13 @@ def expand_tensor(field: int, key: bytes, n: int, ctx: Context | None = None) ->
     return out
 
 
+def field_one(field: int) -> np.ndarray:
+    """Field::one() in its stored (Montgomery) form: R mod p as L limbs.  Host-only."""
+    out = np.empty(FIELD_LIMBS[field], np.uint64)
+    _check(_cabi.lib().lcpc_b200_field_one(field, _ptr(out)))
+    return out
+
+
 _OPS = {"add": 0, "sub": 1, "mul": 2, "from_mont": 4, "mul_sos": 5, "lazy_sum37": 6, "mul_karatsuba": 7}
 
 

@@ -27,8 +27,16 @@ class OracleEnc:
     def __init__(self, oenc):
         self.o, self.field, self.L = oenc, oenc.field, oenc.L
 
+    LABEL_DT, LABEL_PR, LABEL_PE, LABEL_CO = b"$l//DT", b"$l//PR", b"$l//PE", b"$l//CO"
+
     def get_dims(self, n):
         return self.o.get_dims(n)
+
+    def get_n_degree_tests(self):
+        return self.o.get_n_degree_tests()
+
+    def get_n_col_opens(self):
+        return self.o.get_n_col_opens()
 
 
 class OracleOps:
@@ -79,6 +87,23 @@ class OracleOps:
             off, ln = off + ln, ln // 2
 
 
+    # ---- prove side ----
+    def collapse_rows(self, coeffs, row_stride, tensor, poly, n_rows, n_per_row):
+        c = self._u64(coeffs)[:n_rows * row_stride * self.L].reshape(n_rows, row_stride, self.L)[:, :n_per_row]
+        t = self._u64(tensor)[:n_rows * self.L].reshape(n_rows, self.L)
+        out = O.collapse(self.field, np.ascontiguousarray(c).reshape(-1, self.L), t, n_rows, n_per_row)
+        self._u64(poly)[:n_per_row * self.L] = out.reshape(-1)
+
+    def expand_tensor(self, key, n):
+        return O.random_elems_from_key(self.field, key, n)
+
+    def to_repr(self, elems):
+        return O.to_repr(self.field, elems)
+
+    def one(self):
+        return O.to_mont(self.field, [1])[0]
+
+
 def main():
     backend, kind, field, n, seed = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
     transport = sys.argv[6] if len(sys.argv) > 6 else None
@@ -116,8 +141,26 @@ def main():
     else:
         dc.run()  # a second run into the same buffers must reproduce the root
     again = dc.get_root().root
+    # prove() over the sharded commit == the oracle's single-process prove, on every rank
+    import lcpc_b200 as P
+    from oracle import protocol as PR
+    from oracle.transcript import Transcript as OTranscript
+    outer = O.random_elems(field, p.n_rows, seed=seed + 200)
+    proof = dc.prove(outer, P.Transcript(b"dist"))
+    oproof = PR.prove(field, oc, outer, oenc.get_n_degree_tests(), oenc.get_n_col_opens(), OTranscript(b"dist"))
+    ok_prove = bool((proof.p_eval == oproof["p_eval"]).all()) and len(oproof["p_random_vec"]) == proof.p_random_vec.shape[0]
+    ok_prove = ok_prove and all(bool((a == b).all()) for a, b in zip(proof.p_random_vec, oproof["p_random_vec"]))
+    ok_prove = ok_prove and [int(v) for v in proof.col_idx] == oproof["cols_to_open"]
+    ok_prove = ok_prove and all(bool((proof.cols[j] == col).all()) and bool((proof.paths[j] == path).all())
+                                for j, (col, path) in enumerate(oproof["columns"]))
+    ok_verify = True
+    if backend == "nccl":  # the verifier is one party: every rank checks the sharded proof on its own GPU
+        inner = O.random_elems(field, p.n_per_row, seed=seed + 300)
+        ev = proof.verify(root, outer, inner, enc, P.Transcript(b"dist"))
+        ok_verify = bool((ev == O.dot(field, inner, oproof["p_eval"])).all())
     print(json.dumps(dict(rank=rank, root=root.hex(), want=oc["root"].hex(), ok_cols=ok_cols, ok_leaves=ok_leaves,
-                          again=again.hex(), rows=[r0, r1], cols=[c0, c1], transport=dc.transport)), flush=True)
+                          again=again.hex(), rows=[r0, r1], cols=[c0, c1], transport=dc.transport,
+                          ok_prove=ok_prove, ok_verify=ok_verify)), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -51,6 +51,7 @@ def check(lines):
     for d in lines:
         assert d["root"] == d["want"] == d["again"], d
         assert d["ok_cols"] and d["ok_leaves"], d
+        assert d["ok_prove"] and d["ok_verify"], d  # prove() over the sharded commit == the oracle's proof
 
 
 @pytest.mark.parametrize("shape", [(256, 65536, 131072, 8), (72, 235173, 357699, 8), (72, 235173, 357699, 4),
