@@ -209,3 +209,63 @@ def test_wire_rejects_malformed_input():
     blob[off:off + 8] = (c["n_rows"] + 1).to_bytes(8, "little")  # n_rows inconsistent with comm.len()
     with pytest.raises(P.LcpcError):
         P.deserialize_commit_fields(bytes(blob), field)
+
+
+# ------------------------------------------------------------------ pins against the real reference's output
+def _reference_sizes():
+    import json
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_proof_sizes.json")))
+
+
+def _proof_shape(kind, field, lgl, rho=None, code=None):
+    """(n_rows, n_per_row, n_cols, n_col_opens, n_degree_tests) from the PRODUCT's host-side setup functions."""
+    import ctypes as C
+    from lcpc_b200 import _cabi, host
+    lib, n = _cabi.lib(), 1 << lgl
+    if kind == "ligero":
+        n_rows, n_per_row, n_cols = host.ligero_get_dims(field, n, tuple(rho))
+        n_open = lib.lcpc_b200_ligero_n_col_opens(rho[0], rho[1])
+    else:
+        npr = C.c_size_t()
+        assert lib.lcpc_b200_sdig_choose_n_per_row(field, code, n, C.byref(npr)) == 0
+        n_per_row = npr.value
+        pre, post = O.sdig_level_dims(field, code, n_per_row)  # level shapes only; codeword_length, encode.rs:18-33
+        n_cols = pre[0][0] + post[-1][0] + sum(p[1] for p in pre[:-1]) + sum(p[1] for p in post)
+        n_rows = (n + n_per_row - 1) // n_per_row
+        n_open = lib.lcpc_b200_sdig_n_col_opens(code)
+    ndt = host.n_degree_tests(128, n_cols, lib.lcpc_b200_field_flog2(field))
+    return n_rows, n_per_row, n_cols, n_open, ndt
+
+
+@pytest.mark.parametrize("name", ["ligero_rho_1_4", "ligero_rho_1_2", "sdig_code3"])
+def test_proof_sizes_equal_the_reference_runs(name):
+    """The reference's own benchmark logs hold `bincode::serialize(&pf).len()` for Ft255 proofs at 2^13 .. 2^29
+    coefficients.  Our dimension choosers, n_col_opens / n_degree_tests and the bincode layout together must give
+    exactly those byte counts -- a pin against real Rust output (not against our restatement)."""
+    g = _reference_sizes()
+    case, field = g[name], P.FT255
+    for lgl, want in zip(g["lgl"], case["proof_bytes"]):
+        kind = "ligero" if "rho" in case else "sdig"
+        n_rows, n_per_row, n_cols, n_open, ndt = _proof_shape(kind, field, lgl, case.get("rho"), case.get("code"))
+        path_len = (n_cols - 1).bit_length()
+        size = 8 + (8 + n_per_row * 32) + 8 + ndt * (8 + n_per_row * 32) + 8 + n_open * (8 + n_rows * 32 + 8 + path_len * 40)
+        assert size == want, (name, lgl, size, want)
+        if lgl <= 15:  # and the serializer itself, on a proof of that shape
+            pf = P.LcEvalProof(field, n_cols, np.zeros((n_per_row, 4), np.uint64), np.zeros((ndt, n_per_row, 4), np.uint64),
+                               np.zeros((n_open, n_rows, 4), np.uint64), np.zeros((n_open, path_len, 32), np.uint8))
+            assert len(P.serialize_proof(pf)) == want
+
+
+def test_oracle_dims_agree_with_the_reference_runs():
+    """Same pin for the ORACLE's dimension functions (they feed every parity test)."""
+    g = _reference_sizes()
+    for lgl, want in zip(g["lgl"][:4], g["ligero_rho_1_2"]["proof_bytes"][:4]):
+        enc = O.Encoding.ligero(P.FT255, 1 << lgl)
+        n_rows, n_per_row, n_cols = enc.get_dims(1 << lgl)
+        n_open, ndt, path_len = enc.get_n_col_opens(), enc.get_n_degree_tests(), (n_cols - 1).bit_length()
+        assert 8 + (8 + n_per_row * 32) * (1 + ndt) + 16 + n_open * (16 + n_rows * 32 + path_len * 40) == want
+    for lgl, want in zip(g["lgl"][:3], g["sdig_code3"]["proof_bytes"][:3]):
+        enc = O.Encoding.sdig(P.FT255, 1 << lgl, seed=0)
+        n_rows, n_per_row, n_cols = enc.get_dims(1 << lgl)
+        n_open, ndt, path_len = enc.get_n_col_opens(), enc.get_n_degree_tests(), (n_cols - 1).bit_length()
+        assert 8 + (8 + n_per_row * 32) * (1 + ndt) + 16 + n_open * (16 + n_rows * 32 + path_len * 40) == want
