@@ -161,6 +161,12 @@ int lcpc_b200_commit_new_dev(lcpc_b200_enc *enc, const uint64_t *d_coeffs_in, si
 /* re-run the commit into an existing object of the same shape (no allocation; for timing loops) */
 int lcpc_b200_commit_rerun_dev(lcpc_b200_commit *c, const uint64_t *d_coeffs_in, size_t len);
 int lcpc_b200_commit_rerun(lcpc_b200_commit *c, const uint64_t *coeffs_in, size_t len);
+/* Deserialize for LcCommit (:256-268): a device-resident commit from the fields of one made elsewhere (host arrays:
+ * comm_len = n_rows*n_cols elements, coeffs_len = n_rows*n_per_row, n_hashes = 2*np2-1 digests).  Nothing is recomputed;
+ * sizes are checked like check_comm (:672-688), ERR_BAD_ARG standing for ProverError::Commit. */
+int lcpc_b200_commit_from_host(lcpc_b200_enc *enc, const uint64_t *comm, size_t comm_len, const uint64_t *coeffs,
+                               size_t coeffs_len, const uint8_t *hashes, size_t n_hashes, size_t n_rows,
+                               lcpc_b200_commit **out);
 void lcpc_b200_commit_free(lcpc_b200_commit *c);
 /* n_hashes = 2 * next_power_of_two(n_cols) - 1 (:656-666) */
 int lcpc_b200_commit_dims(const lcpc_b200_commit *c, size_t *n_rows, size_t *n_per_row, size_t *n_cols,

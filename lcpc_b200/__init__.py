@@ -29,10 +29,10 @@ from .host import (FT63, FT127, FT191, FT255, FIELD_LIMBS, Context, LcCommit, Lc
                    ligero_get_dims, n_degree_tests, expand_tensor)
 from ._cabi import LcpcError, LIB_PATH  # noqa: F401
 from .proof import (LcEvalProof, Transcript, prove, sample_columns, serialize_root, serialize_commit,  # noqa: F401
-                    serialize_proof, deserialize_root, deserialize_commit_fields, deserialize_proof)
+                    serialize_proof, deserialize_root, deserialize_commit_fields, deserialize_commit, deserialize_proof)
 
 __all__ = ["FT63", "FT127", "FT191", "FT255", "FIELD_LIMBS", "Context", "LcCommit", "LcEncoding", "LcRoot",
            "LigeroEncoding", "SdigEncoding", "LcpcError", "default_context", "field_op", "merkleize",
            "collapse_columns", "ligero_get_dims", "n_degree_tests", "expand_tensor", "LcEvalProof", "Transcript", "prove",
            "sample_columns", "serialize_root", "serialize_commit", "serialize_proof", "deserialize_root",
-           "deserialize_commit_fields", "deserialize_proof"]
+           "deserialize_commit_fields", "deserialize_commit", "deserialize_proof"]

@@ -87,6 +87,7 @@ SIGNATURES = {
     "lcpc_b200_commit_new_dev": (_i, [_vp, _vp, _sz, _pvp]),
     "lcpc_b200_commit_rerun_dev": (_i, [_vp, _vp, _sz]),
     "lcpc_b200_commit_rerun": (_i, [_vp, _vp, _sz]),
+    "lcpc_b200_commit_from_host": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _sz, _pvp]),
     "lcpc_b200_commit_free": (None, [_vp]),
     "lcpc_b200_commit_dims": (_i, [_vp, _psz, _psz, _psz, _psz]),
     "lcpc_b200_commit_root": (_i, [_vp, _vp]),

@@ -803,6 +803,38 @@ int lcpc_b200_commit_rerun(lcpc_b200_commit *c, const uint64_t *coeffs_in, size_
   return commit_rerun_impl(c, coeffs_in, len, cudaMemcpyHostToDevice, true);
 }
 
+// Deserialize for LcCommit (lcpc-2d/src/lib.rs:256-268) onto the device: the fields of a commitment that was made
+// elsewhere (or earlier) become a device-resident commit that prove() can use.  Nothing is recomputed -- like the
+// reference, which trusts the deserialized fields and only checks their consistency in prove() (check_comm, :672-688).
+int lcpc_b200_commit_from_host(lcpc_b200_enc *enc, const uint64_t *comm, size_t comm_len, const uint64_t *coeffs,
+                               size_t coeffs_len, const uint8_t *hashes, size_t n_hashes, size_t n_rows,
+                               lcpc_b200_commit **out) {
+  if (!enc || !out || !comm || !coeffs || !hashes) return LCPC_B200_ERR_BAD_ARG;
+  *out = nullptr;
+  lcpc_b200_ctx *ctx = enc->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  const size_t n_per_row = enc->n_per_row, n_cols = enc->n_cols;
+  // check_comm: comm.len() == n_rows * n_cols, coeffs.len() == n_rows * n_per_row, hashes.len() == 2 * np2 - 1
+  if (n_rows == 0 || comm_len != n_rows * n_cols || coeffs_len != n_rows * n_per_row ||
+      n_hashes != 2 * ((size_t)1 << log2_ceil(n_cols)) - 1)
+    return fail(ctx, LCPC_B200_ERR_BAD_ARG, "inconsistent commitment fields");  // ProverError::Commit
+  if (int rc = bind_device(ctx)) return rc;
+  lcpc_b200_commit *c = nullptr;
+  if (int rc = commit_alloc(enc, (n_rows - 1) * n_per_row + 1, &c)) return rc;  // any length with this row count
+  const size_t B = field_bytes(enc->field);
+  cudaError_t ce = cudaMemcpyAsync(c->d_comm, comm, comm_len * B, cudaMemcpyHostToDevice, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(c->d_coeffs, coeffs, coeffs_len * B, cudaMemcpyHostToDevice, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(c->d_hashes, hashes, n_hashes * 32, cudaMemcpyHostToDevice, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+  if (ce != cudaSuccess) {
+    commit_release(c);
+    enc->refs.fetch_sub(1);
+    return cuda_fail(ctx, ce, "commit_from_host");
+  }
+  *out = c;
+  return LCPC_B200_OK;
+}
+
 void lcpc_b200_commit_free(lcpc_b200_commit *c) {
   if (!c) return;
   lcpc_b200_enc *enc = c->enc;

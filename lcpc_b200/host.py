@@ -314,6 +314,17 @@ class LcCommit:
         _check(_cabi.lib().lcpc_b200_commit_new_dev(enc._h, C.c_void_p(d_ptr), length, C.byref(h)), enc.ctx)
         return cls(enc, h)
 
+    @classmethod
+    def from_fields(cls, enc: LcEncoding, comm, coeffs, hashes, n_rows: int) -> "LcCommit":
+        """``Deserialize for LcCommit`` (:256-268): a device-resident commit from host-side fields (e.g. the output of
+        ``deserialize_commit_fields``); sizes are checked like ``check_comm`` (:672-688), nothing is recomputed."""
+        a, k = _elems(comm, enc.field), _elems(coeffs, enc.field)
+        hs = np.ascontiguousarray(hashes, dtype=np.uint8).reshape(-1, 32)
+        h = C.c_void_p()
+        _check(_cabi.lib().lcpc_b200_commit_from_host(enc._h, _ptr(a), a.shape[0], _ptr(k), k.shape[0], _ptr(hs),
+                                                      hs.shape[0], int(n_rows), C.byref(h)), enc.ctx)
+        return cls(enc, h)
+
     def rerun_device(self, d_ptr: int, length: int):
         """Enqueue the commit again into this object's buffers (no allocation, no sync)."""
         _check(_cabi.lib().lcpc_b200_commit_rerun_dev(self._h, C.c_void_p(d_ptr), length), self.enc.ctx)

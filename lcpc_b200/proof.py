@@ -255,6 +255,14 @@ def deserialize_commit_fields(data: bytes, field: int) -> dict:
     return dict(comm=comm, coeffs=coeffs, n_rows=n_rows, n_cols=n_cols, n_per_row=n_per_row, hashes=hashes)
 
 
+def deserialize_commit(data: bytes, enc: LcEncoding) -> LcCommit:
+    """``bincode::deserialize::<LcCommit<D, E>>``: the wire image back into a device-resident commit for ``enc``."""
+    f = deserialize_commit_fields(data, enc.field)
+    if (f["n_per_row"], f["n_cols"]) != (enc.n_per_row, enc.n_cols):
+        raise LcpcError(_cabi.ERR_BAD_ARG, "wire: commitment dimensions do not match the encoding")
+    return LcCommit.from_fields(enc, f["comm"], f["coeffs"], f["hashes"], f["n_rows"])
+
+
 def deserialize_proof(data: bytes, field: int) -> LcEvalProof:
     r, L = _Reader(data), FIELD_LIMBS[field]
     n_cols = r.u64()

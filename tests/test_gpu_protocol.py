@@ -167,6 +167,18 @@ def test_wire_commit_from_device_resident_commit():
     again = P.LcCommit.commit(f["coeffs"][:length], enc)  # a device-resident commit is rebuilt from its coefficients
     assert again.get_root().root == oc["root"] and (again.hashes == f["hashes"]).all()
     assert P.serialize_root(c.get_root()) == PR.wire_root(oc["root"])
+    # Deserialize for LcCommit: the wire image becomes a device-resident commit that proves like the original
+    back = P.deserialize_commit(blob, enc)
+    assert back.get_root().root == oc["root"] and (back.comm == oc["comm"]).all() and (back.coeffs == oc["coeffs"]).all()
+    p1 = c.prove(outer, enc, P.Transcript(LABEL))
+    p2 = back.prove(outer, enc, P.Transcript(LABEL))
+    assert P.serialize_proof(p1) == P.serialize_proof(p2)
+    assert (p2.verify(oc["root"], outer, inner, enc, P.Transcript(LABEL)) ==
+            O.dot(field, inner, O.collapse(field, oc["coeffs"], outer, c.n_rows, c.n_per_row))).all()
+    with pytest.raises(P.LcpcError):  # check_comm: inconsistent sizes -> ProverError::Commit
+        P.LcCommit.from_fields(enc, oc["comm"][:-1], oc["coeffs"], oc["hashes"], c.n_rows)
+    with pytest.raises(P.LcpcError):
+        P.LcCommit.from_fields(enc, oc["comm"], oc["coeffs"], oc["hashes"][:-1], c.n_rows)
 
 
 def test_handles_may_be_freed_in_any_order():
