@@ -8,8 +8,40 @@ import pytest
 
 import oracle as O
 import lcpc_b200 as P
+from oracle import protocol as PR
+from oracle.transcript import Transcript as OTranscript
 
 pytestmark = pytest.mark.gpu
+
+
+def check_prove_verify(c, enc, field, oc=None, oenc=None, seed=0):
+    """Whole prove() + verify() at the full size.  With the oracle's commit at hand the proof is compared field by
+    field; always: the proof verifies on the device against the commit's root, survives the wire, and the returned
+    evaluation is <inner, collapse(coeffs, outer)> (lcpc-2d/src/tests.rs end_to_end)."""
+    outer = O.random_elems(field, c.n_rows, seed=seed + 1)
+    inner = O.random_elems(field, c.n_per_row, seed=seed + 2)
+    proof = c.prove(outer, enc, P.Transcript(b"full size"))
+    assert proof.cols.shape[:2] == (enc.get_n_col_opens(), c.n_rows)
+    assert proof.p_random_vec.shape[0] == enc.get_n_degree_tests()
+    if oc is not None:
+        oproof = PR.prove(field, oc, outer, oenc.get_n_degree_tests(), oenc.get_n_col_opens(), OTranscript(b"full size"))
+        assert P.serialize_proof(proof) == PR.wire_proof(oproof)
+        assert [int(v) for v in proof.col_idx] == oproof["cols_to_open"]
+    back = P.deserialize_proof(P.serialize_proof(proof), field)
+    ev = back.verify(c.get_root(), outer, inner, enc, P.Transcript(b"full size"))
+    want = O.dot(field, inner, O.collapse(field, c.coeffs, outer, c.n_rows, c.n_per_row))
+    assert (ev == want).all()
+    # every opened column is the committed column and its path leads to the root
+    comm = c.comm.reshape(c.n_rows, c.n_cols, -1)
+    for j in (0, proof.cols.shape[0] // 2, proof.cols.shape[0] - 1):
+        col = int(proof.col_idx[j])
+        assert (proof.cols[j] == comm[:, col]).all()
+        assert O.verify_column_path(field, proof.cols[j], proof.paths[j], col, c.get_root().root)
+    bad = proof.cols.copy()
+    bad[-1, -1, 0] ^= 1
+    with pytest.raises(P.LcpcError):
+        P.LcEvalProof(field, proof.n_cols, proof.p_eval, proof.p_random_vec, bad, proof.paths).verify(
+            c.get_root(), outer, inner, enc, P.Transcript(b"full size"))
 
 
 def check_commit_samples(c, oenc, x, field, rows, cols, full_oracle=False):
@@ -44,6 +76,7 @@ def test_ligero_ft255_2_20_full_oracle():
     c = P.LcCommit.commit(x, enc)
     assert c.n_rows == 64
     check_commit_samples(c, oenc, x, field, rows=[0, 63], cols=[0, 1, 32767, 12345], full_oracle=True)
+    check_prove_verify(c, enc, field, oc=oenc.commit(x), oenc=oenc, seed=20)
 
 
 def test_ligero_ft255_2_24_sampled():
@@ -68,6 +101,7 @@ def test_ligero_ft255_2_24_sampled():
     for i, col in enumerate([7, 131071]):
         assert (vals[i] == comm[:, col]).all()
         assert O.verify_column_path(field, vals[i], paths[i], col, c.get_root().root)
+    check_prove_verify(c, enc, field, seed=24)  # config 4's "commit + prove"
 
 
 def test_brakedown_ft127_2_24_sampled():
@@ -83,6 +117,7 @@ def test_brakedown_ft127_2_24_sampled():
     check_commit_samples(c, oenc, x, field, rows=[0, 35, 71], cols=[0, 1, 235172, 235173, 357698, 300000, 41861])
     tensor = O.random_elems(field, c.n_rows, seed=6)
     assert (c.collapse(tensor) == O.collapse(field, c.coeffs, tensor, c.n_rows, c.n_per_row)).all()
+    check_prove_verify(c, enc, field, seed=3)  # 6593 column openings, 2 degree tests
 
 
 def test_ligero_ragged_length_chunked_host_copy():
