@@ -49,6 +49,9 @@ struct lcpc_b200_ctx {
   // grow-only device scratch shared by the stateless entry points
   void *scratch = nullptr;
   size_t scratch_bytes = 0;
+  // grow-only page-locked host staging (results the host has to read right away: canonical bytes for the transcript)
+  void *h_stage = nullptr;
+  size_t h_stage_bytes = 0;
 };
 
 static int fail(lcpc_b200_ctx *ctx, int code, const char *fmt, ...) {
@@ -87,6 +90,20 @@ static int ensure_scratch(lcpc_b200_ctx *ctx, size_t bytes) {
   CU(ctx, cudaMalloc(&ctx->scratch, bytes));
   ctx->scratch_bytes = bytes;
   return LCPC_B200_OK;
+}
+
+// page-locked staging of at least `bytes`; nullptr if the allocation fails (callers fall back to pageable memory)
+static void *host_stage(lcpc_b200_ctx *ctx, size_t bytes) {
+  if (bytes <= ctx->h_stage_bytes) return ctx->h_stage;
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  ctx->h_stage = nullptr, ctx->h_stage_bytes = 0;
+  if (cudaHostAlloc(&ctx->h_stage, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    ctx->h_stage = nullptr;
+    return nullptr;
+  }
+  ctx->h_stage_bytes = bytes;
+  return ctx->h_stage;
 }
 
 static bool is_pow2(size_t v) { return v && !(v & (v - 1)); }
@@ -170,7 +187,7 @@ struct lcpc_b200_commit {
   void *d_hash_scratch = nullptr;
   void *d_enc_scratch = nullptr;
   // prove-side staging
-  uint32_t *d_tensor = nullptr, *d_poly = nullptr, *d_key = nullptr;
+  uint32_t *d_tensor = nullptr, *d_poly = nullptr, *d_key = nullptr, *d_repr = nullptr;
   void *h_poly = nullptr;  // page-locked landing buffer for collapse results (pageable destinations copy from it)
   // phase boundaries of the last run: start | copy+pad | encode | leaf hash | merkle
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -248,6 +265,7 @@ static void ctx_unref(lcpc_b200_ctx *ctx) {
   if (ctx->lane_fork) cudaEventDestroy(ctx->lane_fork);
   if (ctx->lane_join) cudaEventDestroy(ctx->lane_join);
   if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   delete ctx;
 }
 
@@ -610,6 +628,7 @@ static void commit_release(lcpc_b200_commit *c) {
   cudaFree(c->d_tensor);
   cudaFree(c->d_poly);
   cudaFree(c->d_key);
+  cudaFree(c->d_repr);
   if (c->h_poly) cudaFreeHost(c->h_poly);
   for (auto &e : c->ev)
     if (e) cudaEventDestroy(e);
@@ -1102,21 +1121,13 @@ Labels resolve_labels(const lcpc_b200_labels *in) {
   return Labels{in->dt, in->pr, in->pe, in->co, in->dt_len, in->pr_len, in->pe_len, in->co_len};
 }
 
-// a device allocation that lives for one call
+// layout of one call's device buffers inside the context's grow-only scratch: 256-byte aligned regions
 struct DeviceBlock {
-  uint8_t *base = nullptr;
-  size_t used = 0, cap = 0;
-  ~DeviceBlock() {
-    if (base) cudaFree(base);
-  }
-  size_t reserve(size_t bytes) {  // returns the offset of a 256-byte aligned region
+  size_t used = 0;
+  size_t reserve(size_t bytes) {  // returns the offset of the region
     size_t off = (used + 255) & ~(size_t)255;
     used = off + bytes;
     return off;
-  }
-  cudaError_t commit() {
-    cap = used ? used : 256;
-    return cudaMalloc(&base, cap);
   }
 };
 
@@ -1148,9 +1159,16 @@ int lcpc_b200_commit_prove(lcpc_b200_commit *c, lcpc_b200_transcript *tr, const 
   const Labels lb = resolve_labels(labels);
   const int field = c->enc->field;
   const size_t B = field_bytes(field), L = B / 8, pbytes = c->n_per_row * B;
-  uint32_t *d_repr = nullptr;
-  CU(ctx, cudaMalloc(&d_repr, pbytes));
-  std::vector<uint8_t> repr(pbytes);
+  if (!c->d_repr) CU(ctx, cudaMalloc(&c->d_repr, pbytes));
+  uint32_t *d_repr = c->d_repr;
+  // results land in page-locked staging [poly | repr] (a pageable destination would be staged by the driver at a
+  // fraction of the PCIe rate); pageable fallback if the allocation fails
+  std::vector<uint8_t> pageable;
+  uint8_t *stage = (uint8_t *)host_stage(ctx, 2 * pbytes);
+  if (!stage) {
+    pageable.resize(2 * pbytes);
+    stage = pageable.data();
+  }
   int rc = LCPC_B200_OK;
   // one collapse against the tensor in c->d_tensor: Montgomery limbs to `dst`, canonical bytes into the transcript
   auto collapse_and_absorb = [&](uint64_t *dst, const uint8_t *label, size_t label_len) -> int {
@@ -1160,10 +1178,13 @@ int lcpc_b200_commit_prove(lcpc_b200_commit *c, lcpc_b200_transcript *tr, const 
     if (ce == cudaSuccess) ce = launch_field_op(field, 4, d_repr, c->d_poly, nullptr, c->n_per_row, ctx->stream);
     ctx->launches += nl + 1;
     if (ce != cudaSuccess) return cuda_fail(ctx, ce, "prove: collapse");
-    CU(ctx, cudaMemcpyAsync(dst, c->d_poly, pbytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(repr.data(), d_repr, pbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(stage + pbytes, d_repr, pbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->begin_ev, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(stage, c->d_poly, pbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaEventSynchronize(ctx->begin_ev));  // the canonical bytes are in: absorb them while the limbs follow
+    tr->tr.append_elems(label, label_len, stage + pbytes, B, c->n_per_row);  // transcript_update per coefficient (:1043-1045)
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    tr->tr.append_elems(label, label_len, repr.data(), B, c->n_per_row);  // transcript_update per coefficient (:1043-1045)
+    memcpy(dst, stage, pbytes);
     return LCPC_B200_OK;
   };
   for (size_t i = 0; i < n_degree_tests && rc == LCPC_B200_OK; i++) {  // :1025-1048
@@ -1177,7 +1198,6 @@ int lcpc_b200_commit_prove(lcpc_b200_commit *c, lcpc_b200_transcript *tr, const 
     if (ce != cudaSuccess) rc = cuda_fail(ctx, ce, "prove: outer tensor");
     else rc = collapse_and_absorb(p_eval, lb.pe, lb.pe_len);
   }
-  cudaFree(d_repr);
   if (rc != LCPC_B200_OK) return rc;
   // :1066-1085
   uint8_t key[32];
@@ -1222,8 +1242,8 @@ int lcpc_b200_verify(lcpc_b200_enc *enc, lcpc_b200_transcript *tr, const lcpc_b2
   const size_t o_hs = blk.reserve(hash_scratch_bytes(field, n_rows, n_open) + 32);
   const size_t o_es = blk.reserve(enc_scratch_bytes(enc, T) + 32);
   const size_t o_inner = blk.reserve(n_per_row * B), o_part = blk.reserve((DOT_PARTIALS + 1) * B);
-  CU(ctx, blk.commit());
-  uint8_t *d = blk.base;
+  if (int rc = ensure_scratch(ctx, blk.used)) return rc;
+  uint8_t *d = (uint8_t *)ctx->scratch;
   auto w32 = [&](size_t off) { return (uint32_t *)(d + off); };
   cudaStream_t st = ctx->stream;
 
@@ -1234,8 +1254,14 @@ int lcpc_b200_verify(lcpc_b200_enc *enc, lcpc_b200_transcript *tr, const lcpc_b2
   cudaError_t ce = launch_field_op(field, 4, w32(o_repr), w32(o_in), nullptr, T * n_per_row, st);
   ctx->launches += 1;
   if (ce != cudaSuccess) return cuda_fail(ctx, ce, "verify: from_mont");
-  std::vector<uint8_t> repr(T * n_per_row * B);
-  CU(ctx, cudaMemcpyAsync(repr.data(), d + o_repr, repr.size(), cudaMemcpyDeviceToHost, st));
+  const size_t repr_bytes = T * n_per_row * B;
+  std::vector<uint8_t> pageable;
+  uint8_t *repr = (uint8_t *)host_stage(ctx, repr_bytes);
+  if (!repr) {
+    pageable.resize(repr_bytes);
+    repr = pageable.data();
+  }
+  CU(ctx, cudaMemcpyAsync(repr, d + o_repr, repr_bytes, cudaMemcpyDeviceToHost, st));
   CU(ctx, cudaEventRecord(ctx->begin_ev, st));
   // step 1b / step 2 (:883-888, :914-921): every row zero-extended to n_cols and encoded, in one batch
   if (int rc = encode_rows(enc, w32(o_in), n_per_row, n_per_row, w32(o_rows), T, d + o_es)) return rc;
@@ -1245,9 +1271,9 @@ int lcpc_b200_verify(lcpc_b200_enc *enc, lcpc_b200_transcript *tr, const lcpc_b2
   std::vector<uint8_t> keys(T * 32);
   for (size_t i = 0; i < n_degree_tests; i++) {
     tr->tr.challenge_bytes(lb.dt, lb.dt_len, keys.data() + 32 * i, 32);
-    tr->tr.append_elems(lb.pr, lb.pr_len, repr.data() + i * n_per_row * B, B, n_per_row);
+    tr->tr.append_elems(lb.pr, lb.pr_len, repr + i * n_per_row * B, B, n_per_row);
   }
-  tr->tr.append_elems(lb.pe, lb.pe_len, repr.data() + n_degree_tests * n_per_row * B, B, n_per_row);
+  tr->tr.append_elems(lb.pe, lb.pe_len, repr + n_degree_tests * n_per_row * B, B, n_per_row);
   uint8_t key_co[32];
   tr->tr.challenge_bytes(lb.co, lb.co_len, key_co, 32);
   std::vector<uint64_t> cols(n_open);
