@@ -55,4 +55,8 @@ def test_oracle_reproduces_reference_roots():
         x = mod.case_coeffs(name, field, length)
         enc = O.Encoding.ligero(field, length) if kind == "ligero" else O.Encoding.sdig(field, length, seed=seed)
         assert list(enc.get_dims(length)) == [want[name][k] for k in ("n_rows", "n_per_row", "n_cols")], name
-        assert enc.commit(x)["root"].hex() == want[name]["root"], name
+        c = enc.commit(x)
+        assert c["root"].hex() == want[name]["root"], name
+        if "proof_blake3" in want[name]:  # prove / verify / bincode wire image of the real reference
+            got = mod.case_proof(field, enc, c, x)
+            assert got == {k: want[name][k] for k in ("proof_len", "proof_blake3", "eval")}, name

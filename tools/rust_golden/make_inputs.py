@@ -33,6 +33,20 @@ def case_coeffs(name, field, length):
     return O.random_elems(field, length, seed=sum(name.encode()) % 997)
 
 
+def case_proof(field, enc, c, x):
+    """What the Rust program prints about prove/verify: the wire image of the proof made on
+    Transcript::new(b"rust golden") with outer = first n_rows coefficients, and the evaluation verify() returns with
+    inner = first n_per_row coefficients."""
+    from oracle import protocol as PR
+    from oracle.transcript import Transcript
+    outer, inner = x[:c["n_rows"]], x[:c["n_per_row"]]
+    proof = PR.prove(field, c, outer, enc.get_n_degree_tests(), enc.get_n_col_opens(), Transcript(b"rust golden"))
+    wire = PR.wire_proof(proof)
+    ev = PR.verify(field, enc, c["root"], outer, inner, proof, Transcript(b"rust golden"))
+    return {"proof_len": len(wire), "proof_blake3": O.blake3(wire).hex(),
+            "eval": O.to_repr(field, ev.reshape(1, -1)).tobytes().hex()}
+
+
 def main(out):
     os.makedirs(out, exist_ok=True)
     roots = []
@@ -42,7 +56,9 @@ def main(out):
         enc = O.Encoding.ligero(field, length) if kind == "ligero" else O.Encoding.sdig(field, length, seed=seed)
         c = enc.commit(x)
         n_rows, n_per_row, n_cols = enc.get_dims(length)
-        roots.append({"case": name, "root": c["root"].hex(), "n_rows": n_rows, "n_per_row": n_per_row, "n_cols": n_cols})
+        rec = {"case": name, "root": c["root"].hex(), "n_rows": n_rows, "n_per_row": n_per_row, "n_cols": n_cols}
+        rec.update(case_proof(field, enc, c, x))
+        roots.append(rec)
     json.dump(roots, open(os.path.join(out, "oracle_roots.json"), "w"), indent=1)
     print(f"wrote {len(CASES)} input files and oracle_roots.json to {out}")
 

@@ -1,10 +1,15 @@
 // Reads the input files written by make_inputs.py (canonical little-endian field elements, one file per case),
 // commits to each with the unmodified reference and prints one JSON object per case:
-//   {"case": "...", "root": "<hex>", "n_rows": .., "n_per_row": .., "n_cols": ..}
+//   {"case": "...", "root": "<hex>", "n_rows": .., "n_per_row": .., "n_cols": ..,
+//    "proof_len": .., "proof_blake3": "<hex>", "eval": "<hex>"}
+// proof_* describe bincode::serialize(&proof) of an evaluation proof made on Transcript::new(b"rust golden") with
+// outer tensor = the first n_rows input coefficients; eval = to_repr of what verify() returns with inner tensor =
+// the first n_per_row input coefficients.
 // Paste the output into tests/golden/rust_roots.json; tests/test_rust_golden.py then holds the oracle to it.
 use blake3::Hasher as Blake3;
 use ff::PrimeField;
 use lcpc_2d::LcEncoding;
+use merlin::Transcript;
 use lcpc_brakedown_pc::{BrakedownCommit, SdigEncoding};
 use lcpc_ligero_pc::{LigeroCommit, LigeroEncoding};
 use lcpc_test_fields::{ft127::Ft127, ft255::Ft255, ft63::Ft63};
@@ -31,9 +36,18 @@ macro_rules! ligero_case {
         let enc = LigeroEncoding::<$f>::new(coeffs.len());
         let (n_rows, n_per_row, n_cols) = enc.get_dims(coeffs.len());
         let comm = LigeroCommit::<Blake3, $f>::commit(&coeffs, &enc).unwrap();
+        let root = comm.get_root();
+        let outer: Vec<$f> = coeffs[..n_rows].to_vec();
+        let inner: Vec<$f> = coeffs[..n_per_row].to_vec();
+        let mut tr = Transcript::new(b"rust golden");
+        let pf = comm.prove(&outer[..], &enc, &mut tr).unwrap();
+        let wire: Vec<u8> = bincode::serialize(&pf).unwrap();
+        let mut tr2 = Transcript::new(b"rust golden");
+        let ev = pf.verify(root.as_ref(), &outer[..], &inner[..], &enc, &mut tr2).unwrap();
         println!(
-            "{{\"case\": \"{}\", \"root\": \"{}\", \"n_rows\": {}, \"n_per_row\": {}, \"n_cols\": {}}}",
-            $name, hex(comm.get_root().as_ref()), n_rows, n_per_row, n_cols
+            "{{\"case\": \"{}\", \"root\": \"{}\", \"n_rows\": {}, \"n_per_row\": {}, \"n_cols\": {}, \"proof_len\": {}, \"proof_blake3\": \"{}\", \"eval\": \"{}\"}}",
+            $name, hex(root.as_ref()), n_rows, n_per_row, n_cols, wire.len(),
+            hex(blake3::hash(&wire).as_bytes()), hex(ev.to_repr().as_ref())
         );
     }};
 }
@@ -44,9 +58,18 @@ macro_rules! brakedown_case {
         let enc = SdigEncoding::<$f>::new(coeffs.len(), $seed);
         let (n_rows, n_per_row, n_cols) = enc.get_dims(coeffs.len());
         let comm = BrakedownCommit::<Blake3, $f>::commit(&coeffs, &enc).unwrap();
+        let root = comm.get_root();
+        let outer: Vec<$f> = coeffs[..n_rows].to_vec();
+        let inner: Vec<$f> = coeffs[..n_per_row].to_vec();
+        let mut tr = Transcript::new(b"rust golden");
+        let pf = comm.prove(&outer[..], &enc, &mut tr).unwrap();
+        let wire: Vec<u8> = bincode::serialize(&pf).unwrap();
+        let mut tr2 = Transcript::new(b"rust golden");
+        let ev = pf.verify(root.as_ref(), &outer[..], &inner[..], &enc, &mut tr2).unwrap();
         println!(
-            "{{\"case\": \"{}\", \"root\": \"{}\", \"n_rows\": {}, \"n_per_row\": {}, \"n_cols\": {}}}",
-            $name, hex(comm.get_root().as_ref()), n_rows, n_per_row, n_cols
+            "{{\"case\": \"{}\", \"root\": \"{}\", \"n_rows\": {}, \"n_per_row\": {}, \"n_cols\": {}, \"proof_len\": {}, \"proof_blake3\": \"{}\", \"eval\": \"{}\"}}",
+            $name, hex(root.as_ref()), n_rows, n_per_row, n_cols, wire.len(),
+            hex(blake3::hash(&wire).as_bytes()), hex(ev.to_repr().as_ref())
         );
     }};
 }
