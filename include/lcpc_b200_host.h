@@ -25,6 +25,8 @@ int lcpc_b200_ligero_get_dims(int field, size_t len, size_t rho_num, size_t rho_
  * code = 1..6 selects SdigCode1..6 (codespec.rs:169-232; the default alias is SdigCode3, lib.rs:19) */
 size_t lcpc_b200_sdig_n_col_opens(int code);
 int lcpc_b200_sdig_choose_n_per_row(int field, int code, size_t len, size_t *n_per_row);
+/* the same for SdigEncodingS::new_ml (:114-124): 2^n_vars monomials, first guess rounded up to a power of two */
+int lcpc_b200_sdig_choose_n_per_row_ml(int field, int code, size_t n_vars, size_t *n_per_row);
 
 /* matgen::generate (lcpc-brakedown-pc/src/matgen.rs:28-52): the seeded precodes/postcodes, host memory */
 typedef struct lcpc_b200_sdig_code lcpc_b200_sdig_code;

@@ -121,6 +121,7 @@ SIGNATURES = {
     "lcpc_b200_ligero_get_dims": (_i, [_i, _sz, _sz, _sz, _psz, _psz, _psz]),
     "lcpc_b200_sdig_n_col_opens": (_sz, [_i]),
     "lcpc_b200_sdig_choose_n_per_row": (_i, [_i, _i, _sz, _psz]),
+    "lcpc_b200_sdig_choose_n_per_row_ml": (_i, [_i, _i, _sz, _psz]),
     "lcpc_b200_sdig_code_generate": (_i, [_i, _i, _sz, _u64, _pvp]),
     "lcpc_b200_sdig_code_free": (None, [_vp]),
     "lcpc_b200_sdig_code_levels": (_sz, [_vp]),

@@ -163,7 +163,8 @@ size_t sdig_n_col_opens(const CodeSpec &s) {
   return (size_t)std::ceil(-(double)LAMBDA / std::log2(1.0 - s.dist() / 3.0));
 }
 
-int sdig_choose_n_per_row(int field, const CodeSpec &s, size_t len, size_t *n_per_row) {
+// `ml`: SdigEncodingS::new_ml (lcpc-brakedown-pc/src/lib.rs:114-124) rounds the first guess up to a power of two
+int sdig_choose_n_per_row(int field, const CodeSpec &s, size_t len, size_t *n_per_row, bool ml) {
   const FieldDesc *fd = field_desc(field);
   if (!fd || len == 0) return LCPC_B200_ERR_BAD_ARG;
   const size_t flog2 = fd->bits - 1;
@@ -171,6 +172,11 @@ int sdig_choose_n_per_row(int field, const CodeSpec &s, size_t len, size_t *n_pe
   const double lncf = (double)(opens * len);
   const double ndt = (double)n_degree_tests(LAMBDA, (size_t)std::ceil(std::sqrt(lncf)) * 2, flog2);
   size_t np1 = (size_t)std::ceil(std::sqrt(lncf / ndt));
+  if (ml) {  // checked_next_power_of_two
+    size_t p = 1;
+    while (p < np1) p <<= 1;
+    np1 = p;
+  }
   if (np1 > len) np1 = len;
   const size_t np2 = np1 / 2;
   if (np2 == 0) return LCPC_B200_ERR_BAD_ARG;
@@ -260,6 +266,11 @@ int lcpc_b200_ligero_get_dims(int field, size_t len, size_t rho_num, size_t rho_
 size_t lcpc_b200_sdig_n_col_opens(int code) {
   CodeSpec s;
   return sdig_code_spec(code, &s) ? sdig_n_col_opens(s) : 0;
+}
+int lcpc_b200_sdig_choose_n_per_row_ml(int field, int code, size_t n_vars, size_t *n_per_row) {
+  CodeSpec s;
+  if (!n_per_row || n_vars >= 8 * sizeof(size_t) - 1 || !sdig_code_spec(code, &s)) return LCPC_B200_ERR_BAD_ARG;
+  return sdig_choose_n_per_row(field, s, (size_t)1 << n_vars, n_per_row, true);
 }
 int lcpc_b200_sdig_choose_n_per_row(int field, int code, size_t len, size_t *n_per_row) {
   CodeSpec s;

@@ -37,7 +37,7 @@ size_t ligero_n_col_opens(size_t rho_num, size_t rho_den);       // lcpc-ligero-
 int ligero_get_dims(int field, size_t len, size_t rho_num, size_t rho_den, size_t *n_rows, size_t *n_per_row,
                     size_t *n_cols);                             // lcpc-ligero-pc/src/lib.rs:70-112
 size_t sdig_n_col_opens(const CodeSpec &s);                      // lcpc-brakedown-pc/src/lib.rs:57-61
-int sdig_choose_n_per_row(int field, const CodeSpec &s, size_t len, size_t *n_per_row);  // :69-110
+int sdig_choose_n_per_row(int field, const CodeSpec &s, size_t len, size_t *n_per_row, bool ml = false);  // :69-124
 int sdig_level_dims(int field, const CodeSpec &s, size_t n, std::vector<LevelDims> *pre,
                     std::vector<LevelDims> *post);               // matgen.rs:56-111
 int sdig_generate(int field, int code, size_t n_per_row, uint64_t seed, SdigCode *out);  // matgen.rs:28-52

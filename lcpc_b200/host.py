@@ -158,6 +158,14 @@ class LigeroEncoding(LcEncoding):
         self._init_dims(field, n_per_row, n_cols, rho, ctx)
 
     @classmethod
+    def new_ml(cls, field: int, n_vars: int, rho=(1, 2), ctx: Context | None = None):
+        """LigeroEncodingRho::new_ml (:126-135): a multilinear polynomial with 2^n_vars monomials."""
+        n_rows, n_per_row, n_cols = ligero_get_dims(field, 1 << n_vars, rho)
+        if n_rows & (n_rows - 1) or n_per_row & (n_per_row - 1) or n_rows * n_per_row != 1 << n_vars:  # asserts :131-133
+            raise LcpcError(_cabi.ERR_BAD_ARG, "new_ml: dimensions are not powers of two")
+        return cls.new_from_dims(field, n_per_row, n_cols, rho, ctx)
+
+    @classmethod
     def new_from_dims(cls, field: int, n_per_row: int, n_cols: int, rho=(1, 2), ctx: Context | None = None):
         """LigeroEncodingRho::new_from_dims (:138-148)."""
         self = cls.__new__(cls)
@@ -185,6 +193,13 @@ class SdigEncoding(LcEncoding):
         npr = C.c_size_t()
         _check(_cabi.lib().lcpc_b200_sdig_choose_n_per_row(field, code, length, C.byref(npr)))
         self._init_dims(field, npr.value, 0, seed, code, ctx)
+
+    @classmethod
+    def new_ml(cls, field: int, n_vars: int, seed: int = 0, code: int = 3, ctx: Context | None = None):
+        """SdigEncodingS::new_ml (:114-124): 2^n_vars monomials, n_per_row a power of two."""
+        npr = C.c_size_t()
+        _check(_cabi.lib().lcpc_b200_sdig_choose_n_per_row_ml(field, code, n_vars, C.byref(npr)))
+        return cls.new_from_dims(field, npr.value, 0, seed, code, ctx)
 
     @classmethod
     def new_from_dims(cls, field: int, n_per_row: int, n_cols: int = 0, seed: int = 0, code: int = 3,
@@ -278,6 +293,10 @@ class LcRoot:
     def __init__(self, root: bytes):
         self.root = bytes(root)
 
+    def into_raw(self) -> bytes:
+        """LcRoot::into_raw (:337-339)."""
+        return self.root
+
     def __eq__(self, other):
         return isinstance(other, LcRoot) and self.root == other.root
 
@@ -345,6 +364,18 @@ class LcCommit:
             self.close()
         except Exception:
             pass
+
+    def get_n_per_row(self) -> int:
+        """:284-286."""
+        return self.n_per_row
+
+    def get_n_cols(self) -> int:
+        """:289-291."""
+        return self.n_cols
+
+    def get_n_rows(self) -> int:
+        """:294-296."""
+        return self.n_rows
 
     def get_root(self) -> LcRoot:
         """LcCommit::get_root (:276-281)."""

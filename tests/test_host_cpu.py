@@ -177,3 +177,25 @@ def test_field_carry_chains_on_host_emulation(hostcheck, field):
     for k in range(37):
         want = O.field_op(field, "add", want, sq)
     assert (r == want).all()
+
+
+def test_sdig_new_ml_chooses_a_power_of_two_first_guess():
+    """SdigEncodingS::new_ml (lcpc-brakedown-pc/src/lib.rs:114-124) restated here in Python: the first guess is rounded
+    up to a power of two, then _new_from_np1 (:69-99) keeps it or halves it."""
+    import ctypes as C
+    import math
+    lib = _cabi.lib()
+    for field, flog2 in ((P.FT127, 126), (P.FT255, 254)):
+        for n_vars in (12, 16, 20, 24, 28):
+            n = 1 << n_vars
+            opens = lib.lcpc_b200_sdig_n_col_opens(3)
+            lncf = float(opens * n)
+            ndt = host.n_degree_tests(128, math.ceil(math.sqrt(lncf)) * 2, flog2)
+            np1 = 1 << (math.ceil(math.sqrt(lncf / ndt)) - 1).bit_length()
+            np1 = min(np1, n)
+            np2 = np1 // 2
+            sz = lambda npr: opens * -(-n // npr) + (1 + host.n_degree_tests(128, npr * 2, flog2)) * npr
+            want = np1 if sz(np1) < sz(np2) else np2
+            got = C.c_size_t()
+            assert lib.lcpc_b200_sdig_choose_n_per_row_ml(field, 3, n_vars, C.byref(got)) == 0
+            assert got.value == want and want & (want - 1) == 0
