@@ -197,3 +197,19 @@ def test_handles_may_be_freed_in_any_order():
     t = O.random_elems(field, c.n_rows, seed=9)
     assert (c.collapse(t) == O.collapse(field, want["coeffs"], t, c.n_rows, c.n_per_row)).all()
     c.close()
+
+
+def test_new_ml_encodings_commit_like_the_oracle():
+    """LigeroEncodingRho::new_ml / SdigEncodingS::new_ml (multilinear sizes): power-of-two row lengths, same commit."""
+    field, n_vars = P.FT127, 12
+    x = O.random_elems(field, 1 << n_vars, seed=12)
+    enc = P.LigeroEncoding.new_ml(field, n_vars)
+    oenc = O.Encoding.ligero_from_dims(field, enc.n_per_row, enc.n_cols)
+    c = P.LcCommit.commit(x, enc)
+    assert c.get_n_rows() * c.get_n_per_row() == 1 << n_vars and c.get_root().into_raw() == oenc.commit(x)["root"]
+    senc = P.SdigEncoding.new_ml(field, n_vars, seed=3)
+    assert senc.n_per_row & (senc.n_per_row - 1) == 0
+    soenc = O.Encoding.sdig_from_dims(field, senc.n_per_row, seed=3)
+    assert soenc.n_cols == senc.n_cols
+    sc = P.LcCommit.commit(x, senc)
+    assert sc.get_n_cols() == senc.n_cols and sc.get_root().root == soenc.commit(x)["root"]
