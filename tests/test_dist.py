@@ -86,6 +86,11 @@ def test_gloo_world3_ragged():
     check(run_workers(3, "gloo", "ligero", 2, (1 << 11) - 5))
 
 
+def test_gloo_world4_brakedown_ft191():
+    # 4 ranks, 3-limb field, non-power-of-two column count: commit + prove over the sharded commit
+    check(run_workers(4, "gloo", "sdig", 3, 2500, seed=2))
+
+
 def _n_gpus():
     try:
         import torch
