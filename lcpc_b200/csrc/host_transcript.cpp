@@ -1,8 +1,10 @@
 // lcpc_b200/csrc/host_transcript.cpp -- merlin 2.0 transcript (STROBE-128 over Keccak-f[1600]); see the header.
 #include "host_transcript.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <new>
+#include <string>
 
 #include "../../include/lcpc_b200_host.h"
 
@@ -56,10 +58,90 @@ __attribute__((target("bmi,bmi2"))) static void keccak_f1600_bmi(uint64_t st[25]
 #endif
 static void keccak_f1600_base(uint64_t st[25]) { keccak_rounds(st); }
 
+#if defined(__x86_64__) && defined(__GNUC__)
+}  // namespace host
+}  // namespace lcpc
+#include <immintrin.h>
+namespace lcpc {
+namespace host {
+// AVX-512 build: one register per plane (the five lanes that share y in elements 0..4).  theta is two 3-way xors, two
+// in-register lane rotations and a rotate; rho is one variable rotate per plane; pi moves plane y into the register of
+// column x' = y with ONE in-register permute (B[y][2x+3y] = A[x][y] reads only plane y), which leaves the state
+// transposed -- exactly the form in which chi is five 3-operand logic ops across registers with no shuffles -- and a
+// 5x5 transpose (14 two-source shuffles) brings it back to planes for the next round.
+__attribute__((target("avx512f,avx512vl"))) static void keccak_f1600_avx512(uint64_t st[25]) {
+  static const uint64_t RC[24] = {
+      0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808aull, 0x8000000080008000ull,
+      0x000000000000808bull, 0x0000000080000001ull, 0x8000000080008081ull, 0x8000000000008009ull,
+      0x000000000000008aull, 0x0000000000000088ull, 0x0000000080008009ull, 0x000000008000000aull,
+      0x000000008000808bull, 0x800000000000008bull, 0x8000000000008089ull, 0x8000000000008003ull,
+      0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800aull, 0x800000008000000aull,
+      0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull};
+  const __mmask8 m5 = 0x1f;
+  __m512i p0 = _mm512_maskz_loadu_epi64(m5, st), p1 = _mm512_maskz_loadu_epi64(m5, st + 5),
+          p2 = _mm512_maskz_loadu_epi64(m5, st + 10), p3 = _mm512_maskz_loadu_epi64(m5, st + 15),
+          p4 = _mm512_maskz_loadu_epi64(m5, st + 20);
+  const __m512i i_prev = _mm512_setr_epi64(4, 0, 1, 2, 3, 5, 6, 7), i_next = _mm512_setr_epi64(1, 2, 3, 4, 0, 5, 6, 7);
+  // rho offsets r[x][y] of plane y in elements x
+  const __m512i r0 = _mm512_setr_epi64(0, 1, 62, 28, 27, 0, 0, 0), r1 = _mm512_setr_epi64(36, 44, 6, 55, 20, 0, 0, 0),
+                r2 = _mm512_setr_epi64(3, 10, 43, 25, 39, 0, 0, 0), r3 = _mm512_setr_epi64(41, 45, 15, 21, 8, 0, 0, 0),
+                r4 = _mm512_setr_epi64(18, 2, 61, 56, 14, 0, 0, 0);
+  // pi: register x' (= source plane y) element y' takes the source's lane (3 y' + x') mod 5
+  const __m512i q0 = _mm512_setr_epi64(0, 3, 1, 4, 2, 5, 6, 7), q1 = _mm512_setr_epi64(1, 4, 2, 0, 3, 5, 6, 7),
+                q2 = _mm512_setr_epi64(2, 0, 3, 1, 4, 5, 6, 7), q3 = _mm512_setr_epi64(3, 1, 4, 2, 0, 5, 6, 7),
+                q4 = _mm512_setr_epi64(4, 2, 0, 3, 1, 5, 6, 7);
+  // transpose helpers
+  const __m512i t_pairs = _mm512_setr_epi64(0, 8, 1, 9, 2, 10, 3, 11), t_last = _mm512_setr_epi64(4, 12, 4, 12, 4, 12, 4, 12);
+  const __m512i u0 = _mm512_setr_epi64(0, 1, 8, 9, 0, 0, 0, 0), u1 = _mm512_setr_epi64(2, 3, 10, 11, 0, 0, 0, 0),
+                u2 = _mm512_setr_epi64(4, 5, 12, 13, 0, 0, 0, 0), u3 = _mm512_setr_epi64(6, 7, 14, 15, 0, 0, 0, 0);
+  const __m512i e0 = _mm512_set1_epi64(0), e1 = _mm512_set1_epi64(1), e2 = _mm512_set1_epi64(2), e3 = _mm512_set1_epi64(3),
+                e4 = _mm512_set1_epi64(4);
+  const __mmask8 k4 = 0x10;
+  for (int round = 0; round < 24; round++) {
+    // theta
+    __m512i c = _mm512_ternarylogic_epi64(_mm512_ternarylogic_epi64(p0, p1, p2, 0x96), p3, p4, 0x96);
+    __m512i d = _mm512_xor_si512(_mm512_permutexvar_epi64(i_prev, c), _mm512_rol_epi64(_mm512_permutexvar_epi64(i_next, c), 1));
+    // rho, then pi into the transposed form (register = column x', element = row y')
+    __m512i x0 = _mm512_permutexvar_epi64(q0, _mm512_rolv_epi64(_mm512_xor_si512(p0, d), r0));
+    __m512i x1 = _mm512_permutexvar_epi64(q1, _mm512_rolv_epi64(_mm512_xor_si512(p1, d), r1));
+    __m512i x2 = _mm512_permutexvar_epi64(q2, _mm512_rolv_epi64(_mm512_xor_si512(p2, d), r2));
+    __m512i x3 = _mm512_permutexvar_epi64(q3, _mm512_rolv_epi64(_mm512_xor_si512(p3, d), r3));
+    __m512i x4 = _mm512_permutexvar_epi64(q4, _mm512_rolv_epi64(_mm512_xor_si512(p4, d), r4));
+    // chi: a ^ (~b & c) across columns, iota into lane (0, 0)
+    __m512i y0 = _mm512_ternarylogic_epi64(x0, x1, x2, 0xD2), y1 = _mm512_ternarylogic_epi64(x1, x2, x3, 0xD2),
+            y2 = _mm512_ternarylogic_epi64(x2, x3, x4, 0xD2), y3 = _mm512_ternarylogic_epi64(x3, x4, x0, 0xD2),
+            y4 = _mm512_ternarylogic_epi64(x4, x0, x1, 0xD2);
+    y0 = _mm512_xor_si512(y0, _mm512_maskz_set1_epi64(0x01, (long long)RC[round]));
+    // back to planes: p_j[x'] = y_{x'}[j]
+    __m512i a = _mm512_permutex2var_epi64(y0, t_pairs, y1), a4 = _mm512_permutex2var_epi64(y0, t_last, y1);
+    __m512i b = _mm512_permutex2var_epi64(y2, t_pairs, y3), b4 = _mm512_permutex2var_epi64(y2, t_last, y3);
+    p0 = _mm512_mask_permutexvar_epi64(_mm512_permutex2var_epi64(a, u0, b), k4, e0, y4);
+    p1 = _mm512_mask_permutexvar_epi64(_mm512_permutex2var_epi64(a, u1, b), k4, e1, y4);
+    p2 = _mm512_mask_permutexvar_epi64(_mm512_permutex2var_epi64(a, u2, b), k4, e2, y4);
+    p3 = _mm512_mask_permutexvar_epi64(_mm512_permutex2var_epi64(a, u3, b), k4, e3, y4);
+    p4 = _mm512_mask_permutexvar_epi64(_mm512_permutex2var_epi64(a4, u0, b4), k4, e4, y4);
+  }
+  _mm512_mask_storeu_epi64(st, m5, p0);
+  _mm512_mask_storeu_epi64(st + 5, m5, p1);
+  _mm512_mask_storeu_epi64(st + 10, m5, p2);
+  _mm512_mask_storeu_epi64(st + 15, m5, p3);
+  _mm512_mask_storeu_epi64(st + 20, m5, p4);
+}
+#endif
+
 void keccak_f1600(uint64_t st[25]) {
 #if defined(__x86_64__) && defined(__GNUC__)
-  static void (*const impl)(uint64_t *) =
-      (__builtin_cpu_supports("bmi") && __builtin_cpu_supports("bmi2")) ? keccak_f1600_bmi : keccak_f1600_base;
+  static void (*const impl)(uint64_t *) = [] {
+    // LCPC_B200_KECCAK = base | bmi | avx512 forces a build the CPU supports (tests compare all of them)
+    const char *want = getenv("LCPC_B200_KECCAK");
+    const std::string w = want ? want : "";
+    const bool has_bmi = __builtin_cpu_supports("bmi") && __builtin_cpu_supports("bmi2");
+    const bool has_512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512vl");
+    if (w == "base") return keccak_f1600_base;
+    if (w == "bmi" && has_bmi) return keccak_f1600_bmi;
+    if (has_512 && w != "bmi") return keccak_f1600_avx512;
+    return has_bmi ? keccak_f1600_bmi : keccak_f1600_base;
+  }();
   impl(st);
 #else
   keccak_f1600_base(st);
@@ -93,7 +175,15 @@ void Strobe128::run_f() {
 void Strobe128::absorb(const uint8_t *data, size_t n) {
   while (n) {
     size_t run = (size_t)(R - pos_) < n ? (size_t)(R - pos_) : n;
-    for (size_t i = 0; i < run; i++) st_[pos_ + i] ^= data[i];
+    size_t i = 0;
+    for (; i + 8 <= run; i += 8) {  // eight bytes at a time (unaligned access through memcpy)
+      uint64_t a, b;
+      memcpy(&a, st_ + pos_ + i, 8);
+      memcpy(&b, data + i, 8);
+      a ^= b;
+      memcpy(st_ + pos_ + i, &a, 8);
+    }
+    for (; i < run; i++) st_[pos_ + i] ^= data[i];
     pos_ = (uint8_t)(pos_ + run), data += run, n -= run;
     if (pos_ == R) run_f();
   }

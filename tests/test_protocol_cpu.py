@@ -39,6 +39,25 @@ def test_product_transcript_reproduces_merlin_vector():
     assert t.challenge_bytes(b"challenge", 32).hex() == MERLIN_VECTOR
 
 
+@pytest.mark.parametrize("impl", ["base", "bmi", "avx512"])
+def test_every_keccak_build_reproduces_merlin_vector_and_agrees(impl):
+    """The transcript's permutation has three builds (portable, BMI, AVX-512) chosen at run time; each one the CPU
+    supports is forced in a fresh process and must give the merlin vector and the same digest of a long absorb."""
+    import subprocess
+    import sys
+    code = ("import numpy as np, lcpc_b200 as P\n"
+            "t = P.Transcript(b'test protocol'); t.append_message(b'some label', b'some data')\n"
+            "print(t.challenge_bytes(b'challenge', 32).hex())\n"
+            "t.append_reprs(b'$l//PR', (np.arange(5000 * 32) % 251).astype(np.uint8).reshape(5000, 32))\n"
+            "print(t.challenge_bytes(b'x', 64).hex())\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for which in ("base", impl):
+        env = dict(os.environ, LCPC_B200_KECCAK=which, PYTHONPATH=root)
+        outs[which] = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.split()
+    assert outs[impl][0] == MERLIN_VECTOR and outs[impl] == outs["base"]
+
+
 def test_product_transcript_equals_oracle_on_random_operation_sequences():
     rng = random.Random(11)
     for trial in range(4):
