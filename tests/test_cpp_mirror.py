@@ -1,0 +1,58 @@
+"""The C++ host-side mirror (include/lcpc_b200.hpp) against the in-tree library: compiles with the system g++, its
+host-only parts run on CPU, the full commit / prove / verify flow on the GPU is compared with the Python path."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "host", "cpp_mirror_check.cpp")
+EXE = os.path.join(ROOT, "tests", "host", "cpp_mirror_check")
+LIBDIR = os.path.join(ROOT, "lcpc_b200", "lib")
+MERLIN_VECTOR = "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
+
+
+@pytest.fixture(scope="module")
+def exe():
+    deps = [SRC, os.path.join(ROOT, "include", "lcpc_b200.hpp"), os.path.join(ROOT, "include", "lcpc_b200.h"),
+            os.path.join(ROOT, "include", "lcpc_b200_host.h"), os.path.join(LIBDIR, "liblcpc_b200.so")]
+    if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-o", EXE, SRC, "-L" + LIBDIR, "-llcpc_b200",
+                               "-Wl,-rpath," + LIBDIR])
+    return EXE
+
+
+def test_cpp_mirror_compiles_and_host_parts_work(exe):
+    out = subprocess.run([exe, "host"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.split("\n")
+    assert lines[0] == "merlin " + MERLIN_VECTOR
+    import torch
+    if not torch.cuda.is_available():
+        assert lines[1] == "no device: code -4"  # LCPC_B200_ERR_CUDA, never a CPU fallback
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["ligero", "sdig"])
+def test_cpp_mirror_commit_prove_verify_equal_the_python_path(exe, kind):
+    import lcpc_b200 as P
+    out = subprocess.run([exe, "gpu", kind], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    got = dict(l.split(" ", 1) for l in out.stdout.strip().split("\n") if " " in l)
+    assert out.stdout.strip().endswith("ok")
+    field, length, L = P.FT127, 3000, 2
+
+    def small(n, mul, add):
+        v = np.zeros((n, L), np.uint64)
+        v[:, 0] = np.arange(n, dtype=np.uint64) * np.uint64(mul) + np.uint64(add)
+        return v
+
+    enc = P.LigeroEncoding(field, length) if kind == "ligero" else P.SdigEncoding(field, length, seed=5)
+    c = P.LcCommit.commit(small(length, 7, 1), enc)
+    assert got["root"] == c.get_root().root.hex()
+    outer, inner = small(c.n_rows, 11, 3), small(c.n_per_row, 13, 2)
+    proof = c.prove(outer, enc, P.Transcript(b"cpp mirror"))
+    ev = proof.verify(c.get_root(), outer, inner, enc, P.Transcript(b"cpp mirror"))
+    assert got["eval"] == ev.tobytes().hex()
+    assert got["cols"].split() == [str(int(v)) for v in proof.col_idx[:3]]
