@@ -238,6 +238,94 @@ struct LcEvalProof {
   }
 };
 
+// ---- wire format: bincode 1.x (default options) over the reference's Wrapped* structs (:186-197, :353-357, :430-437,
+// :551-560): usize and Vec lengths are little-endian u64, a field element is its L Montgomery limbs (a newtype around
+// [u64; L], no length), a digest is WrappedOutput { #[serde(with = "serde_bytes")] bytes } = u64 length + raw bytes ----
+namespace detail {
+inline void put_u64(std::vector<uint8_t> &out, uint64_t v) {
+  for (int i = 0; i < 8; i++) out.push_back(static_cast<uint8_t>(v >> (8 * i)));
+}
+inline void put_elems(std::vector<uint8_t> &out, const uint64_t *e, size_t n_elems, size_t L) {
+  put_u64(out, n_elems);
+  for (size_t i = 0; i < n_elems * L; i++) put_u64(out, e[i]);
+}
+struct Reader {
+  const uint8_t *p;
+  size_t n, o = 0;
+  uint64_t u64() {
+    if (o + 8 > n) throw Error(LCPC_B200_ERR_BAD_ARG, "wire: truncated");
+    uint64_t v = 0;
+    for (int i = 0; i < 8; i++) v |= static_cast<uint64_t>(p[o + i]) << (8 * i);
+    o += 8;
+    return v;
+  }
+  void elems(std::vector<uint64_t> &dst, size_t L, size_t *count) {
+    const uint64_t k = u64();
+    if (k > (n - o) / (8 * L)) throw Error(LCPC_B200_ERR_BAD_ARG, "wire: truncated");
+    for (uint64_t i = 0; i < k * L; i++) dst.push_back(u64());
+    *count = static_cast<size_t>(k);
+  }
+  void digest(std::vector<uint8_t> &dst) {
+    if (u64() != 32 || o + 32 > n) throw Error(LCPC_B200_ERR_BAD_ARG, "wire: digest is not 32 bytes");
+    dst.insert(dst.end(), p + o, p + o + 32);
+    o += 32;
+  }
+};
+}  // namespace detail
+
+/// bincode::serialize(&LcRoot)
+inline std::vector<uint8_t> serialize(const LcRoot &r) {
+  std::vector<uint8_t> out;
+  detail::put_u64(out, 32);
+  out.insert(out.end(), r.root.begin(), r.root.end());
+  return out;
+}
+
+/// bincode::serialize(&LcEvalProof): {n_cols, p_eval, p_random_vec, columns[{col, path}]}; L = limbs per element
+inline std::vector<uint8_t> serialize(const LcEvalProof &p, size_t L) {
+  std::vector<uint8_t> out;
+  detail::put_u64(out, p.n_cols);
+  detail::put_elems(out, p.p_eval.data(), p.n_per_row, L);
+  detail::put_u64(out, p.n_degree_tests);
+  for (size_t i = 0; i < p.n_degree_tests; i++) detail::put_elems(out, p.p_random_vec.data() + i * p.n_per_row * L, p.n_per_row, L);
+  detail::put_u64(out, p.n_columns);
+  for (size_t j = 0; j < p.n_columns; j++) {
+    detail::put_elems(out, p.cols.data() + j * p.n_rows * L, p.n_rows, L);
+    detail::put_u64(out, p.path_len);
+    for (size_t l = 0; l < p.path_len; l++) {
+      detail::put_u64(out, 32);
+      const uint8_t *d = p.paths.data() + (j * p.path_len + l) * 32;
+      out.insert(out.end(), d, d + 32);
+    }
+  }
+  return out;
+}
+
+/// bincode::deserialize::<LcEvalProof>; throws Error(ERR_BAD_ARG) on truncated, ragged or trailing input
+inline LcEvalProof deserialize_proof(const uint8_t *data, size_t n, size_t L) {
+  detail::Reader r{data, n};
+  LcEvalProof p;
+  p.n_cols = static_cast<size_t>(r.u64());
+  r.elems(p.p_eval, L, &p.n_per_row);
+  p.n_degree_tests = static_cast<size_t>(r.u64());
+  for (size_t i = 0; i < p.n_degree_tests; i++) {
+    size_t k = 0;
+    r.elems(p.p_random_vec, L, &k);
+    if (k != p.n_per_row) throw Error(LCPC_B200_ERR_BAD_ARG, "wire: ragged proof");
+  }
+  p.n_columns = static_cast<size_t>(r.u64());
+  for (size_t j = 0; j < p.n_columns; j++) {
+    size_t k = 0;
+    r.elems(p.cols, L, &k);
+    const size_t pl = static_cast<size_t>(r.u64());
+    if (j == 0) p.n_rows = k, p.path_len = pl;
+    if (k != p.n_rows || pl != p.path_len) throw Error(LCPC_B200_ERR_BAD_ARG, "wire: ragged proof");
+    for (size_t l = 0; l < pl; l++) r.digest(p.paths);
+  }
+  if (r.o != n) throw Error(LCPC_B200_ERR_BAD_ARG, "wire: trailing bytes");
+  return p;
+}
+
 /// LcCommit<D, E> (:172-184), device resident; the fields are downloaded on request.
 class LcCommit {
  public:

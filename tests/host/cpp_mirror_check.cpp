@@ -1,6 +1,8 @@
 // tests/host/cpp_mirror_check.cpp -- exercises include/lcpc_b200.hpp (the C++ host-side mirror of the reference's
 // operator interface) against the in-tree library.
 //   cpp_mirror_check host        transcript conformance vector + "no device -> Error(ERR_CUDA)" (no GPU needed)
+//   cpp_mirror_check wire FILE   writes the bincode image of a deterministic synthetic LcEvalProof (Ft255 shapes) to FILE
+//                                after a serialize -> deserialize -> serialize round trip (no GPU needed)
 //   cpp_mirror_check gpu KIND    KIND = ligero | sdig: commit, prove, verify, tamper, re-import of the commit's fields;
 //                                prints `root <hex>`, `eval <hex>`, `cols <first opened column numbers>`, `ok`
 // The coefficient / tensor values are small integers used directly as limb 0 (any value below p is a valid element),
@@ -39,6 +41,36 @@ static int run_host() {
     printf("no device: code %d\n", e.code());
     if (e.code() != LCPC_B200_ERR_CUDA) return 1;
   }
+  return 0;
+}
+
+static int run_wire(const char *path) {
+  const size_t L = 4;
+  LcEvalProof p;
+  p.n_cols = 1024, p.n_per_row = 512, p.n_degree_tests = 2, p.n_columns = 7, p.n_rows = 3, p.path_len = 10;
+  for (size_t i = 0; i < p.n_per_row * L; i++) p.p_eval.push_back(0x0101010101010101ull * (i % 251) + i);
+  for (size_t i = 0; i < p.n_degree_tests * p.n_per_row * L; i++) p.p_random_vec.push_back(i * 0x9e3779b97f4a7c15ull);
+  for (size_t i = 0; i < p.n_columns * p.n_rows * L; i++) p.cols.push_back(~(uint64_t)i * 3);
+  for (size_t i = 0; i < p.n_columns * p.path_len * 32; i++) p.paths.push_back((uint8_t)(i * 7 + 1));
+  std::vector<uint8_t> w = serialize(p, L);
+  LcEvalProof q = deserialize_proof(w.data(), w.size(), L);
+  if (q.n_cols != p.n_cols || q.p_eval != p.p_eval || q.p_random_vec != p.p_random_vec || q.cols != p.cols || q.paths != p.paths ||
+      q.n_rows != p.n_rows || q.path_len != p.path_len || serialize(q, L) != w)
+    return 11;
+  try {
+    deserialize_proof(w.data(), w.size() - 1, L);
+    return 12;
+  } catch (const Error &) {
+  }
+  LcRoot r;
+  for (int i = 0; i < 32; i++) r.root[i] = (uint8_t)(200 - i);
+  std::vector<uint8_t> wr = serialize(r);
+  FILE *f = fopen(path, "wb");
+  if (!f) return 13;
+  fwrite(w.data(), 1, w.size(), f);
+  fwrite(wr.data(), 1, wr.size(), f);
+  fclose(f);
+  printf("wire %zu %zu\n", w.size(), wr.size());
   return 0;
 }
 
@@ -98,6 +130,7 @@ int main(int argc, char **argv) {
   try {
     if (argc >= 2 && std::string(argv[1]) == "host") return run_host();
     if (argc >= 3 && std::string(argv[1]) == "gpu") return run_gpu(argv[2]);
+    if (argc >= 3 && std::string(argv[1]) == "wire") return run_wire(argv[2]);
   } catch (const std::exception &e) {
     fprintf(stderr, "exception: %s\n", e.what());
     return 20;

@@ -33,6 +33,27 @@ def test_cpp_mirror_compiles_and_host_parts_work(exe):
         assert lines[1] == "no device: code -4"  # LCPC_B200_ERR_CUDA, never a CPU fallback
 
 
+def test_cpp_mirror_wire_format_equals_python_writer(exe, tmp_path):
+    """serialize / deserialize_proof of the C++ mirror: byte-identical to lcpc_b200.proof (which is held to the oracle's
+    element-by-element writer and to the reference's logged proof sizes)."""
+    import lcpc_b200 as P
+    out_file = str(tmp_path / "wire.bin")
+    out = subprocess.run([exe, "wire", out_file], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stderr)
+    n_proof, n_root = (int(v) for v in out.stdout.split()[1:3])
+    blob = open(out_file, "rb").read()
+    assert len(blob) == n_proof + n_root
+    L, npr, ndt, ncol, nrows, plen = 4, 512, 2, 7, 3, 10
+    M = (1 << 64) - 1
+    p_eval = np.array([(0x0101010101010101 * (i % 251) + i) & M for i in range(npr * L)], np.uint64).reshape(npr, L)
+    p_rand = np.array([(i * 0x9E3779B97F4A7C15) & M for i in range(ndt * npr * L)], np.uint64).reshape(ndt, npr, L)
+    cols = np.array([((~i & M) * 3) & M for i in range(ncol * nrows * L)], np.uint64).reshape(ncol, nrows, L)
+    paths = np.array([(i * 7 + 1) & 255 for i in range(ncol * plen * 32)], np.uint8).reshape(ncol, plen, 32)
+    want = P.serialize_proof(P.LcEvalProof(P.FT255, 1024, p_eval, p_rand, cols, paths))
+    assert blob[:n_proof] == want
+    assert blob[n_proof:] == P.serialize_root(P.LcRoot(bytes(200 - i for i in range(32))))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind", ["ligero", "sdig"])
 def test_cpp_mirror_commit_prove_verify_equal_the_python_path(exe, kind):
