@@ -15,6 +15,11 @@ ncu --set full --clock-control none --import-source on -k regex:"ntt_pass|leaf_c
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 ncu --set full --clock-control none -k regex:"spmm_kernel|leaf_chunk|transpose_kernel|fused_levels" -s 11 -c 11 \
     -o gpurun_out/prof_brakedown24 python bench.py --workload brakedown --steps 1 --warmup 1 --no-cpu-baseline >> gpurun_out/ncu_full.log 2>&1
+# prove / verify kernels (collapse, check_columns, dot, expand_tensor, gathers) of one proof at the bench size
+ncu --set full --clock-control none -k regex:"collapse_kernel|check_columns|dot_kernel|expand_tensor|gather_|transpose_columns" -c 24 \
+    -o gpurun_out/prof_prove_verify python bench.py --steps 1 --warmup 1 --no-cpu-baseline >> gpurun_out/ncu_full.log 2>&1
+# host side of prove / verify: the transcript absorb per Keccak build on this box's CPU
+python tools/time_transcript.py > gpurun_out/time_transcript.txt 2>&1
 # pipe ceilings the design rests on
 for m in microbench microbench_fp64; do
   [ -x tools/$m ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/$m tools/$m.cu
