@@ -288,3 +288,33 @@ def test_oracle_dims_agree_with_the_reference_runs():
         n_rows, n_per_row, n_cols = enc.get_dims(1 << lgl)
         n_open, ndt, path_len = enc.get_n_col_opens(), enc.get_n_degree_tests(), (n_cols - 1).bit_length()
         assert 8 + (8 + n_per_row * 32) * (1 + ndt) + 16 + n_open * (16 + n_rows * 32 + path_len * 40) == want
+
+
+def test_wire_round_trip_on_random_shapes():
+    """Property test: any proof shape survives serialize -> deserialize, and the numpy writer equals the oracle's
+    element-by-element writer (hypothesis drives field, dims, number of degree tests / columns, path length)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.sampled_from([O.FT63, O.FT127, O.FT191, O.FT255]), st.integers(1, 9), st.integers(0, 3), st.integers(1, 6),
+           st.integers(1, 5), st.integers(0, 4), st.integers(0, 2**32 - 1))
+    def run(field, n_per_row, ndt, n_open, n_rows, path_len, seed):
+        rng = np.random.default_rng(seed)
+        L = O.FIELD_LIMBS[field]
+        u64 = lambda *shape: rng.integers(0, 2**64, size=shape, dtype=np.uint64)
+        p_eval, p_rand, cols = u64(n_per_row, L), u64(ndt, n_per_row, L), u64(n_open, n_rows, L)
+        paths = rng.integers(0, 256, size=(n_open, path_len, 32), dtype=np.uint8)
+        pf = P.LcEvalProof(field, int(rng.integers(1, 2**40)), p_eval, p_rand, cols, paths)
+        blob = P.serialize_proof(pf)
+        oracle_form = dict(n_cols=pf.n_cols, p_eval=p_eval, p_random_vec=list(p_rand), columns=[(cols[j], paths[j]) for j in range(n_open)])
+        assert blob == PR.wire_proof(oracle_form)
+        back = P.deserialize_proof(blob, field)
+        assert back.n_cols == pf.n_cols and (back.p_eval == p_eval).all() and (back.cols == cols).all()
+        assert back.p_random_vec.shape == p_rand.shape and (back.p_random_vec == p_rand).all()
+        assert back.paths.shape == paths.shape and (back.paths == paths).all()
+        for cut in (1, 8, len(blob) // 2):
+            if cut < len(blob):
+                with pytest.raises(P.LcpcError):
+                    P.deserialize_proof(blob[:-cut], field)
+
+    run()
