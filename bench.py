@@ -259,7 +259,11 @@ def run_ours(args):
                            "frac": ach / hbm_peak, "traffic": dk.get("traffic"), "peak_source": peak_src,
                            "launches_per_step": dk["launches_per_step"], "ms_per_launch": dk["ms_per_launch"],
                            "algorithmic_bytes_per_launch": dk["bytes_per_launch"],
-                           "note": "integer-pipe bound (256-bit Montgomery products), see DESIGN.md"}
+                           "note": ("integer-pipe bound (256-bit Montgomery products), see DESIGN.md"
+                                    if args.workload == "ligero" else
+                                    "bound by the L2 gather traffic of the sparse products (every input position is read "
+                                    "once per non-zero of its column: nnz x n_rows x B bytes through L2 per commit) and "
+                                    "by the multiplier pipe, not by HBM; see DESIGN.md")}
     if dk and args.workload == "ligero" and field == 4 and world == 1:
         # the roof that actually binds: Ft255 Montgomery products against the measured
         # IMAD.WIDE ceiling of 7.09e10 products/s/GPU (profiles/r01_microbench_int_pipes.txt)
