@@ -38,16 +38,18 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="ligero", choices=["ligero", "brakedown"])
+    ap.add_argument("--workload", default=None, choices=["ligero", "brakedown"],
+                    help="default: the Ligero/Ft255 headline line plus a Brakedown/Ft127 block in the same JSON line")
     ap.add_argument("--lgl", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
 def workload_desc(args):
-    if args.workload == "ligero":
-        return dict(field=4, name=f"lcpc-ligero-pc commit, Ft255, 2^{args.lgl} coeffs (rho=1/2, BLAKE3)")
-    return dict(field=2, name=f"lcpc-brakedown-pc commit, Ft127, 2^{args.lgl} coeffs (SdigCode3, seed 0, BLAKE3)")
+    if (args.workload or "ligero") == "ligero":
+        return dict(kind="ligero", field=4, name=f"lcpc-ligero-pc commit, Ft255, 2^{args.lgl} coeffs (rho=1/2, BLAKE3)")
+    return dict(kind="brakedown", field=2,
+                name=f"lcpc-brakedown-pc commit, Ft127, 2^{args.lgl} coeffs (SdigCode3, seed 0, BLAKE3)")
 
 
 def synthetic_coeffs(field, n, seed=0):
@@ -110,14 +112,18 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ CPU baseline (oracle = port of the reference)
-def cpu_commit_rate(args, seconds_budget=20.0):
+def cpu_commit_rate(args, seconds_budget=20.0, x=None, oenc=None):
     """Time the oracle's commit (row-parallel encode, 32-column hash tiles: the reference's decomposition)
-    on a bounded sample: the workload's own encoding (same n_per_row -> n_cols) over fewer rows."""
+    on a bounded sample: the workload's own encoding (same n_per_row -> n_cols) over the first rows of the
+    polynomial `x` (the GPU arm's own coefficients when given, so the sample's LcRoot doubles as the parity
+    check of the benchmarked commit).  Returns (baseline dict, rows in the sample, the sample's root)."""
     import oracle as O
     wl = workload_desc(args)
     field = wl["field"]
     n = 1 << args.lgl
-    if args.workload == "ligero":
+    if oenc is not None:
+        enc, npr = oenc, oenc.n_per_row
+    elif wl["kind"] == "ligero":
         _, npr, nc = O.ligero_get_dims(field, n)
         enc = O.Encoding.ligero_from_dims(field, npr, nc)
     else:
@@ -125,34 +131,49 @@ def cpu_commit_rate(args, seconds_budget=20.0):
         npr = enc.n_per_row
     n_rows_full = (n + npr - 1) // npr
     threads = O.max_threads()
-    # calibrate on 2 * threads rows, then size the sample for ~seconds_budget
+    if x is None:
+        x = synthetic_coeffs(field, n, seed=0)
+    # calibrate on a few rows, then size the sample for ~seconds_budget
     rows = min(n_rows_full, max(threads, 8))
-    x = synthetic_coeffs(field, rows * npr, seed=1)
     t0 = time.perf_counter()
-    enc.commit(x)
+    oc = enc.commit(x[:rows * npr])
     dt = time.perf_counter() - t0
     per_row = dt / rows
     rows2 = int(min(n_rows_full, max(rows, seconds_budget / max(per_row, 1e-9))))
-    rows2 = max(threads, rows2 - rows2 % threads) if rows2 >= threads else rows2
+    rows2 = max(threads, rows2 - rows2 % threads) if rows2 >= threads and rows2 < n_rows_full else rows2
     if rows2 > rows:
-        x = synthetic_coeffs(field, rows2 * npr, seed=2)
         t0 = time.perf_counter()
-        enc.commit(x)
+        oc = enc.commit(x[:rows2 * npr])
         dt = time.perf_counter() - t0
         rows = rows2
     # repeat the sample while the budget lasts (the whole workload fits it several times on a many-core host)
     times, spent = [dt], dt
     while spent + dt < seconds_budget and len(times) < 7:
         t0 = time.perf_counter()
-        enc.commit(x)
+        enc.commit(x[:rows * npr])
         times.append(time.perf_counter() - t0)
         spent += times[-1]
     dt = statistics.median(times)
-    coeffs = rows * npr
-    return dict(value=coeffs / dt, unit="field-elts/s", cores=threads, kind="port",
+    coeffs = min(rows * npr, x.shape[0])
+    base = dict(value=coeffs / dt, unit="field-elts/s", cores=threads, kind="port",
                 sample=f"{rows} of {n_rows_full} rows ({coeffs} coefficients) of the same {npr}->{enc.n_cols} "
                        f"encoding, median of {len(times)} commits, {dt:.2f} s each, C+OpenMP restatement of the reference CPU path "
-                       f"(Rust reference not buildable here)"), enc, npr
+                       f"(Rust reference not buildable here)")
+    return base, rows, oc["root"]
+
+
+def oracle_root(enc, field, x):
+    """LcRoot of the oracle's commit of `x` under the same encoding (checker leg; called by the N>1 arm on rank 0)."""
+    import oracle as O
+    if enc.__class__.__name__ == "LigeroEncoding":
+        oenc = O.Encoding.ligero_from_dims(field, enc.n_per_row, enc.n_cols)
+    else:
+        pre, post = enc.matrices()
+        oenc = O.Encoding.sdig_from_matrices(field, pre, post)
+    return oenc.commit(x)["root"]
+
+
+CONFIG_KEYS = ("workload", "n_rows", "n_per_row", "n_cols", "parallelism", "root_check", "l2", "timing")
 
 
 def run_reference(args):
@@ -161,27 +182,135 @@ def run_reference(args):
         return
     wl = workload_desc(args)
     import oracle as O
+    n = 1 << args.lgl
+    field = wl["field"]
+    if wl["kind"] == "ligero":
+        _, npr, nc = O.ligero_get_dims(field, n)
+        oenc = O.Encoding.ligero_from_dims(field, npr, nc)
+    else:
+        oenc = O.Encoding.sdig(field, n, seed=0)
+        npr, nc = oenc.n_per_row, oenc.n_cols
+    x = synthetic_coeffs(field, n, seed=0)
     rates = []
     base = None
     for i in range(args.warmup + args.steps):
         # each step: a bounded sample of the workload (seconds), see cpu_commit_rate
-        base, _, _ = cpu_commit_rate(args, seconds_budget=4.0)
+        base, _, _ = cpu_commit_rate(args, seconds_budget=4.0, x=x, oenc=oenc)
         if i >= args.warmup:
             rates.append(base["value"])
     value = statistics.median(rates)
     base["value"] = value
     out = {"metric": "committed field-elts/s", "value": value, "unit": "field-elts/s", "impl": "reference",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": (1 << args.lgl) / value * 1e3, "higher_is_better": True, "scaling": "strong",
+           "ms_per_step": n / value * 1e3, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "u64", "dtype_note": "64-bit limbs (unsigned __int128 products) on the host",
            "data": "synthetic",
-           "config": {"workload": wl["name"], "host_threads": O.max_threads()},
+           "config": {"workload": wl["name"], "n_rows": (n + npr - 1) // npr, "n_per_row": npr, "n_cols": nc,
+                      "parallelism": f"{O.max_threads()} host threads (OpenMP; row-parallel encode, 32-column hash tiles)",
+                      "root_check": "this arm is the checker the GPU arm's root_check compares with",
+                      "l2": "n/a (host)", "timing": "time.perf_counter around the oracle's commit"},
            "cpu_baseline": base,
            "e2e": {"value": value, "unit": "field-elts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
 
 # ------------------------------------------------------------------ our arm
+def load_peaks():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    if peaks.get("hbm_gbs"):
+        return peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_workload(args, kind, ctx, world, rank, torch, P, cpu_budget):
+    """One workload (kind = ligero | brakedown) on this process group; rank 0 gets the JSON object back."""
+    wargs = argparse.Namespace(**vars(args))
+    wargs.workload = kind
+    wl = workload_desc(wargs)
+    field, n = wl["field"], 1 << args.lgl
+    L = P.FIELD_LIMBS[field]
+    hbm_peak, peak_src = load_peaks()
+    if kind == "ligero":
+        enc = P.LigeroEncoding(field, n, ctx=ctx)
+    else:
+        enc = P.SdigEncoding(field, n, seed=0, ctx=ctx)
+    n_rows, n_per_row, n_cols = enc.get_dims(n)
+    if world > 1:
+        from lcpc_b200 import dist as D
+        result = D.bench_distributed(wargs, ctx, enc, field, n, synthetic_coeffs)
+    else:
+        result = bench_single(wargs, ctx, enc, field, n, torch, P, cpu_budget)
+    if rank != 0:
+        return None
+    B = 8 * L
+    np2 = 1 << (n_cols - 1).bit_length()
+    code_bytes = result.get("code_bytes", 0)
+    # SURVEY.md section 8(d): read the input once, write every output once (+ the code once, Brakedown)
+    algo_encode = B * n_rows * n_per_row + B * n_rows * n_cols + code_bytes
+    algo_commit = algo_encode + 32 * (2 * np2 - 1)
+    out = {"metric": "committed field-elts/s", "value": result["value"], "unit": "field-elts/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": result["ms_per_step"],
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "u32", "dtype_note": "32-bit limbs of Montgomery-form prime-field elements; BLAKE3 32-bit words",
+           "data": "synthetic",
+           "config": {"workload": wl["name"], "n_rows": n_rows, "n_per_row": n_per_row, "n_cols": n_cols,
+                      "parallelism": (f"row-block x{world}, exchange={result.get('transport')}, column-block hash"
+                                      if world > 1 else "1 GPU"),
+                      "root_check": result.get("root_check"),
+                      "l2": "inputs+outputs (>= 0.6 GiB at 2^24) exceed the 126 MB L2; no flush needed",
+                      "timing": "CUDA events on the engine stream, max over ranks"},
+           "e2e": result["e2e"], "gpu_launches": result["gpu_launches"], "clocks": result["clocks"],
+           "phases_ms": result.get("phases_ms"), "prove": result.get("prove"), "e2e_eager": result.get("e2e_eager"),
+           "roofline": None, "cpu_baseline": result.get("cpu_baseline")}
+    assert tuple(out["config"]) == CONFIG_KEYS
+    # roofline of the dominant kernel: ALGORITHMIC bytes of the encode phase (section 8(d): coefficients read once,
+    # codeword written once, code read once) over the phase's event-timed duration, per launch of the kernel that
+    # makes up the phase; what the launches really move is `traffic` (ncu dram bytes per launch, from the committed
+    # capture under profiles/ -- evidence copied from a profile, never a quantity measured in this run)
+    dk = result.get("dominant")
+    if dk:
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            key = f"{kind}_{FIELD_NAMES[field]}_2^{args.lgl}"
+            if key in tr and world == 1:
+                dk["traffic"] = tr[key]["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        per_gpu_algo = algo_encode / world
+        ach = per_gpu_algo / (dk["phase_ms"] * 1e-3) / 1e9
+        out["roofline"] = {"bound": "hbm", "kernel": dk["kernel"], "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": ach / hbm_peak, "traffic": dk.get("traffic"), "peak_source": peak_src,
+                           "launches_per_step": dk["launches_per_step"],
+                           "ms_per_launch": dk["phase_ms"] / dk["launches_per_step"],
+                           "algorithmic_bytes_per_launch": per_gpu_algo / dk["launches_per_step"],
+                           "moved_bytes_per_launch": dk.get("moved_bytes_per_launch"),
+                           "note": ("algorithmic bytes = coefficients read once + codeword written once (SURVEY 8d) over "
+                                    "the encode phase; the kernel is bound by the integer multiplier pipe (256-bit "
+                                    "Montgomery products), see `secondary` and DESIGN.md"
+                                    if kind == "ligero" else
+                                    "algorithmic bytes = coefficients + codeword + code once (SURVEY 8d) over the encode "
+                                    "phase; the sparse products gather nnz x n_rows x B bytes (6x the algorithmic bytes) "
+                                    "through L2, see DESIGN.md")}
+    if dk and kind == "ligero" and field == 4 and world == 1:
+        # the roof that actually binds (DESIGN.md section 3): Ft255 Montgomery products against the measured
+        # IMAD.WIDE ceiling of 7.09e10 products/s/GPU (profiles/r01_microbench_int_pipes.txt)
+        log_n = n_cols.bit_length() - 1
+        products = n_rows * (n_cols // 2) * (log_n - 3) + n_rows * (n_cols // 8) * 5  # last 3 stages: 5 per 8 points
+        enc_ms = result["phases_ms"]["encode"]
+        out["roofline"]["secondary"] = {"bound": "int32 multiplier pipe (IMAD.WIDE.U32)", "unit": "Ft255 products/s",
+                                        "achieved": products / (enc_ms * 1e-3), "peak": 7.09e10,
+                                        "frac": products / (enc_ms * 1e-3) / 7.09e10, "products_per_step": products,
+                                        "peak_source": "measured, tools/microbench.cu on this pool's B200"}
+    ach_c = algo_commit / (result["ms_per_step"] * 1e-3) / 1e9
+    out["roofline_commit"] = {"bound": "hbm", "algorithmic_bytes": algo_commit, "achieved": ach_c,
+                              "peak": hbm_peak * world, "unit": "GB/s", "frac": ach_c / (hbm_peak * world)}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -196,98 +325,25 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    wl = workload_desc(args)
-    field, n = wl["field"], 1 << args.lgl
-    L = P.FIELD_LIMBS[field]
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json hbm_gbs)") if peaks.get("hbm_gbs") else (6650.0, "fallback (B200_PROFILING.md)")
-
     ctx = P.Context(local_rank)
-    if args.workload == "ligero":
-        enc = P.LigeroEncoding(field, n, ctx=ctx)
-    else:
-        enc = P.SdigEncoding(field, n, seed=0, ctx=ctx)
-    n_rows, n_per_row, n_cols = enc.get_dims(n)
-
-    if world > 1:
-        from lcpc_b200 import dist as D
-        result = D.bench_distributed(args, ctx, enc, field, n, synthetic_coeffs)
-    else:
-        result = bench_single(args, ctx, enc, field, n, torch, P)
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    B = 8 * L
-    np2 = 1 << (n_cols - 1).bit_length()
-    algo_commit = B * n_rows * n_per_row + B * n_rows * n_cols + 32 * (2 * np2 - 1)
-    if args.workload == "brakedown":
-        algo_commit += result.get("code_bytes", 0)
-    out = {"metric": "committed field-elts/s", "value": result["value"], "unit": "field-elts/s", "n_gpus": world,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": result["ms_per_step"],
-           "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-           "dtype": "u32", "dtype_note": "32-bit limbs of Montgomery-form prime-field elements; BLAKE3 32-bit words",
-           "data": "synthetic",
-           "config": {"workload": wl["name"], "n_rows": n_rows, "n_per_row": n_per_row, "n_cols": n_cols,
-                      "parallelism": (f"row-block x{world}, exchange={result.get('transport')}, column-block hash"
-                                      if world > 1 else "1 GPU"),
-                      "root_check": result.get("root_check"),
-                      "l2": "inputs+outputs (>= 1.5 GiB at 2^24) exceed the 126 MB L2; no flush needed",
-                      "timing": "CUDA events on the engine stream, max over ranks"},
-           "e2e": result["e2e"], "gpu_launches": result["gpu_launches"], "clocks": result["clocks"],
-           "phases_ms": result.get("phases_ms"), "prove": result.get("prove"), "e2e_eager": result.get("e2e_eager"),
-           "roofline": None, "cpu_baseline": None}
-    # roofline of the dominant kernel (per launch) + of the whole commit
-    dk = result.get("dominant")
-    if dk:
-        # dram bytes per launch of the same kernel from the committed `ncu --set full` capture (profiles/), if one
-        # exists for this workload; it is evidence copied from a profile, never a quantity measured in this run
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            key = f"{args.workload}_{FIELD_NAMES[field]}_2^{args.lgl}"
-            if key in tr and world == 1:
-                dk["traffic"] = tr[key]["dram_bytes_per_launch"]
-        except Exception:
-            pass
-        ach = dk["bytes_per_launch"] / (dk["ms_per_launch"] * 1e-3) / 1e9
-        out["roofline"] = {"bound": "hbm", "kernel": dk["kernel"], "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                           "frac": ach / hbm_peak, "traffic": dk.get("traffic"), "peak_source": peak_src,
-                           "launches_per_step": dk["launches_per_step"], "ms_per_launch": dk["ms_per_launch"],
-                           "algorithmic_bytes_per_launch": dk["bytes_per_launch"],
-                           "note": ("integer-pipe bound (256-bit Montgomery products), see DESIGN.md"
-                                    if args.workload == "ligero" else
-                                    "bound by the L2 gather traffic of the sparse products (every input position is read "
-                                    "once per non-zero of its column: nnz x n_rows x B bytes through L2 per commit) and "
-                                    "by the multiplier pipe, not by HBM; see DESIGN.md")}
-    if dk and args.workload == "ligero" and field == 4 and world == 1:
-        # the roof that actually binds: Ft255 Montgomery products against the measured
-        # IMAD.WIDE ceiling of 7.09e10 products/s/GPU (profiles/r01_microbench_int_pipes.txt)
-        log_n = n_cols.bit_length() - 1
-        products = n_rows * (n_cols // 2) * (log_n - 3) + n_rows * (n_cols // 8) * 5  # last 3 stages: 5 per 8 points
-        enc_ms = result["phases_ms"]["encode"]
-        out["roofline"]["secondary"] = {"bound": "int32 multiplier pipe (IMAD.WIDE.U32)", "unit": "Ft255 products/s",
-                                        "achieved": products / (enc_ms * 1e-3), "peak": 7.09e10,
-                                        "frac": products / (enc_ms * 1e-3) / 7.09e10, "products_per_step": products,
-                                        "peak_source": "measured, tools/microbench.cu on this pool's B200"}
-    ach_c = algo_commit / (result["ms_per_step"] * 1e-3) / 1e9
-    out["roofline_commit"] = {"bound": "hbm", "algorithmic_bytes": algo_commit, "achieved": ach_c,
-                              "peak": hbm_peak * world, "unit": "GB/s", "frac": ach_c / (hbm_peak * world)}
-    if world == 1 and not args.no_cpu_baseline:
-        try:
-            out["cpu_baseline"] = cpu_commit_rate(args)[0]
-        except Exception as e:  # the checker is optional for the number, never for the tests
-            out["cpu_baseline"] = {"error": repr(e)}
-    print(json.dumps(out), flush=True)
+    # default run: the headline line (Ligero/Ft255) carries a second block for the other half of BASELINE.json's
+    # metric (Brakedown/Ft127 at the same 2^lgl), measured by the same code in the same process
+    kinds = [args.workload] if args.workload else ["ligero", "brakedown"]
+    no_cpu = args.no_cpu_baseline or world > 1
+    out = run_workload(args, kinds[0], ctx, world, rank, torch, P, 0.0 if no_cpu else 18.0)
+    for kind in kinds[1:]:
+        sub = run_workload(args, kind, ctx, world, rank, torch, P, 0.0 if no_cpu else 8.0)
+        if rank == 0:
+            keep = ("value", "unit", "ms_per_step", "config", "e2e", "gpu_launches", "phases_ms", "roofline",
+                    "roofline_commit", "cpu_baseline", "prove")
+            out[kind] = {k: sub[k] for k in keep if k in sub}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def bench_single(args, ctx, enc, field, n, torch, P):
+def bench_single(args, ctx, enc, field, n, torch, P, cpu_budget=0.0):
     L = P.FIELD_LIMBS[field]
     n_rows, n_per_row, n_cols = enc.get_dims(n)
     if n >= (1 << 25):
@@ -299,6 +355,7 @@ def bench_single(args, ctx, enc, field, n, torch, P):
         host = torch.empty((n, L), dtype=torch.int64, pin_memory=True)
         host.copy_(dev)
         torch.cuda.synchronize()
+        x = host.numpy().view(np.uint64)
     else:
         x = synthetic_coeffs(field, n, seed=0)
         host = torch.from_numpy(x.view(np.int64)).pin_memory()
@@ -415,27 +472,53 @@ def bench_single(args, ctx, enc, field, n, torch, P):
     ms_per_step = total_ms / args.steps
     B = 8 * L
     if enc.__class__.__name__ == "LigeroEncoding":
-        per_pass = []
         n_pass = max(1, nl[0])
-        # pass 1 reads the coefficient rows, writes the commit's own copy of them (the pad/copy of the reference,
-        # folded into the pass) and writes comm; later passes read + write comm
-        per_pass.append(B * n_rows * (2 * n_per_row + n_cols))
-        for _ in range(n_pass - 1):
-            per_pass.append(2 * B * n_rows * n_cols)
-        dominant = dict(kernel="ntt_pass_kernel", launches_per_step=n_pass, ms_per_launch=phases[1] / n_pass,
-                        bytes_per_launch=sum(per_pass) / n_pass, traffic=None)
+        # what the passes move: pass 1 reads the coefficient rows, writes the commit's own copy of them (the pad/copy
+        # of the reference, folded into the pass) and writes comm; later passes read + write comm
+        moved = B * n_rows * (2 * n_per_row + n_cols) + (n_pass - 1) * 2 * B * n_rows * n_cols
+        dominant = dict(kernel=f"ntt_pass_kernel (encode phase = {n_pass} launches)", launches_per_step=n_pass,
+                        phase_ms=phases[1], moved_bytes_per_launch=moved / n_pass, traffic=None)
         code_bytes = 0
     else:
-        from lcpc_b200 import _cabi  # noqa: F401
         nnz = sum(int(m["ptrs"][-1]) for mats in enc.matrices() for m in mats)
         code_bytes = nnz * (B + 4)
-        # the expander phase = transposes + SpMM chain; algorithmic bytes: coefficients in, codeword out, code once
-        dominant = dict(kernel="expander phase (spmm_kernel + transposes)", launches_per_step=nl[0],
-                        ms_per_launch=phases[1] / max(1, nl[0]),
-                        bytes_per_launch=(B * n_rows * (n_per_row + n_cols) + code_bytes) / max(1, nl[0]), traffic=None)
+        # the expander phase = transposes + SpMM chain
+        dominant = dict(kernel=f"spmm_kernel chain + transposes (encode phase = {nl[0]} launches)",
+                        launches_per_step=max(1, nl[0]), phase_ms=phases[1],
+                        moved_bytes_per_launch=None, traffic=None)
+    # parity at the benchmarked size: the oracle (CPU restatement of the reference) commits the SAME coefficients --
+    # as many leading rows of them as its time budget allows -- and the LcRoots must be equal.  The timing of that
+    # oracle run is the cpu_baseline.
+    cpu_baseline, root_check = None, None
+    if cpu_budget > 0:
+        try:
+            wargs = argparse.Namespace(**vars(args))
+            oenc = None
+            if enc.__class__.__name__ != "LigeroEncoding":
+                import oracle as O
+                pre, post = enc.matrices()
+                oenc = O.Encoding.sdig_from_matrices(field, pre, post)  # the same code, no second generator run
+            cpu_baseline, rows, oroot = cpu_commit_rate(wargs, cpu_budget, x=x, oenc=oenc)
+            if rows >= n_rows:
+                ok = oroot == root0.root
+                root_check = ("equals the oracle's LcRoot (all %d rows, same coefficients)" % n_rows) if ok else "MISMATCH"
+            else:
+                part = P.LcCommit.commit(np.ascontiguousarray(x[:rows * n_per_row]), enc)
+                ok = part.get_root().root == oroot
+                part.close()
+                root_check = (("equals the oracle's LcRoot on the first %d of %d rows of the same coefficients (the "
+                               "oracle's time budget), full commit deterministic across %d runs") % (rows, n_rows, args.steps)
+                              if ok else "MISMATCH")
+            assert ok, "LcRoot differs from the oracle's"
+        except AssertionError:
+            raise
+        except Exception as e:  # the checker is optional for the number, never for the tests
+            cpu_baseline = {"error": repr(e)}
+    commit.close()
     return dict(value=n / (ms_per_step * 1e-3), ms_per_step=ms_per_step, gpu_launches=int(launches),
                 clocks=clocks, phases_ms=dict(zip(["pad_copy", "encode", "leaf_hash", "merkle"], phases.tolist())),
-                dominant=dominant, code_bytes=code_bytes, prove=prove, e2e_eager=eager,
+                dominant=dominant, code_bytes=code_bytes, prove=prove, e2e_eager=eager, root_check=root_check,
+                cpu_baseline=cpu_baseline,
                 e2e={"value": n / e2e_s, "unit": "field-elts/s", "h2d_bytes_per_step": int(n * B), "d2h_bytes_per_step": 32,
                      "ms_per_step": e2e_s * 1e3, "mode": "device-resident LcCommit; host receives the LcRoot"})
 

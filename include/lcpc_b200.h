@@ -63,6 +63,10 @@ typedef struct lcpc_b200_commit lcpc_b200_commit; /* device-resident LcCommit (l
 
 /* ---- library / context ---- */
 const char *lcpc_b200_version(void);
+/* Schedule knobs for A/B measurements (never change results): `name` without the LCPC_B200_ prefix of the
+ * equivalent environment variable, e.g. "SPMM_WINDOW_KB".  A set value wins over the environment. */
+int lcpc_b200_set_tunable(const char *name, long value);
+long lcpc_b200_get_tunable(const char *name, long dflt);
 /* number of u64 limbs of a field (1,2,3,4) or -1 */
 int lcpc_b200_field_limbs(int field);
 /* Field::one() as stored: R mod p, L u64 limbs (ff_derive's R constant); host-only, no device needed */

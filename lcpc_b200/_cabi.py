@@ -61,6 +61,8 @@ _pvp, _psz = C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)
 # name -> (restype, argtypes); mirrors include/lcpc_b200.h and include/lcpc_b200_host.h one to one
 SIGNATURES = {
     "lcpc_b200_version": (C.c_char_p, []),
+    "lcpc_b200_set_tunable": (_i, [C.c_char_p, C.c_long]),
+    "lcpc_b200_get_tunable": (C.c_long, [C.c_char_p, C.c_long]),
     "lcpc_b200_field_limbs": (_i, [_i]),
     "lcpc_b200_field_one": (_i, [_i, _vp]),
     "lcpc_b200_ctx_create": (_i, [_i, _pvp]),

@@ -200,6 +200,13 @@ static int return_poly(lcpc_b200_commit *c, uint64_t *poly);
 
 const char *lcpc_b200_version(void) { return "lcpc_b200 0.1 (sm_100a)"; }
 
+int lcpc_b200_set_tunable(const char *name, long value) {
+  if (!name || !*name) return LCPC_B200_ERR_BAD_ARG;
+  set_tunable(name, value);
+  return LCPC_B200_OK;
+}
+long lcpc_b200_get_tunable(const char *name, long dflt) { return name ? tunable(name, dflt) : dflt; }
+
 int lcpc_b200_field_limbs(int field) {
   int n = field_limbs32(field);
   return n < 0 ? -1 : n / 2;
@@ -223,8 +230,13 @@ int lcpc_b200_ctx_create(int device, lcpc_b200_ctx **out) {
   lcpc_b200_ctx *ctx = new (std::nothrow) lcpc_b200_ctx;
   if (!ctx) return LCPC_B200_ERR_OOM;
   ctx->device = device;
-  bool ok = cudaSetDevice(device) == cudaSuccess &&
-            cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+  bool ok = cudaSetDevice(device) == cudaSuccess;
+  if (ok) {
+    // A/B knob: L2 set-aside for persisting (evict_last) lines, in MiB; 0 leaves the device default
+    const long mb = tunable("L2_PERSIST_MB", 0);
+    if (mb > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)mb << 20) != cudaSuccess) cudaGetLastError();
+  }
+  ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&ctx->begin_ev, cudaEventDisableTiming) == cudaSuccess &&
@@ -695,11 +707,7 @@ static int commit_run(lcpc_b200_commit *c, const void *src, size_t len, cudaMemc
     // 2^24: 1/4/8/16 chunks = 5.63/5.72/5.90/6.14 ms -- the transform CTAs hold every register of the SM, so the
     // hash CTAs cannot co-reside and the extra launch tails cost more than the overlap gains.  Default: 1.
     CU(ctx, cudaEventRecord(c->ev[1], st));
-    static const size_t want_chunks = [] {
-      const char *e = getenv("LCPC_B200_DEV_CHUNKS");
-      long v = e ? atol(e) : 1;
-      return (size_t)std::min<long>(std::max<long>(v, 1), lcpc_b200_ctx::MAX_CHUNKS);
-    }();
+    const size_t want_chunks = (size_t)std::min<long>(std::max<long>(tunable("DEV_CHUNKS", 1), 1), lcpc_b200_ctx::MAX_CHUNKS);
     const size_t N = B / 4;
     size_t n_rc = trail.n_chunks > 1 ? std::min(want_chunks, c->n_rows) : 1;
     while (n_rc > 1 && (c->n_rows / n_rc) * c->n_cols * B < ((size_t)32 << 20)) n_rc--;
@@ -1137,6 +1145,36 @@ void sample_columns(const uint8_t key[32], size_t n_cols, size_t n, uint64_t *ou
   for (size_t i = 0; i < n; i++) out[i] = rng.below(n_cols);
 }
 
+// index of the first element whose limbs are not < p, or (size_t)-1
+size_t first_noncanonical(int field, const uint64_t *v, size_t n, size_t L) {
+  uint64_t p[4] = {0, 0, 0, 0};
+  {
+    uint32_t p32[8] = {0};
+    const int N = field_limbs32(field);
+    for (int i = 0; i < N; i++) {
+      switch (field) {
+        case FT63: p32[i] = FieldP<FT63>::P(i); break;
+        case FT127: p32[i] = FieldP<FT127>::P(i); break;
+        case FT191: p32[i] = FieldP<FT191>::P(i); break;
+        default: p32[i] = FieldP<FT255>::P(i); break;
+      }
+    }
+    for (size_t l = 0; l < L; l++) p[l] = (uint64_t)p32[2 * l] | ((uint64_t)p32[2 * l + 1] << 32);
+  }
+  for (size_t i = 0; i < n; i++) {
+    const uint64_t *e = v + i * L;
+    bool less = false;
+    for (size_t l = L; l-- > 0;) {
+      if (e[l] != p[l]) {
+        less = e[l] < p[l];
+        break;
+      }
+    }
+    if (!less) return i;
+  }
+  return (size_t)-1;
+}
+
 }  // namespace
 
 int lcpc_b200_sample_columns(const uint8_t key[32], size_t n_cols, size_t n, uint64_t *out) {
@@ -1226,9 +1264,28 @@ int lcpc_b200_verify(lcpc_b200_enc *enc, lcpc_b200_transcript *tr, const lcpc_b2
   if (proof->n_degree_tests != n_degree_tests || n_rows == 0 || !outer_tensor || !inner_tensor || !proof->p_eval ||
       (n_degree_tests && !proof->p_random) || !proof->cols || (proof->path_len && !proof->paths) || proof->path_len > 64)
     return fail(ctx, LCPC_B200_ERR_BAD_ARG, "verify: malformed proof");
+  // The proof comes from the other side of a trust boundary: every field element in it must be a canonical residue
+  // (limbs < p).  The device arithmetic assumes it (field.cuh: `2p < 2^(32N)`, no carry out of add/sub), and
+  // from_mont maps v and v + p to the same transcript bytes, so a non-canonical element would be both a malleable
+  // proof and an encode input outside the kernels' precondition.  (The reference's derived Deserialize does not
+  // check either; rejecting is the stricter, safe reading.)
+  const int field = enc->field;
+  {
+    const size_t L = field_bytes(field) / 8;
+    const size_t bad_pr = first_noncanonical(field, proof->p_random, n_degree_tests * n_per_row, L);
+    const size_t bad_pe = first_noncanonical(field, proof->p_eval, n_per_row, L);
+    const size_t bad_col = first_noncanonical(field, proof->cols, n_open * n_rows, L);
+    if (bad_pr != (size_t)-1 || bad_pe != (size_t)-1 || bad_col != (size_t)-1)
+      return fail(ctx, LCPC_B200_ERR_BAD_ARG, "verify: non-canonical field element in the proof (%s[%zu] >= p)",
+                  bad_pr != (size_t)-1 ? "p_random" : bad_pe != (size_t)-1 ? "p_eval" : "columns",
+                  bad_pr != (size_t)-1 ? bad_pr : bad_pe != (size_t)-1 ? bad_pe : bad_col);
+  }
+  // a Merkle path has exactly log2(n_cols.next_power_of_two()) siblings (open_column, :811-821); any other length
+  // cannot lead from a leaf to the root of the committed tree
+  if (proof->path_len != log2_ceil(n_cols))
+    return fail(ctx, LCPC_B200_VERR_COLUMN_PATH, "merkle path length %zu, expected %u", (size_t)proof->path_len, log2_ceil(n_cols));
   if (int rc = bind_device(ctx)) return rc;
   const Labels lb = resolve_labels(labels);
-  const int field = enc->field;
   const size_t B = field_bytes(field), T = n_degree_tests + 1;
   const unsigned path_len = (unsigned)proof->path_len;
 

@@ -9,6 +9,11 @@
 
 namespace lcpc {
 
+// named integer knobs for A/B measurements (tunables.cpp): set value > LCPC_B200_<NAME> > dflt
+long tunable(const char *name, long dflt);
+void set_tunable(const char *name, long value);
+void clear_tunable(const char *name);
+
 int field_limbs32(int field);  // 2/4/6/8, or -1
 inline size_t field_bytes(int field) { return 4 * (size_t)field_limbs32(field); }
 

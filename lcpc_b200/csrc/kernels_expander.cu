@@ -34,8 +34,12 @@ constexpr int MAX_FUSED_OPS = 16;
 struct DeviceCsr {
   size_t m = 0, n = 0, nnz = 0;
   uint32_t *rowptr = nullptr;  // m + 1
-  uint32_t *colidx = nullptr;  // nnz
+  uint32_t *colidx = nullptr;  // nnz, ascending within a row
   uint32_t *vals = nullptr;    // nnz * N limbs
+  // column-chunked schedule (see spmm_kernel): seg[q * m + i] = first non-zero of row i whose column is >= q * n / seg_q,
+  // q = 0 .. seg_q; built on first use for a given chunk count and kept
+  mutable uint32_t *seg = nullptr;
+  mutable unsigned seg_q = 0;
 };
 
 struct ExpanderOp {
@@ -65,6 +69,7 @@ void expander_free(ExpanderCode *c) {
     cudaFree(m.rowptr);
     cudaFree(m.colidx);
     cudaFree(m.vals);
+    cudaFree(m.seg);
   }
   delete c;
 }
@@ -231,6 +236,29 @@ __device__ __forceinline__ void ldv_early(uint32_t (&v)[N], const uint32_t *p) {
       asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v[2 * i]), "=r"(v[2 * i + 1]) : "l"(p + 2 * i));
   }
 }
+// the same with an L2 eviction policy (createpolicy): the gathered work-buffer window is asked to stay (evict_last),
+// the matrix stream (values, column indices) to leave first
+template <int N>
+__device__ __forceinline__ void ldv_early_pol(uint32_t (&v)[N], const uint32_t *p, uint64_t pol) {
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 4; i++)
+      asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                   : "=r"(v[4 * i]), "=r"(v[4 * i + 1]), "=r"(v[4 * i + 2]), "=r"(v[4 * i + 3])
+                   : "l"(p + 4 * i), "l"(pol));
+  } else {
+#pragma unroll
+    for (int i = 0; i < N / 2; i++)
+      asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;"
+                   : "=r"(v[2 * i]), "=r"(v[2 * i + 1])
+                   : "l"(p + 2 * i), "l"(pol));
+  }
+}
+__device__ __forceinline__ uint32_t ld_u32_pol(const uint32_t *p, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
 template <int N>
 __device__ __forceinline__ void stv(uint32_t *p, const uint32_t (&v)[N]) {
   if constexpr (N % 4 == 0) {
@@ -317,24 +345,37 @@ scatter_rows_kernel(const uint32_t *__restrict__ src, size_t src_ld, size_t src_
 // y[i][r] = sum_k vals[k] * x[colidx[k]][r]; one thread per (output i, batch row r), r fastest.
 // The sum is kept double-width and Montgomery-reduced once per output (field.cuh, mac_wide / redc):
 // a sparse row has 8..45 terms, so this halves the multiplier work against reduce-every-product.
-// The gathers are the latency that matters (random positions of a work buffer far larger than L1), so
-// the loop issues SPMM_UNROLL index loads, then that many gathers, before the first multiply.  A launch
-// covers the batch rows [r0, r0 + rg) (normally all of them, see encode_impl).
+// The gathers are what matters: every input position is read once per non-zero of its column, at random, so the
+// chain pulls nnz * n_rows * B bytes (6x the algorithmic bytes of the encode) through L2 -- and from DRAM as well
+// unless the gathered window of the work buffer stays L2-resident (round 1: 1.62 GB of DRAM reads per big level,
+// 19 % L2 hits).  Two measures keep it resident:
+//  * HINT: gathers carry an evict_last L2 policy, the matrix stream (values, indices) evict_first, so that the
+//    window is not pushed out by data that is used once;
+//  * column chunks: a level whose window n * n_rows * B exceeds the L2 budget runs as Q launches, launch q
+//    covering the non-zeros with columns in [q n/Q, (q+1) n/Q) (the rows are column-sorted, `seg` holds the
+//    cut points) and ACCUMulating onto y: y = y + REDC(partial sum), exact mod p, so the result is the same
+//    canonical element.  Each window chunk then comes from DRAM once.
+// The loop issues SPMM_UNROLL index loads, then that many gathers, before the first multiply.
 // __launch_bounds__(256, 4) is what makes ptxas keep all eight 16-byte loads of a batch in front of the first
 // product (64 registers); left to itself it settles on 48 registers and sinks each load next to its use, which
-// measured 6 % slower on the 2^24 chain.
-// Wider elements (Ft191, Ft255) batch two deep under a 128-register budget instead.
-template <int FID>
+// measured 6 % slower on the 2^24 chain.  Wider elements (Ft191, Ft255) batch two deep under a 128-register budget.
+template <int FID, bool HINT, bool ACCUM>
 __global__ void __launch_bounds__(256, (Field<FID>::N <= 4 ? 4 : 2))
-spmm_kernel(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ colidx, const uint32_t *__restrict__ vals,
-            const uint32_t *__restrict__ x, uint32_t *__restrict__ y, size_t m, size_t n_rows, unsigned r0, unsigned rg) {
+spmm_kernel(const uint32_t *__restrict__ seg_lo, const uint32_t *__restrict__ seg_hi, const uint32_t *__restrict__ colidx,
+            const uint32_t *__restrict__ vals, const uint32_t *__restrict__ x, uint32_t *__restrict__ y, size_t m,
+            size_t n_rows, unsigned r0, unsigned rg, float keep_frac) {
   using F = Field<FID>;
   constexpr int N = F::N;
   constexpr int SPMM_UNROLL = N <= 4 ? 4 : 2;
   const size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= m * rg) return;
   const size_t i = item / rg, r = r0 + item % rg;
-  const uint32_t k0 = __ldg(rowptr + i), k1 = __ldg(rowptr + i + 1);
+  const uint32_t k0 = __ldg(seg_lo + i), k1 = __ldg(seg_hi + i);
+  uint64_t pol_keep = 0, pol_stream = 0;
+  if (HINT) {
+    asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(pol_keep) : "f"(keep_frac));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  }
   typename F::Wide acc = F::wide_zero();
   // address arithmetic kept off the multiplier pipe: one 32x32->64 product per gather, pointer bumps elsewhere
   const uint32_t *xr = x + r * N;
@@ -346,11 +387,16 @@ spmm_kernel(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ co
     uint32_t j[SPMM_UNROLL];
     typename F::Elem a[SPMM_UNROLL], xv[SPMM_UNROLL];
 #pragma unroll
-    for (int u = 0; u < SPMM_UNROLL; u++) j[u] = __ldg(cp + u);
+    for (int u = 0; u < SPMM_UNROLL; u++) j[u] = HINT ? ld_u32_pol(cp + u, pol_stream) : __ldg(cp + u);
 #pragma unroll
     for (int u = 0; u < SPMM_UNROLL; u++) {
-      ldv_early<N>(xv[u].v, xr + (size_t)j[u] * pos_stride);
-      ldv_early<N>(a[u].v, vp + u * N);
+      if (HINT) {
+        ldv_early_pol<N>(xv[u].v, xr + (size_t)j[u] * pos_stride, pol_keep);
+        ldv_early_pol<N>(a[u].v, vp + u * N, pol_stream);
+      } else {
+        ldv_early<N>(xv[u].v, xr + (size_t)j[u] * pos_stride);
+        ldv_early<N>(a[u].v, vp + u * N);
+      }
     }
 #pragma unroll
     for (int u = 0; u < SPMM_UNROLL; u++) F::mac_wide(acc, a[u], xv[u]);
@@ -359,11 +405,36 @@ spmm_kernel(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ co
     const uint32_t j = __ldg(cp);
     typename F::Elem a, xv;
     ldv<N>(a.v, vp);
-    ldv<N>(xv.v, xr + (size_t)j * pos_stride);
+    if (HINT) ldv_early_pol<N>(xv.v, xr + (size_t)j * pos_stride, pol_keep);
+    else ldv<N>(xv.v, xr + (size_t)j * pos_stride);
     F::mac_wide(acc, a, xv);
   }
   typename F::Elem out = F::template redc<2>(acc);
-  stv<N>(y + (i * n_rows + r) * N, out.v);
+  uint32_t *yp = y + (i * n_rows + r) * N;
+  if (ACCUM) {
+    typename F::Elem prev;
+    ldv<N>(prev.v, yp);
+    out = F::add(out, prev);
+  }
+  stv<N>(yp, out.v);
+}
+
+// seg[q * m + i] = first k in [rowptr[i], rowptr[i+1]) with colidx[k] >= q * n / Q  (q = 0 .. Q)
+__global__ void __launch_bounds__(256)
+spmm_segments_kernel(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ colidx, size_t m, size_t n,
+                     unsigned Q, uint32_t *__restrict__ seg) {
+  const size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= m * (Q + 1)) return;
+  const size_t q = item / m, i = item % m;
+  uint32_t lo = rowptr[i], hi = rowptr[i + 1];
+  const uint32_t bound = (uint32_t)(q * n / Q);
+  if (q == Q) lo = hi;
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (colidx[mid] < bound) lo = mid + 1;
+    else hi = mid;
+  }
+  seg[q * m + i] = lo;
 }
 
 // reed_solomon (encode.rs:97-110): out[k][r] = Horner of in[.][r] at the point k+1
@@ -564,22 +635,45 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
       const DeviceCsr &M = c->mats[op.mat];
       const uint32_t *x = W + op.in_off * n_rows * N;
       uint32_t *y = op.out_tmp ? T : W + op.out_off * n_rows * N;
-      // batch rows per launch.  Splitting a level so that the gathered slice x[0..n)[r0..r0+rg) fits in L2 was
-      // measured (24/48/96 MB slices: 1.59/1.54/1.45 ms encode at 2^24) and lost to one launch over all rows
-      // (1.40 ms), so the default is no split; LCPC_B200_SPMM_SLICE_MB keeps the knob for other shapes.
+      // Schedule of this level (all knobs are A/B tunables, see tunables.cpp; none changes the result):
+      //   SPMM_HINTS      1: L2 policies on the gathers / the matrix stream (default), 0: plain loads
+      //   SPMM_WINDOW_KB  L2 budget for the gathered window; a larger window runs as column chunks (0: never)
+      //   SPMM_SLICE_KB   round-1 alternative: split the BATCH rows so that the slice fits (0: off)
+      const bool hints = tunable("SPMM_HINTS", 1) != 0;
+      const size_t cap = (size_t)std::max<long>(0, tunable("SPMM_WINDOW_KB", 56 << 10)) << 10;
+      const size_t slice_cap = (size_t)std::max<long>(0, tunable("SPMM_SLICE_KB", 0)) << 10;
+      const size_t window = M.n * n_rows * F::BYTES;
       size_t rg = n_rows;
-      static const size_t slice_cap = [] {
-        const char *e = getenv("LCPC_B200_SPMM_SLICE_MB");
-        size_t mb = e ? (size_t)atol(e) : 0;
-        return mb ? mb << 20 : ~(size_t)0;
-      }();
-      if (M.n * n_rows * F::BYTES > slice_cap) rg = std::max<size_t>(8, slice_cap / (M.n * F::BYTES));
-      rg = std::min(rg, n_rows);
-      for (size_t r0 = 0; r0 < n_rows && M.m; r0 += rg) {
-        const size_t cnt = std::min(rg, n_rows - r0), items = M.m * cnt;
-        spmm_kernel<FID><<<(unsigned)((items + 255) / 256), 256, 0, st>>>(M.rowptr, M.colidx, M.vals, x, y, M.m, n_rows,
-                                                                          (unsigned)r0, (unsigned)cnt);
+      unsigned Q = 1;
+      if (slice_cap && window > slice_cap) rg = std::min(n_rows, std::max<size_t>(8, slice_cap / (M.n * F::BYTES)));
+      else if (cap && window > cap) Q = (unsigned)std::min<size_t>((window + cap - 1) / cap, 16);
+      if (Q > 1 && (M.seg_q != Q || !M.seg)) {  // cut points, once per (matrix, chunk count)
+        if (M.seg) cudaFree(M.seg);
+        M.seg = nullptr, M.seg_q = 0;
+        cudaError_t e = cudaMalloc(&M.seg, (size_t)(Q + 1) * M.m * 4);
+        if (e != cudaSuccess) return e;
+        const size_t items = M.m * (Q + 1);
+        spmm_segments_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(M.rowptr, M.colidx, M.m, M.n, Q, M.seg);
+        M.seg_q = Q;
         launches++;
+      }
+      const size_t eff_window = Q > 1 ? window / Q : (rg < n_rows ? M.n * rg * F::BYTES : window);
+      const float keep = (!cap || eff_window <= cap) ? 1.0f : (float)((double)cap / (double)eff_window);
+      for (unsigned q = 0; q < Q; q++) {
+        const uint32_t *lo = Q > 1 ? M.seg + (size_t)q * M.m : M.rowptr;
+        const uint32_t *hi = Q > 1 ? M.seg + (size_t)(q + 1) * M.m : M.rowptr + 1;
+        for (size_t r0 = 0; r0 < n_rows && M.m; r0 += rg) {
+          const size_t cnt = std::min(rg, n_rows - r0), items = M.m * cnt;
+          const unsigned grid = (unsigned)((items + 255) / 256);
+#define LCPC_SPMM_LAUNCH(H, A) \
+  spmm_kernel<FID, H, A><<<grid, 256, 0, st>>>(lo, hi, M.colidx, M.vals, x, y, M.m, n_rows, (unsigned)r0, (unsigned)cnt, keep)
+          if (hints && q) LCPC_SPMM_LAUNCH(true, true);
+          else if (hints) LCPC_SPMM_LAUNCH(true, false);
+          else if (q) LCPC_SPMM_LAUNCH(false, true);
+          else LCPC_SPMM_LAUNCH(false, false);
+#undef LCPC_SPMM_LAUNCH
+          launches++;
+        }
       }
     } else {
       size_t items = op.out_len * n_rows;

@@ -442,7 +442,8 @@ static cudaError_t ntt_rows_impl(const uint32_t *src, size_t src_stride, size_t 
   if (!attr_set) {
     // tile + (last pass) up to 2^(LOG_TILE-1) twiddles
     cudaError_t e = cudaFuncSetAttribute(ntt_pass_kernel<FID>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(SmemLayout<F::N>::bytes(1u << LOG_TILE) + ((size_t)1 << (LOG_TILE - 1)) * F::BYTES));
+                                         (int)(SmemLayout<F::N>::bytes(1u << LOG_TILE) + ((size_t)1 << (LOG_TILE - 1)) * F::BYTES +
+                                               (64u << 10)));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -481,6 +482,8 @@ static cudaError_t ntt_rows_impl(const uint32_t *src, size_t src_stride, size_t 
     size_t grid = n_rows << p.tiles_per_row_log;
     if (grid > 0x7fffffffu) return cudaErrorInvalidValue;
     size_t smem = SmemLayout<F::N>::bytes(1u << (S + logC)) + (last ? ((size_t)1 << (S - 1)) * F::BYTES : 0);
+    // A/B knob: unused shared memory that lowers the CTAs per SM (e.g. to leave registers for a co-resident hash kernel)
+    smem += (size_t)std::min<long>(64, std::max<long>(0, tunable("NTT_SMEM_PAD_KB", 0))) << 10;
     ntt_pass_kernel<FID><<<(unsigned)grid, NTT_THREADS, smem, stream>>>(cur_src, dst, roots, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

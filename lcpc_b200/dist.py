@@ -509,8 +509,9 @@ def bench_distributed(args, ctx, enc, field, n, synthetic_coeffs):
     assert r == root0
     ms_per_step = float(ms.item()) / args.steps
     e2e_s = float(e2e.item())
-    # parity at the benchmarked size: the sharded commit's LcRoot == the single-GPU commit of the same polynomial
-    # (which the parity tests hold to the oracle).  Rank 0 rebuilds every rank's slice; skipped beyond 2^24.
+    # parity at the benchmarked size: the sharded commit's LcRoot == the single-GPU commit of the same polynomial ==
+    # the oracle's commit of it (bench.py's checker leg; the product never imports the oracle).  Rank 0 rebuilds
+    # every rank's slice; beyond 2^24 the full-size comparison is skipped (host memory / minutes of CPU time).
     root_check = "skipped (size)"
     if n <= (1 << 24):
         if rank == 0:
@@ -519,10 +520,16 @@ def bench_distributed(args, ctx, enc, field, n, synthetic_coeffs):
             for g in range(world):
                 g0, g1 = p.rows(g)
                 parts.append(synthetic_coeffs(field, max(min(g1 * p.n_per_row, n) - g0 * p.n_per_row, 0), seed=1000 + g))
-            single = LcCommit.commit(np.concatenate(parts), enc)
-            root_check = "equals the single-GPU commit" if single.get_root() == root0 else "MISMATCH"
+            full = np.concatenate(parts)
+            single = LcCommit.commit(full, enc)
+            same_single = single.get_root() == root0
             single.close()
-            assert root_check != "MISMATCH", "distributed LcRoot differs from the single-GPU commit"
+            root_check = "equals the single-GPU commit" if same_single else "MISMATCH"
+            oracle_root = getattr(B, "oracle_root", None)
+            if same_single and oracle_root is not None:
+                ok = oracle_root(enc, field, full) == root0.root
+                root_check = "equals the oracle's LcRoot and the single-GPU commit (same coefficients)" if ok else "MISMATCH"
+            assert root_check != "MISMATCH", "distributed LcRoot differs from the single-GPU commit / the oracle"
         dist.barrier()
     # prove() over the sharded commit (config 4 of BASELINE.json is commit + prove): wall clock, max over ranks;
     # rank 0 then verifies the proof on its own GPU against the sharded commit's root
@@ -561,7 +568,6 @@ def _dominant_multi(enc, field, p, dc, encode_ms):
     B = 8 * FIELD_LIMBS[field]
     log_n = p.n_cols.bit_length() - 1
     n_pass = 1 if log_n <= 10 else -(-log_n // 10)
-    per_pass = [B * dc.my_rows * (p.n_per_row + p.n_cols)] + [2 * B * dc.my_rows * p.n_cols] * (n_pass - 1)
+    moved = B * dc.my_rows * (p.n_per_row + p.n_cols) + 2 * B * dc.my_rows * p.n_cols * (n_pass - 1)
     return dict(kernel="ntt_pass_kernel (per GPU; last pass stores into the column owners' memory)",
-                launches_per_step=n_pass, ms_per_launch=encode_ms / n_pass, bytes_per_launch=sum(per_pass) / n_pass,
-                traffic=None)
+                launches_per_step=n_pass, phase_ms=encode_ms, moved_bytes_per_launch=moved / n_pass, traffic=None)

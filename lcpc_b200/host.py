@@ -228,6 +228,8 @@ class SdigEncoding(LcEncoding):
         h = C.c_void_p()
         _check(_cabi.lib().lcpc_b200_sdig_new(ctx._h, field, len(pre), pack(pre), pack(post), C.byref(h)), ctx)
         self.code, self.seed, self._code_h = code, None, None
+        # keep the caller's matrices: matrices() of an encoding built this way returns exactly what it was given
+        self._given = ([dict(M) for M in pre], [dict(M) for M in post])
         LcEncoding.__init__(self, ctx, h, field)
         return self
 
@@ -256,6 +258,10 @@ class SdigEncoding(LcEncoding):
 
     def matrices(self):
         """(precodes, postcodes) as lists of dicts -- the CSC arrays matgen::generate produced."""
+        if getattr(self, "_given", None) is not None:
+            return self._given
+        if not self._code_h:
+            raise LcpcError(_cabi.ERR_BAD_ARG, "encoding is closed: no code matrices")
         return host_code_matrices(self._code_h, self.L)
 
 
@@ -269,9 +275,12 @@ def host_code_matrices(code_h, L):
             _check(lib.lcpc_b200_sdig_code_matrix(code_h, i, is_post, C.byref(m)))
             ptrs = np.ctypeslib.as_array(C.cast(m.ptrs, C.POINTER(C.c_uint64)), shape=(m.n + 1,)).copy()
             nnz = int(ptrs[-1])
-            idxs = np.ctypeslib.as_array(C.cast(m.idxs, C.POINTER(C.c_uint64)), shape=(max(nnz, 1),))[:nnz].copy()
-            data = np.ctypeslib.as_array(C.cast(m.data, C.POINTER(C.c_uint64)), shape=(max(nnz, 1) * L,))[:nnz * L]
-            out[is_post].append(dict(m=m.m, n=m.n, ptrs=ptrs, idxs=idxs, data=data.reshape(nnz, L).copy()))
+            if nnz == 0 or not m.idxs or not m.data:  # an empty level may hand back NULL data pointers
+                idxs, data = np.zeros(0, np.uint64), np.zeros((0, L), np.uint64)
+            else:
+                idxs = np.ctypeslib.as_array(C.cast(m.idxs, C.POINTER(C.c_uint64)), shape=(nnz,)).copy()
+                data = np.ctypeslib.as_array(C.cast(m.data, C.POINTER(C.c_uint64)), shape=(nnz * L,)).reshape(nnz, L).copy()
+            out[is_post].append(dict(m=m.m, n=m.n, ptrs=ptrs, idxs=idxs, data=data))
     return out
 
 

@@ -113,14 +113,26 @@ class LcEvalProof:
             raise LcpcError(_cabi.ERR_BAD_ARG, "root must be 32 bytes")
         outer, inner = _elems(outer_tensor, enc.field), _elems(inner_tensor, enc.field)
         L = FIELD_LIMBS[enc.field]
-        p_eval = np.ascontiguousarray(self.p_eval, np.uint64).reshape(-1, L)
-        p_rand = np.ascontiguousarray(self.p_random_vec, np.uint64).reshape(-1, p_eval.shape[0], L)
+        # the C side reads n_open * n_rows * 8L bytes of columns etc.: a proof deserialized for another field (or
+        # ragged arrays) must fail here, not as an out-of-bounds read
+        if self.field != enc.field:
+            raise LcpcError(_cabi.ERR_BAD_ARG, f"proof is over field {self.field}, the encoding over {enc.field}")
+        p_eval = np.ascontiguousarray(self.p_eval, np.uint64)
         cols = np.ascontiguousarray(self.cols, np.uint64)
         paths = np.ascontiguousarray(self.paths, np.uint8)
+        p_rand = np.ascontiguousarray(self.p_random_vec, np.uint64)
+        if p_eval.ndim != 2 or p_eval.shape[1] != L or cols.ndim != 3 or cols.shape[2] != L:
+            raise LcpcError(_cabi.ERR_BAD_ARG, "proof arrays do not have the field's limb count")
+        if p_rand.size == 0:
+            p_rand = p_rand.reshape(0, p_eval.shape[0], L)
+        if p_rand.ndim != 3 or p_rand.shape[1:] != (p_eval.shape[0], L):
+            raise LcpcError(_cabi.ERR_BAD_ARG, "p_random_vec rows must have n_per_row elements")
+        if paths.ndim != 3 or paths.shape[2] != 32 or paths.shape[0] != cols.shape[0]:
+            raise LcpcError(_cabi.ERR_BAD_ARG, "paths must be (n_col_opens, path_len, 32)")
         n_columns = cols.shape[0]
-        n_rows = cols.shape[1] if cols.ndim == 3 else 0
+        n_rows = cols.shape[1]
         pr = _cabi.Proof(self.n_cols, p_eval.shape[0], p_rand.shape[0], n_columns, n_rows,
-                         paths.shape[1] if paths.ndim == 3 else 0, p_eval.ctypes.data, p_rand.ctypes.data,
+                         paths.shape[1], p_eval.ctypes.data, p_rand.ctypes.data,
                          cols.ctypes.data, paths.ctypes.data)
         rb = np.frombuffer(root_b, dtype=np.uint8).copy()
         out = np.empty((1, L), np.uint64)

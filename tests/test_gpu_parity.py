@@ -235,6 +235,33 @@ def test_sdig_encode_vs_oracle(field, n, seed):
         assert (got[r] == oenc.encode(rows[r])).all()
 
 
+@pytest.mark.parametrize("hints,window_kb,slice_kb", [(1, 8, 0), (0, 8, 0), (1, 64, 0), (1, 0, 0), (0, 0, 16), (1, 1 << 20, 0)])
+@pytest.mark.parametrize("field,n,seed", [(P.FT127, 4000, 4), (P.FT255, 1500, 5), (P.FT63, 9000, 6)])
+def test_sdig_encode_schedules_are_result_neutral(field, n, seed, hints, window_kb, slice_kb):
+    """The sparse products' schedule knobs (L2 eviction hints, column chunks with accumulation onto y, batch-row
+    slices) must not change a single limb: windows of 8 KB force up to 16 column chunks on these small codes."""
+    from lcpc_b200 import _cabi
+    lib = _cabi.lib()
+    knobs = {b"SPMM_HINTS": hints, b"SPMM_WINDOW_KB": window_kb, b"SPMM_SLICE_KB": slice_kb}
+    try:
+        for k, v in knobs.items():
+            lib.lcpc_b200_set_tunable(k, v)
+        enc = P.SdigEncoding.new_from_dims(field, n, seed=seed)
+        oenc = O.Encoding.sdig_from_dims(field, n, seed=seed)
+        n_rows = 7
+        rows = np.zeros((n_rows, enc.n_cols, enc.L), np.uint64)
+        rows[:, :n] = O.random_elems(field, n_rows * n, seed=seed + 50).reshape(n_rows, n, -1)
+        got = enc.encode(rows)
+        again = enc.encode(rows)  # the cached cut points are reused
+        for r in range(n_rows):
+            want = oenc.encode(rows[r])
+            assert (got[r] == want).all() and (again[r] == want).all()
+    finally:
+        lib.lcpc_b200_set_tunable(b"SPMM_HINTS", 1)
+        lib.lcpc_b200_set_tunable(b"SPMM_WINDOW_KB", 56 << 10)
+        lib.lcpc_b200_set_tunable(b"SPMM_SLICE_KB", 0)
+
+
 @pytest.mark.parametrize("field,length,seed", [(P.FT127, 1 << 14, 0), (P.FT127, (1 << 16) - 11, 1), (P.FT255, 1 << 13, 0),
                                                (P.FT63, 5000, 1)])
 def test_commit_brakedown_vs_oracle(field, length, seed):

@@ -152,6 +152,52 @@ def test_verify_error_variants(kind, field, length):
         run(label=b"another transcript")
 
 
+@pytest.mark.parametrize("kind,field,length", [("ligero", P.FT255, 1 << 10), ("sdig", P.FT127, 1 << 12)])
+def test_verify_rejects_malformed_proofs(kind, field, length):
+    """The verifier's trust boundary: a non-canonical element (v + p has the same transcript bytes as v), a Merkle
+    path of the wrong length and a proof over another field are refused before anything reaches the device."""
+    enc, oenc, c, oc, outer, inner = _case(kind, field, length, seed=11)
+    proof = c.prove(outer, enc, P.Transcript(LABEL))
+    root = c.get_root()
+    proof.verify(root, outer, inner, enc, P.Transcript(LABEL))
+    L = enc.L
+    p_limbs = O.int_to_limbs(O.field_info(field)["modulus"], L)
+
+    def plus_p(elem):  # the same residue, not canonical: v + p < 2^(64L) for every v < p
+        return O.int_to_limbs(O.limbs_to_int(elem) + O.limbs_to_int(p_limbs), L)
+
+    for which in ("p_eval", "p_random_vec", "cols"):
+        arrs = dict(p_eval=proof.p_eval.copy(), p_random_vec=proof.p_random_vec.copy(), cols=proof.cols.copy())
+        a = arrs[which].reshape(-1, L)
+        a[a.shape[0] // 2] = plus_p(a[a.shape[0] // 2])
+        bad = P.LcEvalProof(field, proof.n_cols, arrs["p_eval"], arrs["p_random_vec"], arrs["cols"], proof.paths)
+        with pytest.raises(P.LcpcError) as e:
+            bad.verify(root, outer, inner, enc, P.Transcript(LABEL))
+        assert e.value.code == _cabi.ERR_BAD_ARG and "non-canonical" in str(e.value), (which, str(e.value))
+    # p itself (the residue 0 in non-canonical form)
+    pe = proof.p_eval.copy()
+    pe[0] = p_limbs
+    _expect(_cabi.ERR_BAD_ARG, lambda: P.LcEvalProof(field, proof.n_cols, pe, proof.p_random_vec, proof.cols, proof.paths)
+            .verify(root, outer, inner, enc, P.Transcript(LABEL)))
+    # path one sibling short / one long
+    short = P.LcEvalProof(field, proof.n_cols, proof.p_eval, proof.p_random_vec, proof.cols, proof.paths[:, :-1].copy())
+    _expect(_cabi.VERR_COLUMN_PATH, lambda: short.verify(root, outer, inner, enc, P.Transcript(LABEL)))
+    longer = np.concatenate([proof.paths, proof.paths[:, :1]], axis=1)
+    _expect(_cabi.VERR_COLUMN_PATH, lambda: P.LcEvalProof(field, proof.n_cols, proof.p_eval, proof.p_random_vec, proof.cols, longer)
+            .verify(root, outer, inner, enc, P.Transcript(LABEL)))
+    # a proof deserialized for a smaller field: refused by shape, never handed to C
+    other = P.FT63 if field != P.FT63 else P.FT127
+    wire = P.serialize_proof(proof)
+    try:
+        small = P.deserialize_proof(wire, other)
+    except Exception:
+        small = None
+    if small is not None:
+        _expect(_cabi.ERR_BAD_ARG, lambda: small.verify(root, outer, inner, enc, P.Transcript(LABEL)))
+    wrong = P.LcEvalProof(other, proof.n_cols, proof.p_eval, proof.p_random_vec, proof.cols, proof.paths)
+    _expect(_cabi.ERR_BAD_ARG, lambda: wrong.verify(root, outer, inner, enc, P.Transcript(LABEL)))
+
+
 def test_prove_rejects_wrong_outer_tensor_length():
     field, length = P.FT63, 2000
     enc, oenc, c, oc, outer, inner = _case("ligero", field, length, seed=2)
