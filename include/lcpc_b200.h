@@ -262,6 +262,84 @@ int lcpc_b200_verify(lcpc_b200_enc *enc, lcpc_b200_transcript *tr, const lcpc_b2
                      const uint64_t *inner_tensor, size_t inner_len, size_t n_col_opens, size_t n_degree_tests,
                      const lcpc_b200_proof *proof, uint64_t *eval_out);
 
+/* ---- commit / prove sharded over the GPUs of one box (no reference analogue: the reference is one process on CPU
+ * threads; what is replaced is still LcCommit::commit, lcpc-2d/src/lib.rs:622-671, and ::prove, :1004-1093) ----
+ * GPU g encodes the row block [row_lo[g], row_lo[g+1]) and hashes the column block [col_lo[g], col_lo[g+1]); the
+ * transpose between the two is fused into the encode, whose last pass stores every tile straight into the owner's
+ * memory over NVLink (peer-mapped windows), ordered by flags in those windows -- no collective library on the path.
+ *
+ * Two shapes:
+ *  (1) ONE PROCESS, several GPUs (a Rust host; the reference's own shape): lcpc_b200_commit_new_multi and the
+ *      lcpc_b200_multi_* calls below -- one encoding per GPU (each on its own context), everything else inside.
+ *  (2) one process per GPU (bench.py under torchrun): every rank creates its lcpc_b200_shard, publishes the 64-byte
+ *      CUDA IPC handle of its window by whatever channel the host has, connects, and calls the same operations;
+ *      ranks stay in lock-step through the windows' flags.  A rank that never arrives makes the others fail with
+ *      LCPC_B200_ERR_CUDA after a timeout (tunable SHARD_TIMEOUT_MS) instead of hanging the device. */
+typedef struct lcpc_b200_shard lcpc_b200_shard; /* one GPU's part of a sharded LcCommit */
+typedef struct lcpc_b200_multi lcpc_b200_multi; /* a whole sharded LcCommit driven from one process */
+
+/* the partition (pure host arithmetic, the same on every rank): world + 1 boundaries each; column blocks are unions
+ * of aligned Merkle subtrees of *sub_leaves leaves, dealt over the subtrees that contain real columns */
+int lcpc_b200_shard_plan(size_t n_rows, size_t n_per_row, size_t n_cols, unsigned world, size_t *row_lo, size_t *col_lo,
+                         size_t *sub_lo, size_t *sub_leaves, size_t *n_sub);
+/* rank `rank` of `world` for a commit of `len` coefficients under `enc` (this GPU's instance of the encoding);
+ * max_open = the most columns one prove() will open (LcEncoding::get_n_col_opens) */
+int lcpc_b200_shard_new(lcpc_b200_enc *enc, size_t len, unsigned world, unsigned rank, size_t max_open,
+                        lcpc_b200_shard **out);
+void lcpc_b200_shard_free(lcpc_b200_shard *s);
+/* this rank's window: device pointer (same-process peers) and/or its CUDA IPC handle (other processes) */
+int lcpc_b200_shard_window(lcpc_b200_shard *s, void **d_ptr, size_t *bytes, uint8_t ipc_handle[64]);
+/* map every peer's window: peer_ptrs[h] (same process; peer access is enabled here) or, where that is NULL,
+ * ipc_handles + 64*h (another process).  Entry `rank` is ignored. */
+int lcpc_b200_shard_connect(lcpc_b200_shard *s, void *const *peer_ptrs, const uint8_t *ipc_handles);
+int lcpc_b200_shard_dims(const lcpc_b200_shard *s, size_t *n_rows, size_t *n_per_row, size_t *n_cols, size_t *row_lo,
+                         size_t *row_hi, size_t *col_lo, size_t *col_hi, size_t *n_elems);
+/* enqueue one commit: `rows` = this rank's n_elems coefficients (row block, the polynomial's last row may be
+ * short) in HOST memory, copied in row-chunks under the encode; _dev: in device memory, or NULL to commit the rows
+ * lcpc_b200_shard_load_rows stored.  No host synchronisation. */
+int lcpc_b200_shard_commit(lcpc_b200_shard *s, const uint64_t *rows, size_t n_elems);
+int lcpc_b200_shard_commit_dev(lcpc_b200_shard *s, const uint64_t *d_rows, size_t n_elems);
+int lcpc_b200_shard_load_rows(lcpc_b200_shard *s, const uint64_t *rows, size_t n_elems);
+/* LcCommit::get_root (:276-281): synchronises this rank's stream; every rank returns the same digest */
+int lcpc_b200_shard_root(lcpc_b200_shard *s, uint8_t root[32]);
+/* the same without the synchronisation: the 32 bytes land in `root` (page-locked host memory) when the stream
+ * gets there; a pipelined caller enqueues the next commit right behind it and reads the roots later */
+int lcpc_b200_shard_root_enqueue(lcpc_b200_shard *s, uint8_t *root);
+/* device times of the last commit on this rank: ms[0] encode + peer stores, ms[1] wait for the peers' tiles,
+ * ms[2] column hashing, subtree roots, root exchange and top tree */
+int lcpc_b200_shard_phase_times(lcpc_b200_shard *s, float ms[3]);
+/* this rank's pieces of the commit (tests): column block [n_rows][my_cols], row block of coeffs, leaf digests, top tree */
+int lcpc_b200_shard_device_ptrs(lcpc_b200_shard *s, uint64_t **d_recv, uint64_t **d_coeffs, uint8_t **d_leaves, uint8_t **d_top);
+/* collapse_columns (:1095-1123) over row-sharded coefficients, split in two so that a caller can overlap host work:
+ * begin = this rank's partial combination (tensor: n_rows elements on the host, or key: the 32 challenge bytes the
+ * device expands, :1026-1032) stored into every peer's window; finish = wait for all partials, sum them on the
+ * device, poly (n_per_row elements) and optionally their canonical bytes (to_repr, for the transcript) to the host. */
+int lcpc_b200_shard_collapse_begin(lcpc_b200_shard *s, const uint64_t *tensor, const uint8_t key[32]);
+int lcpc_b200_shard_collapse_finish(lcpc_b200_shard *s, uint64_t *poly, uint8_t *repr);
+/* open_column (:788-825) for n columns: the owner of a column supplies values and path; all ranks receive all */
+int lcpc_b200_shard_open_begin(lcpc_b200_shard *s, const uint64_t *cols, size_t n);
+int lcpc_b200_shard_open_finish(lcpc_b200_shard *s, uint64_t *cols_out, uint8_t *paths_out);
+/* LcCommit::prove (:1004-1093); arguments as lcpc_b200_commit_prove.  Shape (2): every rank calls it with an
+ * identical transcript and receives the same proof. */
+int lcpc_b200_shard_prove(lcpc_b200_shard *s, lcpc_b200_transcript *tr, const lcpc_b200_labels *labels,
+                          const uint64_t *outer_tensor, size_t outer_len, size_t n_degree_tests, size_t n_col_opens,
+                          uint64_t *p_eval, uint64_t *p_random, uint64_t *col_idx, uint64_t *cols_out, uint8_t *paths_out);
+
+/* shape (1): LcCommit::commit over encs[0..n_gpus) (the same encoding built on n_gpus contexts); coeffs_in: `len`
+ * elements on the host (page-locked memory gives full-rate copies on every GPU's own PCIe link) */
+int lcpc_b200_commit_new_multi(lcpc_b200_enc *const *encs, size_t n_gpus, const uint64_t *coeffs_in, size_t len,
+                               size_t max_open, lcpc_b200_multi **out);
+int lcpc_b200_multi_rerun(lcpc_b200_multi *m, const uint64_t *coeffs_in, size_t len); /* enqueue only */
+int lcpc_b200_multi_root(lcpc_b200_multi *m, uint8_t root[32]);
+int lcpc_b200_multi_collapse(lcpc_b200_multi *m, const uint64_t *tensor, const uint8_t key[32], uint64_t *poly, uint8_t *repr);
+int lcpc_b200_multi_open_columns(lcpc_b200_multi *m, const uint64_t *cols, size_t n, uint64_t *cols_out, uint8_t *paths_out);
+int lcpc_b200_multi_prove(lcpc_b200_multi *m, lcpc_b200_transcript *tr, const lcpc_b200_labels *labels,
+                          const uint64_t *outer_tensor, size_t outer_len, size_t n_degree_tests, size_t n_col_opens,
+                          uint64_t *p_eval, uint64_t *p_random, uint64_t *col_idx, uint64_t *cols_out, uint8_t *paths_out);
+size_t lcpc_b200_multi_n_shards(const lcpc_b200_multi *m);
+lcpc_b200_shard *lcpc_b200_multi_shard(lcpc_b200_multi *m, size_t g);
+void lcpc_b200_multi_free(lcpc_b200_multi *m);
+
 /* ---- standalone pieces (tests, verifier-side use, multi-GPU pipeline) ---- */
 /* merkleize (lcpc-2d/src/lib.rs:690-704) of a host row-major comm into host hashes[2*np2-1][32] */
 int lcpc_b200_merkleize(lcpc_b200_ctx *ctx, int field, const uint64_t *comm, size_t n_rows, size_t n_cols,

@@ -31,7 +31,9 @@ from ._cabi import LcpcError, LIB_PATH  # noqa: F401
 from .proof import (LcEvalProof, Transcript, prove, sample_columns, serialize_root, serialize_commit,  # noqa: F401
                     serialize_proof, deserialize_root, deserialize_commit_fields, deserialize_commit, deserialize_proof)
 
-__all__ = ["FT63", "FT127", "FT191", "FT255", "FIELD_LIMBS", "Context", "LcCommit", "LcEncoding", "LcRoot",
+from .shard import MultiCommit, Shard, ShardedCommit, shard_plan  # noqa: F401,E402
+
+__all__ = ["MultiCommit", "Shard", "ShardedCommit", "shard_plan", "FT63", "FT127", "FT191", "FT255", "FIELD_LIMBS", "Context", "LcCommit", "LcEncoding", "LcRoot",
            "LigeroEncoding", "SdigEncoding", "LcpcError", "default_context", "field_op", "merkleize",
            "collapse_columns", "ligero_get_dims", "n_degree_tests", "expand_tensor", "LcEvalProof", "Transcript", "prove",
            "sample_columns", "serialize_root", "serialize_commit", "serialize_proof", "deserialize_root",

@@ -109,6 +109,33 @@ SIGNATURES = {
     "lcpc_b200_commit_open_columns": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "lcpc_b200_commit_prove": (_i, [_vp, _vp, C.POINTER(Labels), _vp, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
     "lcpc_b200_verify": (_i, [_vp, _vp, C.POINTER(Labels), _vp, _vp, _sz, _vp, _sz, _sz, _sz, C.POINTER(Proof), _vp]),
+    "lcpc_b200_shard_plan": (_i, [_sz, _sz, _sz, C.c_uint, _vp, _vp, _vp, _psz, _psz]),
+    "lcpc_b200_shard_new": (_i, [_vp, _sz, C.c_uint, C.c_uint, _sz, _pvp]),
+    "lcpc_b200_shard_free": (None, [_vp]),
+    "lcpc_b200_shard_window": (_i, [_vp, _pvp, _psz, _vp]),
+    "lcpc_b200_shard_connect": (_i, [_vp, _vp, _vp]),
+    "lcpc_b200_shard_dims": (_i, [_vp, _psz, _psz, _psz, _psz, _psz, _psz, _psz, _psz]),
+    "lcpc_b200_shard_commit": (_i, [_vp, _vp, _sz]),
+    "lcpc_b200_shard_commit_dev": (_i, [_vp, _vp, _sz]),
+    "lcpc_b200_shard_load_rows": (_i, [_vp, _vp, _sz]),
+    "lcpc_b200_shard_root": (_i, [_vp, _vp]),
+    "lcpc_b200_shard_root_enqueue": (_i, [_vp, _vp]),
+    "lcpc_b200_shard_phase_times": (_i, [_vp, _vp]),
+    "lcpc_b200_shard_device_ptrs": (_i, [_vp, _pvp, _pvp, _pvp, _pvp]),
+    "lcpc_b200_shard_collapse_begin": (_i, [_vp, _vp, _vp]),
+    "lcpc_b200_shard_collapse_finish": (_i, [_vp, _vp, _vp]),
+    "lcpc_b200_shard_open_begin": (_i, [_vp, _vp, _sz]),
+    "lcpc_b200_shard_open_finish": (_i, [_vp, _vp, _vp]),
+    "lcpc_b200_shard_prove": (_i, [_vp, _vp, C.POINTER(Labels), _vp, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "lcpc_b200_commit_new_multi": (_i, [_vp, _sz, _vp, _sz, _sz, _pvp]),
+    "lcpc_b200_multi_rerun": (_i, [_vp, _vp, _sz]),
+    "lcpc_b200_multi_root": (_i, [_vp, _vp]),
+    "lcpc_b200_multi_collapse": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "lcpc_b200_multi_open_columns": (_i, [_vp, _vp, _sz, _vp, _vp]),
+    "lcpc_b200_multi_prove": (_i, [_vp, _vp, C.POINTER(Labels), _vp, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "lcpc_b200_multi_n_shards": (_sz, [_vp]),
+    "lcpc_b200_multi_shard": (_vp, [_vp, _sz]),
+    "lcpc_b200_multi_free": (None, [_vp]),
     "lcpc_b200_merkleize": (_i, [_vp, _i, _vp, _sz, _sz, _vp]),
     "lcpc_b200_hash_columns_dev": (_i, [_vp, _i, _vp, _sz, _sz, _sz, _vp]),
     "lcpc_b200_merkle_tree_dev": (_i, [_vp, _vp, _sz]),

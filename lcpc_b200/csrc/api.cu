@@ -13,105 +13,11 @@
 #include <string>
 #include <vector>
 
-#include "../../include/lcpc_b200.h"
-#include "../../include/lcpc_b200_host.h"
-#include "expander.h"
+#include "api_internal.h"
 #include "field.cuh"
 #include "host_chacha.h"
-#include "host_transcript.h"
-#include "kernels.h"
 
 using namespace lcpc;
-
-// ------------------------------------------------------------------------------------------------
-// Lifetimes: an encoding keeps its context alive and a commit keeps its encoding alive (reference counts), so the
-// three `*_destroy` / `*_free` calls may come in any order -- a garbage-collected host (the Python layer here, a
-// Drop order a Rust shim does not control) cannot turn the order of finalisers into a use-after-free.
-struct lcpc_b200_ctx {
-  std::atomic<int> refs{1};
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  // host->device staging stream + events: commit() from host memory copies the coefficient rows in
-  // row-chunks on this stream while the engine stream encodes the chunks that have already landed
-  cudaStream_t copy_stream = nullptr;
-  static constexpr int MAX_CHUNKS = 16;
-  cudaEvent_t chunk_ev[MAX_CHUNKS] = {};
-  cudaEvent_t begin_ev = nullptr;
-  // side stream: column hashing of already-encoded row chunks runs here next to the encode of later rows
-  // (the transforms saturate the multiplier pipe, BLAKE3 the ALU pipe: they overlap on the same SMs)
-  cudaStream_t side_stream = nullptr;
-  cudaEvent_t side_ev[MAX_CHUNKS] = {};
-  cudaEvent_t side_done = nullptr;
-  cudaEvent_t lane_fork = nullptr, lane_join = nullptr;  // lent to the expander encode in scatter mode
-  std::mutex mu;
-  std::string err;
-  uint64_t launches = 0;
-  // grow-only device scratch shared by the stateless entry points
-  void *scratch = nullptr;
-  size_t scratch_bytes = 0;
-  // grow-only page-locked host staging (results the host has to read right away: canonical bytes for the transcript)
-  void *h_stage = nullptr;
-  size_t h_stage_bytes = 0;
-};
-
-static int fail(lcpc_b200_ctx *ctx, int code, const char *fmt, ...) {
-  if (ctx) {
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof buf, fmt, ap);
-    va_end(ap);
-    ctx->err = buf;
-  }
-  return code;
-}
-
-static int cuda_fail(lcpc_b200_ctx *ctx, cudaError_t e, const char *what) {
-  int code = (e == cudaErrorMemoryAllocation) ? LCPC_B200_ERR_OOM : LCPC_B200_ERR_CUDA;
-  return fail(ctx, code, "%s: %s", what, cudaGetErrorString(e));
-}
-
-#define CU(ctx, call)                                        \
-  do {                                                       \
-    cudaError_t e_ = (call);                                 \
-    if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call); \
-  } while (0)
-
-static int bind_device(lcpc_b200_ctx *ctx) {
-  cudaError_t e = cudaSetDevice(ctx->device);
-  if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
-  return LCPC_B200_OK;
-}
-
-static int ensure_scratch(lcpc_b200_ctx *ctx, size_t bytes) {
-  if (bytes <= ctx->scratch_bytes) return LCPC_B200_OK;
-  if (ctx->scratch) cudaFree(ctx->scratch);
-  ctx->scratch = nullptr, ctx->scratch_bytes = 0;
-  CU(ctx, cudaMalloc(&ctx->scratch, bytes));
-  ctx->scratch_bytes = bytes;
-  return LCPC_B200_OK;
-}
-
-// page-locked staging of at least `bytes`; nullptr if the allocation fails (callers fall back to pageable memory)
-static void *host_stage(lcpc_b200_ctx *ctx, size_t bytes) {
-  if (bytes <= ctx->h_stage_bytes) return ctx->h_stage;
-  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
-  ctx->h_stage = nullptr, ctx->h_stage_bytes = 0;
-  if (cudaHostAlloc(&ctx->h_stage, bytes, cudaHostAllocDefault) != cudaSuccess) {
-    cudaGetLastError();
-    ctx->h_stage = nullptr;
-    return nullptr;
-  }
-  ctx->h_stage_bytes = bytes;
-  return ctx->h_stage;
-}
-
-static bool is_pow2(size_t v) { return v && !(v & (v - 1)); }
-static unsigned log2_ceil(size_t v) {  // lcpc-2d/src/lib.rs:827-829
-  unsigned l = 0;
-  while (((size_t)1 << l) < v) l++;
-  return l;
-}
 
 // ------------------------------------------------------------------------------------------------
 // host-side setup scalars (one = R mod p, w = the n_cols-th root of unity).  These few values are
@@ -167,18 +73,6 @@ static void host_root(int field, unsigned log_len, uint32_t *w, uint32_t *one) {
 }
 
 // ------------------------------------------------------------------------------------------------
-struct lcpc_b200_enc {
-  std::atomic<int> refs{1};
-  lcpc_b200_ctx *ctx = nullptr;
-  int kind = 0, field = 0;
-  size_t n_per_row = 0, n_cols = 0;
-  // ligero
-  unsigned log_n = 0;
-  uint32_t *d_roots = nullptr;
-  // sdig
-  ExpanderCode *code = nullptr;
-};
-
 struct lcpc_b200_commit {
   lcpc_b200_enc *enc = nullptr;
   size_t n_rows = 0, n_per_row = 0, n_cols = 0, np2 = 0;
@@ -253,7 +147,7 @@ int lcpc_b200_ctx_create(int device, lcpc_b200_ctx **out) {
   return LCPC_B200_OK;
 }
 
-static void ctx_unref(lcpc_b200_ctx *ctx) {
+void ctx_unref(lcpc_b200_ctx *ctx) {
   if (ctx->refs.fetch_sub(1) != 1) return;  // encodings of this context are still alive
   cudaSetDevice(ctx->device);
   if (ctx->stream) {
@@ -388,7 +282,7 @@ int lcpc_b200_sdig_new(lcpc_b200_ctx *ctx, int field, size_t n_levels, const lcp
   return LCPC_B200_OK;
 }
 
-static void enc_unref(lcpc_b200_enc *enc) {
+void enc_unref(lcpc_b200_enc *enc) {
   if (enc->refs.fetch_sub(1) != 1) return;  // commits made with this encoding are still alive
   lcpc_b200_ctx *ctx = enc->ctx;
   {
@@ -425,8 +319,8 @@ int lcpc_b200_enc_dims_ok(const lcpc_b200_enc *enc, size_t n_per_row, size_t n_c
 }
 
 // encode n_rows rows: src (stride/valid) -> dst (stride n_cols); enqueues only
-static int encode_rows(lcpc_b200_enc *enc, const uint32_t *src, size_t src_stride, size_t valid, uint32_t *dst,
-                       size_t n_rows, void *enc_scratch, const Scatter *scatter = nullptr) {
+int encode_rows(lcpc_b200_enc *enc, const uint32_t *src, size_t src_stride, size_t valid, uint32_t *dst,
+                size_t n_rows, void *enc_scratch, const Scatter *scatter) {
   lcpc_b200_ctx *ctx = enc->ctx;
   int nl = 0;
   cudaError_t ce;
@@ -443,7 +337,7 @@ static int encode_rows(lcpc_b200_enc *enc, const uint32_t *src, size_t src_strid
   return LCPC_B200_OK;
 }
 
-static size_t enc_scratch_bytes(const lcpc_b200_enc *enc, size_t n_rows) {
+size_t enc_scratch_bytes(const lcpc_b200_enc *enc, size_t n_rows) {
   return enc->kind == LCPC_B200_ENC_SDIG ? expander_scratch_bytes(enc->code, n_rows) : 0;
 }
 
@@ -468,10 +362,9 @@ struct HostOut {
   uint64_t *comm, *coeffs;
 };
 
-static int encode_rows_from_host(lcpc_b200_enc *enc, const void *src, size_t len, uint32_t *d_coeffs, uint32_t *d_comm,
-                                 size_t n_rows, void *enc_scratch, cudaEvent_t first_ev,
-                                 const Scatter *scatter = nullptr, HashTrail *trail = nullptr,
-                                 const HostOut *host_out = nullptr) {
+int encode_rows_from_host(lcpc_b200_enc *enc, const void *src, size_t len, uint32_t *d_coeffs, uint32_t *d_comm,
+                          size_t n_rows, void *enc_scratch, cudaEvent_t first_ev, const Scatter *scatter, HashTrail *trail,
+                          const HostOut *host_out, cudaEvent_t coeffs_free_ev) {
   lcpc_b200_ctx *ctx = enc->ctx;
   cudaStream_t st = ctx->stream;
   const size_t B = field_bytes(enc->field), N = B / 4;
@@ -479,8 +372,14 @@ static int encode_rows_from_host(lcpc_b200_enc *enc, const void *src, size_t len
   const size_t row_bytes = n_per_row * B;
   size_t n_chunks = std::min<size_t>(enc->kind == LCPC_B200_ENC_LIGERO ? 16 : 4, n_rows);
   while (n_chunks > 1 && (n_rows / n_chunks) * row_bytes < ((size_t)4 << 20)) n_chunks--;
-  CU(ctx, cudaEventRecord(ctx->begin_ev, st));  // earlier readers of d_coeffs on the engine stream
-  CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->begin_ev, 0));
+  if (coeffs_free_ev) {
+    // the caller knows when the last reader of d_coeffs finished (an event recorded behind it): the copy may start
+    // then, under whatever the engine stream still has queued behind that reader (hashing of the previous commit)
+    CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, coeffs_free_ev, 0));
+  } else {
+    CU(ctx, cudaEventRecord(ctx->begin_ev, st));  // earlier readers of d_coeffs on the engine stream
+    CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->begin_ev, 0));
+  }
   for (size_t k = 0; k < n_chunks; k++) {
     const size_t r0 = k * n_rows / n_chunks, r1 = (k + 1) * n_rows / n_chunks;
     const size_t e0 = r0 * n_per_row, e1 = std::min(r1 * n_per_row, len);
@@ -1116,14 +1015,8 @@ int lcpc_b200_commit_open_columns(lcpc_b200_commit *c, const uint64_t *cols, siz
 
 
 // ------------------------------------------------------------------------------- prove() / verify()
-namespace {
-
-struct Labels {
-  const uint8_t *dt, *pr, *pe, *co;
-  size_t dt_len, pr_len, pe_len, co_len;
-};
 // def_labels! (lcpc-2d/src/macros.rs:28-36) leaves `$l` unsubstituted inside the byte-string literals
-const uint8_t kLabelDT[] = "$l//DT", kLabelPR[] = "$l//PR", kLabelPE[] = "$l//PE", kLabelCO[] = "$l//CO";
+static const uint8_t kLabelDT[] = "$l//DT", kLabelPR[] = "$l//PR", kLabelPE[] = "$l//PE", kLabelCO[] = "$l//CO";
 Labels resolve_labels(const lcpc_b200_labels *in) {
   if (!in) return Labels{kLabelDT, kLabelPR, kLabelPE, kLabelCO, 6, 6, 6, 6};
   return Labels{in->dt, in->pr, in->pe, in->co, in->dt_len, in->pr_len, in->pe_len, in->co_len};
@@ -1146,7 +1039,7 @@ void sample_columns(const uint8_t key[32], size_t n_cols, size_t n, uint64_t *ou
 }
 
 // index of the first element whose limbs are not < p, or (size_t)-1
-size_t first_noncanonical(int field, const uint64_t *v, size_t n, size_t L) {
+static size_t first_noncanonical(int field, const uint64_t *v, size_t n, size_t L) {
   uint64_t p[4] = {0, 0, 0, 0};
   {
     uint32_t p32[8] = {0};
@@ -1174,8 +1067,6 @@ size_t first_noncanonical(int field, const uint64_t *v, size_t n, size_t L) {
   }
   return (size_t)-1;
 }
-
-}  // namespace
 
 int lcpc_b200_sample_columns(const uint8_t key[32], size_t n_cols, size_t n, uint64_t *out) {
   if (!key || n_cols == 0 || (!out && n)) return LCPC_B200_ERR_BAD_ARG;

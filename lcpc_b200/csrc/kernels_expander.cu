@@ -639,8 +639,12 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
       //   SPMM_HINTS      1: L2 policies on the gathers / the matrix stream (default), 0: plain loads
       //   SPMM_WINDOW_KB  L2 budget for the gathered window; a larger window runs as column chunks (0: never)
       //   SPMM_SLICE_KB   round-1 alternative: split the BATCH rows so that the slice fits (0: off)
-      const bool hints = tunable("SPMM_HINTS", 1) != 0;
-      const size_t cap = (size_t)std::max<long>(0, tunable("SPMM_WINDOW_KB", 56 << 10)) << 10;
+      // Measured at 2^24 (profiles/r02_ab_brakedown_schedules.jsonl, r02_ncu_spmm_*.csv): column chunks cut the first
+      // level's DRAM reads from 1.62 GB to 0.65 GB but the level takes 719 us instead of 444 us -- this kernel is
+      // bound by dependent gather rounds per thread, not by DRAM bytes, and shorter per-launch rows mean more
+      // rounds; the hints change nothing measurable.  Both therefore default to off here.
+      const bool hints = tunable("SPMM_HINTS", 0) != 0;
+      const size_t cap = (size_t)std::max<long>(0, tunable("SPMM_WINDOW_KB", 0)) << 10;
       const size_t slice_cap = (size_t)std::max<long>(0, tunable("SPMM_SLICE_KB", 0)) << 10;
       const size_t window = M.n * n_rows * F::BYTES;
       size_t rg = n_rows;

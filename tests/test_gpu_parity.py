@@ -257,8 +257,8 @@ def test_sdig_encode_schedules_are_result_neutral(field, n, seed, hints, window_
             want = oenc.encode(rows[r])
             assert (got[r] == want).all() and (again[r] == want).all()
     finally:
-        lib.lcpc_b200_set_tunable(b"SPMM_HINTS", 1)
-        lib.lcpc_b200_set_tunable(b"SPMM_WINDOW_KB", 56 << 10)
+        lib.lcpc_b200_set_tunable(b"SPMM_HINTS", 0)
+        lib.lcpc_b200_set_tunable(b"SPMM_WINDOW_KB", 0)
         lib.lcpc_b200_set_tunable(b"SPMM_SLICE_KB", 0)
 
 
