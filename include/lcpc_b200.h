@@ -310,6 +310,8 @@ int lcpc_b200_shard_root_enqueue(lcpc_b200_shard *s, uint8_t *root);
 int lcpc_b200_shard_phase_times(lcpc_b200_shard *s, float ms[3]);
 /* this rank's pieces of the commit (tests): column block [n_rows][my_cols], row block of coeffs, leaf digests, top tree */
 int lcpc_b200_shard_device_ptrs(lcpc_b200_shard *s, uint64_t **d_recv, uint64_t **d_coeffs, uint8_t **d_leaves, uint8_t **d_top);
+/* copy this rank's column block of comm ([n_rows][col_hi - col_lo] elements) and its leaf digests to the host */
+int lcpc_b200_shard_download(lcpc_b200_shard *s, uint64_t *cols_out, uint8_t *leaves_out);
 /* collapse_columns (:1095-1123) over row-sharded coefficients, split in two so that a caller can overlap host work:
  * begin = this rank's partial combination (tensor: n_rows elements on the host, or key: the 32 challenge bytes the
  * device expands, :1026-1032) stored into every peer's window; finish = wait for all partials, sum them on the

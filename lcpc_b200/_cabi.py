@@ -122,6 +122,7 @@ SIGNATURES = {
     "lcpc_b200_shard_root_enqueue": (_i, [_vp, _vp]),
     "lcpc_b200_shard_phase_times": (_i, [_vp, _vp]),
     "lcpc_b200_shard_device_ptrs": (_i, [_vp, _pvp, _pvp, _pvp, _pvp]),
+    "lcpc_b200_shard_download": (_i, [_vp, _vp, _vp]),
     "lcpc_b200_shard_collapse_begin": (_i, [_vp, _vp, _vp]),
     "lcpc_b200_shard_collapse_finish": (_i, [_vp, _vp, _vp]),
     "lcpc_b200_shard_open_begin": (_i, [_vp, _vp, _sz]),

@@ -419,6 +419,81 @@ spmm_kernel(const uint32_t *__restrict__ seg_lo, const uint32_t *__restrict__ se
   stv<N>(yp, out.v);
 }
 
+// The same product with the gathers SOFTWARE-PIPELINED one batch ahead: while a thread multiplies batch b, the
+// gathers of batch b+1 are already in flight and the column indices of batch b+2 are on their way, so a warp never
+// sits in front of an empty load queue between its multiply phases (spmm_kernel alternates "wait for 4 gathers" and
+// "4 products", and ran at 3.1 KB/clk of L2 traffic, half of what the L2 delivers).  Costs registers for a second
+// batch of gathered elements (launch bounds allow 3 CTAs per SM instead of 4 for 2- and 4-limb fields); the matrix
+// values are loaded just in time (they are shared by all batch rows of an output: L1 hits).  A ragged tail is one
+// more full batch with clamped indices and masked products, not a serial remainder loop -- which is what makes short
+// rows (column chunks) affordable.
+template <int FID, bool ACCUM>
+__global__ void __launch_bounds__(256, (Field<FID>::N <= 4 ? 3 : 2))
+spmm_pipe_kernel(const uint32_t *__restrict__ seg_lo, const uint32_t *__restrict__ seg_hi, const uint32_t *__restrict__ colidx,
+                 const uint32_t *__restrict__ vals, const uint32_t *__restrict__ x, uint32_t *__restrict__ y, size_t m,
+                 size_t n_rows, unsigned r0, unsigned rg) {
+  using F = Field<FID>;
+  constexpr int N = F::N;
+  constexpr int U = N <= 4 ? 4 : 2;
+  const size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= m * rg) return;
+  const size_t i = item / rg, r = r0 + item % rg;
+  const uint32_t k0 = __ldg(seg_lo + i), k1 = __ldg(seg_hi + i);
+  typename F::Wide acc = F::wide_zero();
+  const uint32_t *xr = x + r * N;
+  const uint32_t pos_stride = (uint32_t)(n_rows * N);
+  uint32_t *yp = y + (i * n_rows + r) * N;
+  if (k1 > k0) {
+    const uint32_t last = k1 - 1;
+    const uint32_t nb = (k1 - k0 + U - 1) / U;
+    auto load_idx = [&](uint32_t (&j)[U], uint32_t b) {
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const uint32_t k = min(k0 + b * U + u, last);
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(j[u]) : "l"(colidx + k));
+      }
+    };
+    auto gather = [&](typename F::Elem (&xv)[U], const uint32_t (&j)[U]) {
+#pragma unroll
+      for (int u = 0; u < U; u++) ldv_early<N>(xv[u].v, xr + (size_t)j[u] * pos_stride);
+    };
+    auto compute = [&](const typename F::Elem (&xv)[U], uint32_t b) {
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const uint32_t k = k0 + b * U + u;
+        if (k <= last) {
+          typename F::Elem a;
+          ldv_early<N>(a.v, vals + (size_t)k * N);
+          F::mac_wide(acc, a, xv[u]);
+        }
+      }
+    };
+    uint32_t jA[U], jB[U];
+    typename F::Elem xA[U], xB[U];
+    load_idx(jA, 0);
+    if (nb > 1) load_idx(jB, 1);
+    gather(xA, jA);
+    uint32_t b = 0;
+    for (;;) {
+      if (b + 1 < nb) gather(xB, jB);
+      if (b + 2 < nb) load_idx(jA, b + 2);
+      compute(xA, b);
+      if (++b >= nb) break;
+      if (b + 1 < nb) gather(xA, jA);
+      if (b + 2 < nb) load_idx(jB, b + 2);
+      compute(xB, b);
+      if (++b >= nb) break;
+    }
+  }
+  typename F::Elem out = F::template redc<2>(acc);
+  if (ACCUM) {
+    typename F::Elem prev;
+    ldv<N>(prev.v, yp);
+    out = F::add(out, prev);
+  }
+  stv<N>(yp, out.v);
+}
+
 // seg[q * m + i] = first k in [rowptr[i], rowptr[i+1]) with colidx[k] >= q * n / Q  (q = 0 .. Q)
 __global__ void __launch_bounds__(256)
 spmm_segments_kernel(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ colidx, size_t m, size_t n,
@@ -644,6 +719,7 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
       // bound by dependent gather rounds per thread, not by DRAM bytes, and shorter per-launch rows mean more
       // rounds; the hints change nothing measurable.  Both therefore default to off here.
       const bool hints = tunable("SPMM_HINTS", 0) != 0;
+      const bool pipe = tunable("SPMM_PIPE", 0) != 0;  // software-pipelined gathers (spmm_pipe_kernel)
       const size_t cap = (size_t)std::max<long>(0, tunable("SPMM_WINDOW_KB", 0)) << 10;
       const size_t slice_cap = (size_t)std::max<long>(0, tunable("SPMM_SLICE_KB", 0)) << 10;
       const size_t window = M.n * n_rows * F::BYTES;
@@ -671,7 +747,9 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
           const unsigned grid = (unsigned)((items + 255) / 256);
 #define LCPC_SPMM_LAUNCH(H, A) \
   spmm_kernel<FID, H, A><<<grid, 256, 0, st>>>(lo, hi, M.colidx, M.vals, x, y, M.m, n_rows, (unsigned)r0, (unsigned)cnt, keep)
-          if (hints && q) LCPC_SPMM_LAUNCH(true, true);
+          if (pipe && q) spmm_pipe_kernel<FID, true><<<grid, 256, 0, st>>>(lo, hi, M.colidx, M.vals, x, y, M.m, n_rows, (unsigned)r0, (unsigned)cnt);
+          else if (pipe) spmm_pipe_kernel<FID, false><<<grid, 256, 0, st>>>(lo, hi, M.colidx, M.vals, x, y, M.m, n_rows, (unsigned)r0, (unsigned)cnt);
+          else if (hints && q) LCPC_SPMM_LAUNCH(true, true);
           else if (hints) LCPC_SPMM_LAUNCH(true, false);
           else if (q) LCPC_SPMM_LAUNCH(false, true);
           else LCPC_SPMM_LAUNCH(false, false);

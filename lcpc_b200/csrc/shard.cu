@@ -672,6 +672,19 @@ int lcpc_b200_shard_device_ptrs(lcpc_b200_shard *s, uint64_t **d_recv, uint64_t 
   return LCPC_B200_OK;
 }
 
+int lcpc_b200_shard_download(lcpc_b200_shard *s, uint64_t *cols_out, uint8_t *leaves_out) {
+  if (!s) return LCPC_B200_ERR_BAD_ARG;
+  lcpc_b200_ctx *ctx = s->enc->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (int rc = bind_device(ctx)) return rc;
+  if (s->epoch == 0) return fail(ctx, LCPC_B200_ERR_BAD_ARG, "shard: no commit has run");
+  if (cols_out && s->my_cols)
+    CU(ctx, cudaMemcpyAsync(cols_out, s->window + s->wl.recv[s->epoch & 1], s->p.n_rows * s->my_cols * s->B, cudaMemcpyDeviceToHost, ctx->stream));
+  if (leaves_out && s->my_cols) CU(ctx, cudaMemcpyAsync(leaves_out, s->d_forest, s->my_cols * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return check_status(s);
+}
+
 // ------------------------------------------------------------------------------------------- prove, split-phase
 // collapse_columns (lcpc-2d/src/lib.rs:1095-1123) with the coefficient rows sharded by row block: every rank combines its
 // rows with its slice of the tensor, stores the partial vector into slot `rank` of every peer's window and signals;

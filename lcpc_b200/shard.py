@@ -159,16 +159,14 @@ class Shard(_ProveMixin):
     # inspection helpers (tests)
     def local_columns(self) -> np.ndarray:
         """This rank's column block of comm as (n_rows, my_cols, L), copied to the host."""
-        import torch
-        self.enc.ctx.synchronize()
-        recv = C.c_void_p()
-        _check(_cabi.lib().lcpc_b200_shard_device_ptrs(self._h, C.byref(recv), None, None, None))
         L, my_cols = FIELD_LIMBS[self.enc.field], self.col_hi - self.col_lo
         out = np.empty((self.n_rows, my_cols, L), np.uint64)
-        if out.size:
-            rt = torch.cuda.cudart()
-            with torch.cuda.device(self.enc.ctx.device):
-                rt.cudaMemcpy(out.ctypes.data, recv.value, out.nbytes, 2)  # cudaMemcpyDeviceToHost
+        _check(_cabi.lib().lcpc_b200_shard_download(self._h, _ptr(out), None), self.enc.ctx)
+        return out
+
+    def local_leaves(self) -> np.ndarray:
+        out = np.empty((self.col_hi - self.col_lo, 32), np.uint8)
+        _check(_cabi.lib().lcpc_b200_shard_download(self._h, None, _ptr(out)), self.enc.ctx)
         return out
 
 

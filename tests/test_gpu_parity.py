@@ -235,14 +235,15 @@ def test_sdig_encode_vs_oracle(field, n, seed):
         assert (got[r] == oenc.encode(rows[r])).all()
 
 
-@pytest.mark.parametrize("hints,window_kb,slice_kb", [(1, 8, 0), (0, 8, 0), (1, 64, 0), (1, 0, 0), (0, 0, 16), (1, 1 << 20, 0)])
-@pytest.mark.parametrize("field,n,seed", [(P.FT127, 4000, 4), (P.FT255, 1500, 5), (P.FT63, 9000, 6)])
-def test_sdig_encode_schedules_are_result_neutral(field, n, seed, hints, window_kb, slice_kb):
+@pytest.mark.parametrize("hints,window_kb,slice_kb,pipe", [(1, 8, 0, 0), (0, 8, 0, 0), (1, 64, 0, 0), (1, 0, 0, 0), (0, 0, 16, 0),
+                                                          (1, 1 << 20, 0, 0), (0, 0, 0, 1), (0, 8, 0, 1), (0, 64, 0, 1), (0, 0, 16, 1)])
+@pytest.mark.parametrize("field,n,seed", [(P.FT127, 4000, 4), (P.FT255, 1500, 5), (P.FT63, 9000, 6), (P.FT191, 700, 7)])
+def test_sdig_encode_schedules_are_result_neutral(field, n, seed, hints, window_kb, slice_kb, pipe):
     """The sparse products' schedule knobs (L2 eviction hints, column chunks with accumulation onto y, batch-row
     slices) must not change a single limb: windows of 8 KB force up to 16 column chunks on these small codes."""
     from lcpc_b200 import _cabi
     lib = _cabi.lib()
-    knobs = {b"SPMM_HINTS": hints, b"SPMM_WINDOW_KB": window_kb, b"SPMM_SLICE_KB": slice_kb}
+    knobs = {b"SPMM_HINTS": hints, b"SPMM_WINDOW_KB": window_kb, b"SPMM_SLICE_KB": slice_kb, b"SPMM_PIPE": pipe}
     try:
         for k, v in knobs.items():
             lib.lcpc_b200_set_tunable(k, v)
@@ -260,6 +261,7 @@ def test_sdig_encode_schedules_are_result_neutral(field, n, seed, hints, window_
         lib.lcpc_b200_set_tunable(b"SPMM_HINTS", 0)
         lib.lcpc_b200_set_tunable(b"SPMM_WINDOW_KB", 0)
         lib.lcpc_b200_set_tunable(b"SPMM_SLICE_KB", 0)
+        lib.lcpc_b200_set_tunable(b"SPMM_PIPE", 0)
 
 
 @pytest.mark.parametrize("field,length,seed", [(P.FT127, 1 << 14, 0), (P.FT127, (1 << 16) - 11, 1), (P.FT255, 1 << 13, 0),

@@ -54,6 +54,35 @@ def test_field_constants(field):
     assert (c["inv"] * c["p"] + 1) % (1 << 64) == 0
 
 
+def test_montgomery_convention_on_a_published_instance():
+    """The formulas test_field_constants holds the oracle to -- R = 2^(64 L) mod p with L the least limb count such
+    that 2p <= 2^(64 L) (ff_derive's rule), INV = -p^-1 mod 2^64, ROOT_OF_UNITY = gen^((p-1)/2^S) in Montgomery form,
+    limbs little-endian -- reproduce the constants the `bls12_381` crate publishes for its scalar field (same
+    `ff::PrimeField` convention; src/scalar.rs: MODULUS, R, R2, INV, GENERATOR = 7, S = 32, ROOT_OF_UNITY)."""
+    q = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+    L = 1
+    while (1 << (64 * L)) < 2 * q:
+        L += 1
+    assert L == 4
+    R = (1 << (64 * L)) % q
+
+    def limbs(v):
+        return [(v >> (64 * i)) & ((1 << 64) - 1) for i in range(L)]
+
+    assert limbs(R) == [0x00000001fffffffe, 0x5884b7fa00034802, 0x998c4fefecbc4ff5, 0x1824b159acc5056f]
+    assert limbs(R * R % q) == [0xc999e990f3f29c6d, 0x2b6cedcb87925c23, 0x05d314967254398f, 0x0748d9d99f59ff11]
+    assert (-pow(q, -1, 1 << 64)) % (1 << 64) == 0xfffffffeffffffff
+    rou = pow(7, (q - 1) >> 32, q)
+    assert limbs(rou * R % q) == [0xb9b58d8c5f0e466a, 0x5b1b4c801819d7ec, 0x0af53ae352a31e64, 0x5bf3adda19e9b27b]
+    # the four test fields follow the same limb rule (and the reference declares exactly these array lengths,
+    # lcpc-test-fields/src/lib.rs:22,34,46,58)
+    for field, c in CONSTS.items():
+        n = 1
+        while (1 << (64 * n)) < 2 * c["p"]:
+            n += 1
+        assert n == O.FIELD_LIMBS[field]
+
+
 @pytest.mark.parametrize("field", FIELDS)
 def test_field_ops_vs_bigint(field):
     p = CONSTS[field]["p"]
@@ -348,3 +377,57 @@ def test_random_elems_from_key_is_the_serial_rejection_draw():
                 got.append(v)
         want = O.random_elems_from_key(field, key, 20)
         assert [sum(int(want[i, j]) << (64 * j) for j in range(nl)) for i in range(20)] == got
+
+
+# ------------------------------------------------------------------ third-party conventions pinned to PUBLISHED vectors
+# The crates that hold these conventions are not vendored in the reference and no Rust toolchain exists here, so the
+# oracle's restatements are held to the vectors those crates' own test suites assert (quoted from their sources).
+CHACHA_ZERO_KEY_BLOCK0 = [0xade0b876, 0x903df1a0, 0xe56a5d40, 0x28bd8653, 0xb819d2bd, 0x1aed8da0, 0xccef36a8, 0xc70d778b,
+                          0x7c5941da, 0x8d485751, 0x3fe02477, 0x374ad8b8, 0xf4b8436a, 0x1ca11815, 0x69b687c3, 0x8665eeb2]
+CHACHA_ZERO_KEY_BLOCK1 = [0xbee7079f, 0x7a385155, 0x7c97ba98, 0x0d082d73, 0xa0290fcb, 0x6965e348, 0x3e53c612, 0xed7aee32,
+                          0x7621b729, 0x434ee69c, 0xb03371d5, 0xd539d874, 0x281fed31, 0x45fb0a51, 0x1f0ae1ac, 0x6f4d794b]
+CHACHA_ZERO_KEY_NONCE2 = [0x374dc6c2, 0x3736d58c, 0xb904e24a, 0xcd3f93ef, 0x88228b1a, 0x96a4dfb3, 0x5b76ab72, 0xc727ee54,
+                          0x0e0e978a, 0xf3145c95, 0x1b748ea8, 0xf786c297, 0x99c28f5f, 0x628314e8, 0x398a19fa, 0x6ded1b53]
+
+
+def test_chacha20rng_true_values_of_rand_chacha():
+    """rand_chacha 0.3 src/chacha.rs `test_chacha_true_values_a` (IETF draft vectors 1 and 2: zero key, blocks 0 and 1
+    of one stream => the 64-bit block counter sits in state words 12-13 and output words are consumed in order) and
+    `test_chacha_nonce` (zero key, `set_stream(2u64 << (24 + 32))` => the stream id sits in words 14-15)."""
+    zero = np.zeros(8, np.uint32)
+    assert [int(w) for w in O.chacha_block(zero, 0, 0)] == CHACHA_ZERO_KEY_BLOCK0
+    assert [int(w) for w in O.chacha_block(zero, 1, 0)] == CHACHA_ZERO_KEY_BLOCK1
+    assert [int(w) for w in O.chacha_block(zero, 0, 2 << 56)] == CHACHA_ZERO_KEY_NONCE2
+
+
+def test_chacha20rng_construction_vector_of_rand_chacha():
+    """rand_chacha 0.3 `test_chacha_construction`: from_seed([0,0,0,0,0,0,0,0, 1,0,..., 2,0,..., 3,0,...]) then
+    next_u32() == 137206642 -- the 32 seed bytes are the key as little-endian words."""
+    seed = bytes([0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 3, 0, 0, 0, 0, 0, 0, 0])
+    key = np.frombuffer(seed, dtype="<u4")
+    assert int(O.chacha_block(key, 0, 0)[0]) == 137206642
+
+
+def _pcg32_seed_bytes(state, n_bytes):
+    """rand_core 0.6 SeedableRng::seed_from_u64: PCG32 (XSH RR) steps, one little-endian u32 per 4 seed bytes."""
+    M, out = (1 << 64) - 1, b""
+    for _ in range(n_bytes // 4):
+        state = (state * 6364136223846793005 + 11634580027462260723) & M
+        xs, rot = (((state >> 18) ^ state) >> 27) & 0xFFFFFFFF, state >> 59
+        out += (((xs >> rot) | (xs << ((32 - rot) & 31))) & 0xFFFFFFFF).to_bytes(4, "little")
+    return out
+
+
+def test_seed_from_u64_value_of_rand_core_and_the_oracle_draw():
+    """rand_core 0.6 `test_seed_from_u64` asserts seed_from_u64(0) of an 8-byte-seed RNG == 5029875928683246316; the
+    oracle's seeded element draw (matgen's and random_coeffs' shape: ChaCha20Rng::seed_from_u64(seed), set_stream,
+    F::random) must be the rejection sampling of exactly the ChaCha20 stream keyed by that expansion."""
+    assert int.from_bytes(_pcg32_seed_bytes(0, 8), "little") == 5029875928683246316
+    for seed, stream in ((0, 0), (7, 3), ((1 << 64) - 1, 1)):
+        key = np.frombuffer(_pcg32_seed_bytes(seed, 32), dtype="<u4")
+        words = [int(w) for c in range(40) for w in O.chacha_block(key, c, stream)]
+        u64s = [words[2 * i] | (words[2 * i + 1] << 32) for i in range(len(words) // 2)]
+        p = O.field_info(O.FT63)["modulus"]
+        want = [v & ((1 << 63) - 1) for v in u64s if (v & ((1 << 63) - 1)) < p][:100]  # ff_derive random: mask, reject >= p
+        got = [int(v) for v in O.random_elems(O.FT63, 100, seed=seed, stream=stream)[:, 0]]
+        assert got == want

@@ -318,3 +318,77 @@ def test_wire_round_trip_on_random_shapes():
                     P.deserialize_proof(blob[:-cut], field)
 
     run()
+
+
+def test_product_chacha20rng_reproduces_rand_chacha_vectors():
+    """The PRODUCT's host ChaCha20Rng (csrc/host_chacha.h, behind lcpc_b200_sample_columns) against rand_chacha 0.3's own
+    test vectors.  Uniform::new(0, 2^64 - 1) exposes the raw stream: range = 2^64 - 1 gives zone = 2^64 - 2 and
+    (hi, lo) = v * range = (v - 1, 2^64 - v), accepted iff v >= 2, so every draw is next_u64() - 1."""
+    from test_oracle import CHACHA_ZERO_KEY_BLOCK0, CHACHA_ZERO_KEY_BLOCK1
+    words = CHACHA_ZERO_KEY_BLOCK0 + CHACHA_ZERO_KEY_BLOCK1
+    want = [(words[2 * i] | (words[2 * i + 1] << 32)) - 1 for i in range(16)]
+    got = [int(v) for v in P.sample_columns(bytes(32), (1 << 64) - 1, 16)]
+    assert got == want
+    seed = bytes([0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 3, 0, 0, 0, 0, 0, 0, 0])
+    first = int(P.sample_columns(seed, (1 << 64) - 1, 1)[0]) + 1
+    assert first & 0xFFFFFFFF == 137206642  # test_chacha_construction: next_u32() of this seed
+    # and the oracle's Uniform draw agrees on the same degenerate range
+    assert [int(v) for v in PR.sample_columns(bytes(32), (1 << 64) - 1, 16)] == want
+
+
+class _Pcg32:
+    """rand_pcg 0.3 Lcg64Xsh32 (what rand 0.8's own tests use as `crate::test::rng(seed)`)."""
+    MUL, M = 6364136223846793005, (1 << 64) - 1
+
+    def __init__(self, state, stream):
+        self.inc = ((stream << 1) | 1) & self.M
+        self.state = (state + self.inc) & self.M
+        self._step()
+
+    def _step(self):
+        self.state = (self.state * self.MUL + self.inc) & self.M
+
+    def next_u32(self):
+        st = self.state
+        self._step()
+        rot, xsh = st >> 59, (((st >> 18) ^ st) >> 27) & 0xFFFFFFFF
+        return ((xsh >> rot) | (xsh << ((32 - rot) & 31))) & 0xFFFFFFFF
+
+
+def _uniform_new_sample(next_word, low, high, bits):
+    """rand 0.8 `uniform_int_impl!`: Uniform::new(low, high).sample() for an unsigned type of `bits` bits."""
+    mx = (1 << bits) - 1
+    rng_range = (high - low) & mx
+    zone = mx - (mx - rng_range + 1) % rng_range
+    while True:
+        m = next_word() * rng_range
+        if m & mx <= zone:
+            return low + (m >> bits)
+
+
+def _uniform_sample_single(next_word, low, high, bits):
+    rng_range = high - low
+    zone = ((rng_range << (bits - rng_range.bit_length())) - 1) & ((1 << bits) - 1)
+    while True:
+        m = next_word() * rng_range
+        if m & ((1 << bits) - 1) <= zone:
+            return low + (m >> bits)
+
+
+def test_uniform_rejection_zone_is_rand_08s():
+    """rand 0.8 src/distributions/uniform.rs `value_stability`: with rng = Pcg32::new(897, 11634580027462260723),
+    three `sample_single(11u32, 219)` give [17, 66, 214] and then three `Uniform::new(11u32, 219)` samples give
+    [181, 93, 165].  The same macro instantiated for usize (64-bit words) is what prove()/verify() draw column numbers
+    with (lcpc-2d/src/lib.rs:1077-1080) and what matgen draws row indices with (matgen.rs:119,147-158): both the
+    oracle's and the product's draw must equal this restatement fed with the ChaCha20 stream."""
+    rng = _Pcg32(897, 11634580027462260723)
+    assert [_uniform_sample_single(rng.next_u32, 11, 219, 32) for _ in range(3)] == [17, 66, 214]
+    assert [_uniform_new_sample(rng.next_u32, 11, 219, 32) for _ in range(3)] == [181, 93, 165]
+    key = bytes(range(32))
+    kw = np.frombuffer(key, dtype="<u4")
+    for n_cols in (1, 2, 3, 1000, 131072, 357699, (1 << 63) + 12345, (1 << 64) - 1):
+        words = iter(int(w) for c in range(64) for w in O.chacha_block(kw, c, 0))
+        next_u64 = lambda: next(words) | (next(words) << 32)  # noqa: E731  (rand_core: next_u64 = lo word, then hi word)
+        want = [_uniform_new_sample(next_u64, 0, n_cols, 64) for _ in range(200)]
+        assert [int(v) for v in P.sample_columns(key, n_cols, 200)] == want
+        assert [int(v) for v in PR.sample_columns(key, n_cols, 200)] == want

@@ -130,6 +130,7 @@ def test_every_shard_holds_its_column_block_and_the_root(kind, field, length, wo
         s = mc.shard(g)
         assert s.get_root().root == oc["root"]
         assert (s.local_columns() == comm[:, s.col_lo:s.col_hi]).all()
+        assert (s.local_leaves() == oc["hashes"][s.col_lo:s.col_hi]).all()
         assert len(s.phase_times()) == 3
         covered += s.col_hi - s.col_lo
     assert covered == mc.n_cols
