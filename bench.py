@@ -526,6 +526,55 @@ def bench_single(args, ctx, enc, field, n, torch, P, cpu_budget=0.0):
                      "ms_per_step": e2e_s * 1e3, "mode": "device-resident LcCommit; host receives the LcRoot"})
 
 
+def sampled_commit_check(sc, enc, field, n, root0, world, rank, dist, P):
+    """Parity of a sharded commit that is too large for a whole oracle commit (2^26 .. 2^28): checks whose cost does not
+    grow with the matrix.  (1) two whole rows: their column slices are collected from the owners' receive matrices and
+    compared with the oracle's single-row encode of the same coefficients; (2) three columns per rank: the leaf rule
+    (BLAKE3 over 0^32 || canonical bytes) on what the rank received; (3) the whole Merkle tree rebuilt by the oracle
+    from all ranks' leaf digests must end in the sharded LcRoot.  Checker leg: the oracle is called here only."""
+    import oracle as O
+    L = P.FIELD_LIMBS[field]
+    plan = P.shard_plan(sc.n_rows, sc.n_per_row, sc.n_cols, world)
+    cols = sc.local_columns()            # (n_rows, my_cols, L)
+    leaves = sc.local_leaves()
+    ok = True
+    rng = np.random.default_rng(1234 + rank)
+    for c in (rng.integers(0, cols.shape[1], size=3) if cols.shape[1] else []):
+        data = bytes(32) + O.to_repr(field, np.ascontiguousarray(cols[:, int(c)])).tobytes()
+        ok = ok and leaves[int(c)].tobytes() == O.blake3(data)
+    rows = sorted({0, sc.n_rows // 2 + 1 if sc.n_rows > 2 else 0, sc.n_rows - 1})
+    slices = [None] * world
+    dist.all_gather_object(slices, (np.ascontiguousarray(cols[rows]), leaves, ok))
+    verdict = [None]
+    if rank == 0:
+        ok = all(s[2] for s in slices)
+        if enc.__class__.__name__ == "LigeroEncoding":
+            oenc = O.Encoding.ligero_from_dims(field, enc.n_per_row, enc.n_cols)
+        else:
+            pre, post = enc.matrices()
+            oenc = O.Encoding.sdig_from_matrices(field, pre, post)
+        for i, r in enumerate(rows):
+            owner = max(g for g in range(world) if plan["row_lo"][g] <= r)
+            lo = plan["row_lo"][owner] * sc.n_per_row
+            hi = min(plan["row_lo"][owner + 1] * sc.n_per_row, n)
+            xo = synthetic_coeffs(field, max(hi - lo, 0), seed=1000 + owner)
+            row = np.zeros((sc.n_cols, L), np.uint64)
+            seg = xo[(r - plan["row_lo"][owner]) * sc.n_per_row:(r - plan["row_lo"][owner] + 1) * sc.n_per_row]
+            row[:seg.shape[0]] = seg
+            got = np.concatenate([s[0][i] for s in slices], axis=0)
+            ok = ok and bool((oenc.encode(row) == got).all())
+        np2 = 1 << (sc.n_cols - 1).bit_length()
+        hashes = np.zeros((np2, 32), np.uint8)
+        hashes[:sc.n_cols] = np.concatenate([s[1] for s in slices], axis=0)
+        ok = ok and O.merkle_tree(hashes)[-1].tobytes() == root0.root
+        verdict[0] = ("sampled: %d whole rows equal the oracle's encode, 3 columns per rank satisfy the leaf rule, the "
+                      "oracle's Merkle tree over all %d leaf digests ends in the sharded LcRoot" % (len(rows), sc.n_cols)
+                      if ok else "MISMATCH")
+    dist.broadcast_object_list(verdict, src=0)
+    assert verdict[0] != "MISMATCH", "sharded commit fails the sampled oracle check"
+    return verdict[0]
+
+
 def bench_sharded(args, ctx, enc, field, n, torch, P):
     """The N>1 arm: one process per GPU, the commit sharded behind the C ABI (lcpc_b200_shard_*, csrc/shard.cu).
     torch.distributed carries the windows' IPC handles at construction and the barriers / max-reductions of the
@@ -600,7 +649,9 @@ def bench_sharded(args, ctx, enc, field, n, torch, P):
     # rebuilds every rank's slice; the oracle is bench.py's checker leg).  Beyond 2^24 the oracle would need minutes
     # and tens of GiB: there the sharded root is compared with a single-GPU commit of the same polynomial only if it
     # fits, else skipped.
-    root_check = "skipped (size)"
+    root_check = None
+    if n > (1 << 24):
+        root_check = sampled_commit_check(sc, enc, field, n, root0, world, rank, dist, P)
     if n <= (1 << 24):
         if rank == 0:
             plan = P.shard_plan(sc.n_rows, sc.n_per_row, sc.n_cols, world)

@@ -40,6 +40,18 @@ int lcpc_b200_sdig_code_matrix(const lcpc_b200_sdig_code *c, size_t level, int i
 /* convenience: lcpc_b200_sdig_new on every matrix of a generated code */
 int lcpc_b200_sdig_new_from_code(lcpc_b200_ctx *ctx, const lcpc_b200_sdig_code *c, lcpc_b200_enc **out);
 
+/* SdigEncodingS::new (lcpc-brakedown-pc/src/lib.rs:103-110) without host matrices: matgen::generate (matgen.rs:28-52,
+ * 114-188) runs ON THE DEVICE -- the sequential ChaCha20 draw of every level is resolved in parallel (keystream, "where
+ * would a column starting at word s end" for every s, pointer doubling over that map) -- straight into the gather form
+ * the encoder reads, bit-identical to lcpc_b200_sdig_code_generate.  Codes are cached per context and
+ * (field, code, n_per_row, seed).  n_per_row: as chosen by lcpc_b200_sdig_choose_n_per_row. */
+int lcpc_b200_sdig_new_seeded(lcpc_b200_ctx *ctx, int field, int code, size_t n_per_row, uint64_t seed, lcpc_b200_enc **out);
+/* levels of a Brakedown encoding; one matrix of a device-generated code back in the reference's CSC form: exactly *d
+ * sorted row indices per input column (ptrs[c] = c * d); idxs / data: n * d entries each, either may be NULL */
+size_t lcpc_b200_enc_sdig_levels(const lcpc_b200_enc *enc);
+int lcpc_b200_enc_sdig_matrix(lcpc_b200_enc *enc, size_t level, int is_post, size_t *m, size_t *n, size_t *d, uint64_t *idxs,
+                              uint64_t *data);
+
 /* merlin::Transcript (merlin 2.0: STROBE-128 over Keccak-f[1600]), the Fiat-Shamir transcript of prove()/verify()
  * (lcpc-2d/src/lib.rs:16, :304-311, :518-527).  Sequential host work; in a Rust integration this stays merlin. */
 int lcpc_b200_transcript_new(const uint8_t *label, size_t n, lcpc_b200_transcript **out); /* Transcript::new */

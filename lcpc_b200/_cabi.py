@@ -159,6 +159,9 @@ SIGNATURES = {
     "lcpc_b200_sdig_code_codeword_length": (_sz, [_vp]),
     "lcpc_b200_sdig_code_matrix": (_i, [_vp, _sz, _i, C.POINTER(Csc)]),
     "lcpc_b200_sdig_new_from_code": (_i, [_vp, _vp, _pvp]),
+    "lcpc_b200_sdig_new_seeded": (_i, [_vp, _i, _i, _sz, _u64, _pvp]),
+    "lcpc_b200_enc_sdig_levels": (_sz, [_vp]),
+    "lcpc_b200_enc_sdig_matrix": (_i, [_vp, _sz, _i, _psz, _psz, _psz, _vp, _vp]),
     "lcpc_b200_transcript_new": (_i, [C.c_char_p, _sz, _pvp]),
     "lcpc_b200_transcript_clone": (_i, [_vp, _pvp]),
     "lcpc_b200_transcript_free": (None, [_vp]),

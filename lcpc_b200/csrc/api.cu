@@ -14,8 +14,10 @@
 #include <vector>
 
 #include "api_internal.h"
+#include "expander_internal.h"
 #include "field.cuh"
 #include "host_chacha.h"
+#include "host_matgen.h"
 
 using namespace lcpc;
 
@@ -170,6 +172,7 @@ void ctx_unref(lcpc_b200_ctx *ctx) {
   if (ctx->side_done) cudaEventDestroy(ctx->side_done);
   if (ctx->lane_fork) cudaEventDestroy(ctx->lane_fork);
   if (ctx->lane_join) cudaEventDestroy(ctx->lane_join);
+  for (auto &e : ctx->code_cache) expander_free(e.ptr);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   delete ctx;
@@ -281,6 +284,67 @@ int lcpc_b200_sdig_new(lcpc_b200_ctx *ctx, int field, size_t n_levels, const lcp
   *out = e;
   return LCPC_B200_OK;
 }
+
+// SdigEncodingS::new / _new_from_np1 (lcpc-brakedown-pc/src/lib.rs:69-110) with the code drawn ON THE DEVICE
+// (device_matgen.cu) and cached per context
+int lcpc_b200_sdig_new_seeded(lcpc_b200_ctx *ctx, int field, int code, size_t n_per_row, uint64_t seed, lcpc_b200_enc **out) {
+  if (!ctx || !out) return LCPC_B200_ERR_BAD_ARG;
+  *out = nullptr;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (field_limbs32(field) < 0) return fail(ctx, LCPC_B200_ERR_BAD_ARG, "unknown field %d", field);
+  lcpc::host::CodeSpec spec;
+  if (!lcpc::host::sdig_code_spec(code, &spec)) return fail(ctx, LCPC_B200_ERR_BAD_ARG, "unknown code spec %d", code);
+  if (int rc = bind_device(ctx)) return rc;
+  ExpanderCode *ec = nullptr;
+  for (auto &e : ctx->code_cache)
+    if (e.field == field && e.code == code && e.n_per_row == n_per_row && e.seed == seed) ec = e.ptr;
+  if (!ec) {
+    std::vector<lcpc::host::LevelDims> pre_d, post_d;
+    if (int rc = lcpc::host::sdig_level_dims(field, spec, n_per_row, &pre_d, &post_d)) return fail(ctx, rc, "sdig: bad row length %zu", n_per_row);
+    std::vector<MatgenDims> pre(pre_d.size()), post(post_d.size());
+    for (size_t i = 0; i < pre_d.size(); i++) pre[i] = {pre_d[i].n, pre_d[i].m, pre_d[i].d}, post[i] = {post_d[i].n, post_d[i].m, post_d[i].d};
+    std::string err;
+    int rc = device_matgen(field, seed, pre.size(), pre.data(), post.data(), ctx->stream, &ec, &err);
+    if (rc != LCPC_B200_OK) return fail(ctx, rc, "sdig_new_seeded: %s", err.c_str());
+    ctx->launches += 14 * 2 * pre.size();
+    ctx->code_cache.push_back({field, code, n_per_row, seed, ec});  // the cache owns the first reference
+  }
+  lcpc_b200_enc *e = new (std::nothrow) lcpc_b200_enc;
+  if (!e) return LCPC_B200_ERR_OOM;
+  expander_retain(ec);
+  e->ctx = ctx, e->kind = LCPC_B200_ENC_SDIG, e->field = field;
+  e->n_per_row = expander_n_in(ec), e->n_cols = expander_codeword_length(ec);
+  e->code = ec;
+  ctx->refs.fetch_add(1);
+  *out = e;
+  return LCPC_B200_OK;
+}
+
+// one matrix of a device-generated code in the reference's own form (CsMat::new_csc, matgen.rs:187): exactly *d sorted
+// row indices per input column, so ptrs[c] = c * d; idxs: n*d row indices, data: n*d elements (either may be NULL)
+int lcpc_b200_enc_sdig_matrix(lcpc_b200_enc *enc, size_t level, int is_post, size_t *m, size_t *n, size_t *d, uint64_t *idxs,
+                              uint64_t *data) {
+  if (!enc || enc->kind != LCPC_B200_ENC_SDIG || !enc->code) return LCPC_B200_ERR_BAD_ARG;
+  lcpc_b200_ctx *ctx = enc->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  const ExpanderCode *c = enc->code;
+  if (level >= c->n_levels) return fail(ctx, LCPC_B200_ERR_BAD_ARG, "level %zu of %zu", level, c->n_levels);
+  const DeviceCsr &M = c->mats[is_post ? c->n_levels + level : level];
+  if (m) *m = M.m;
+  if (n) *n = M.n;
+  if (d) *d = M.csc_d;
+  if (!idxs && !data) return LCPC_B200_OK;
+  if (!M.csc_idx) return fail(ctx, LCPC_B200_ERR_UNSUPPORTED, "this encoding was built from host matrices; the host holds them");
+  if (int rc = bind_device(ctx)) return rc;
+  if (idxs) {
+    std::vector<uint32_t> tmp(M.nnz);
+    CU(ctx, cudaMemcpy(tmp.data(), M.csc_idx, M.nnz * 4, cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < M.nnz; k++) idxs[k] = tmp[k];
+  }
+  if (data) CU(ctx, cudaMemcpy(data, M.csc_data, M.nnz * field_bytes(enc->field), cudaMemcpyDeviceToHost));
+  return LCPC_B200_OK;
+}
+size_t lcpc_b200_enc_sdig_levels(const lcpc_b200_enc *enc) { return (enc && enc->code) ? enc->code->n_levels : 0; }
 
 void enc_unref(lcpc_b200_enc *enc) {
   if (enc->refs.fetch_sub(1) != 1) return;  // commits made with this encoding are still alive

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/lcpc_b200.h"
 #include "../../include/lcpc_b200_host.h"
@@ -42,6 +43,16 @@ struct lcpc_b200_ctx {
   // grow-only device scratch shared by the stateless entry points
   void *scratch = nullptr;
   size_t scratch_bytes = 0;
+  // Brakedown codes generated on this device from (field, code spec, n_per_row, seed): kept for the context's
+  // lifetime, so building the same encoding again (another commit length with the same row length, a verifier next
+  // to a prover) costs nothing (matgen_bench of the reference, lcpc-brakedown-pc/src/bench.rs:22-30, is this setup)
+  struct SeededCode {
+    int field, code;
+    size_t n_per_row;
+    uint64_t seed;
+    lcpc::ExpanderCode *ptr;
+  };
+  std::vector<SeededCode> code_cache;
   // grow-only page-locked host staging (results the host has to read right away: canonical bytes for the transcript)
   void *h_stage = nullptr;
   size_t h_stage_bytes = 0;

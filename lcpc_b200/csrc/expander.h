@@ -27,7 +27,8 @@ struct SideLane {
 // uploads the code in gather (row-compressed) form; returns an LCPC_B200_* status
 int expander_build(int field, size_t n_levels, const CscView *pre, const CscView *post, cudaStream_t stream,
                    ExpanderCode **out, std::string *err);
-void expander_free(ExpanderCode *code);
+void expander_free(ExpanderCode *code);   // drops one reference
+void expander_retain(ExpanderCode *code);
 size_t expander_n_in(const ExpanderCode *code);
 size_t expander_codeword_length(const ExpanderCode *code);  // encode.rs:18-33
 size_t expander_nnz(const ExpanderCode *code);

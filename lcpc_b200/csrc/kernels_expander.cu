@@ -22,54 +22,26 @@
 #include <vector>
 
 #include "../../include/lcpc_b200.h"
-#include "expander.h"
+#include "expander_internal.h"
 #include "field.cuh"
 #include "kernels.h"
 
 namespace lcpc {
 
-constexpr size_t FUSED_SMEM_BYTES = 40 << 10;  // window + temporary of the fused innermost levels
-constexpr int MAX_FUSED_OPS = 16;
-
-struct DeviceCsr {
-  size_t m = 0, n = 0, nnz = 0;
-  uint32_t *rowptr = nullptr;  // m + 1
-  uint32_t *colidx = nullptr;  // nnz, ascending within a row
-  uint32_t *vals = nullptr;    // nnz * N limbs
-  // column-chunked schedule (see spmm_kernel): seg[q * m + i] = first non-zero of row i whose column is >= q * n / seg_q,
-  // q = 0 .. seg_q; built on first use for a given chunk count and kept
-  mutable uint32_t *seg = nullptr;
-  mutable unsigned seg_q = 0;
-};
-
-struct ExpanderOp {
-  int kind;  // 0 = sparse product, 1 = reed-solomon
-  int mat;   // index into mats (kind 0)
-  size_t in_off, in_len, out_off, out_len;
-  bool out_tmp, in_tmp;  // x_t lives in the temporary
-};
-
-struct ExpanderCode {
-  int field = 0;
-  size_t n_levels = 0, n_in = 0, n_cols = 0, nnz = 0, tmp_len = 0;
-  std::vector<DeviceCsr> mats;
-  std::vector<ExpanderOp> ops;
-  // ops [fuse_lo, fuse_hi] (the innermost levels around the Reed-Solomon base) touch only the codeword window
-  // [win_lo, win_lo + win_len) and run as ONE kernel with that window in shared memory; fuse_lo > fuse_hi: none
-  size_t fuse_lo = 1, fuse_hi = 0, win_lo = 0, win_len = 0;
-};
-
+void expander_retain(ExpanderCode *c) { c->refs++; }
 size_t expander_n_in(const ExpanderCode *c) { return c->n_in; }
 size_t expander_codeword_length(const ExpanderCode *c) { return c->n_cols; }
 size_t expander_nnz(const ExpanderCode *c) { return c->nnz; }
 
 void expander_free(ExpanderCode *c) {
-  if (!c) return;
+  if (!c || --c->refs > 0) return;
   for (auto &m : c->mats) {
     cudaFree(m.rowptr);
     cudaFree(m.colidx);
     cudaFree(m.vals);
     cudaFree(m.seg);
+    cudaFree(m.csc_idx);
+    cudaFree(m.csc_data);
   }
   delete c;
 }
@@ -123,66 +95,53 @@ static int upload_csr(int field, const CscView &M, cudaStream_t stream, DeviceCs
   return LCPC_B200_OK;
 }
 
-int expander_build(int field, size_t t, const CscView *pre, const CscView *post, cudaStream_t stream,
-                   ExpanderCode **out, std::string *err) {
-  ExpanderCode *c = new ExpanderCode;
-  c->field = field, c->n_levels = t;
+int expander_assemble(ExpanderCode *c, size_t t, std::string *err) {
   // offsets exactly as encode.rs:36-94 walks them
-  c->n_in = pre[0].n;
-  size_t len = pre[0].n + post[t - 1].n;  // codeword_length, encode.rs:18-33
-  for (size_t i = 0; i + 1 < t; i++) len += pre[i].m;
-  for (size_t i = 0; i < t; i++) len += post[i].m;
+  auto pre = [&](size_t i) -> const DeviceCsr & { return c->mats[i]; };
+  auto post = [&](size_t i) -> const DeviceCsr & { return c->mats[t + i]; };
+  c->n_levels = t;
+  c->n_in = pre(0).n;
+  size_t len = pre(0).n + post(t - 1).n;  // codeword_length, encode.rs:18-33
+  for (size_t i = 0; i + 1 < t; i++) len += pre(i).m;
+  for (size_t i = 0; i < t; i++) len += post(i).m;
   c->n_cols = len;
-  c->mats.resize(2 * t);
-  int rc = LCPC_B200_OK;
+  c->ops.clear();
   size_t in_start = 0;
-  for (size_t i = 0; i < t && rc == LCPC_B200_OK; i++) {
-    if (i + 1 < t && pre[i + 1].n != pre[i].m) {
+  for (size_t i = 0; i < t; i++) {
+    if (i + 1 < t && pre(i + 1).n != pre(i).m) {
       *err = "precode dimensions do not chain";
-      rc = LCPC_B200_ERR_BAD_ARG;
-      break;
+      return LCPC_B200_ERR_BAD_ARG;
     }
-    rc = upload_csr(field, pre[i], stream, &c->mats[i], err);
-    if (rc != LCPC_B200_OK) break;
-    size_t in_end = in_start + pre[i].n;
-    ExpanderOp op{0, (int)i, in_start, pre[i].n, in_end, pre[i].m, i + 1 == t, false};
+    size_t in_end = in_start + pre(i).n;
+    ExpanderOp op{0, (int)i, in_start, pre(i).n, in_end, pre(i).m, i + 1 == t, false};
     c->ops.push_back(op);
     in_start = in_end;
   }
-  size_t out_start = 0;
-  if (rc == LCPC_B200_OK) {
-    // base case: in_start is now the end of x_{t-1}; RS(x_t) fills [in_start, in_start + post[t-1].n)
-    c->tmp_len = pre[t - 1].m;
-    ExpanderOp rs{1, -1, 0, pre[t - 1].m, in_start, post[t - 1].n, false, true};
-    c->ops.push_back(rs);
-    out_start = in_start + post[t - 1].n;
-    in_start = in_start + pre[t - 1].m;
-    for (size_t i = t; i-- > 0 && rc == LCPC_B200_OK;) {
-      in_start -= pre[i].m;
-      if (out_start - in_start != post[i].n) {
-        *err = "postcode dimensions do not match the codeword slice";
-        rc = LCPC_B200_ERR_BAD_ARG;
-        break;
-      }
-      rc = upload_csr(field, post[i], stream, &c->mats[t + i], err);
-      if (rc != LCPC_B200_OK) break;
-      ExpanderOp op{0, (int)(t + i), in_start, post[i].n, out_start, post[i].m, false, false};
-      c->ops.push_back(op);
-      out_start += post[i].m;
+  // base case: in_start is now the end of x_{t-1}; RS(x_t) fills [in_start, in_start + post[t-1].n)
+  c->tmp_len = pre(t - 1).m;
+  ExpanderOp rs{1, -1, 0, pre(t - 1).m, in_start, post(t - 1).n, false, true};
+  c->ops.push_back(rs);
+  size_t out_start = in_start + post(t - 1).n;
+  in_start = in_start + pre(t - 1).m;
+  for (size_t i = t; i-- > 0;) {
+    in_start -= pre(i).m;
+    if (out_start - in_start != post(i).n) {
+      *err = "postcode dimensions do not match the codeword slice";
+      return LCPC_B200_ERR_BAD_ARG;
     }
+    ExpanderOp op{0, (int)(t + i), in_start, post(i).n, out_start, post(i).m, false, false};
+    c->ops.push_back(op);
+    out_start += post(i).m;
   }
-  if (rc == LCPC_B200_OK && (in_start != pre[0].n || out_start != len)) {  // asserts at encode.rs:92-93
+  if (in_start != pre(0).n || out_start != len) {  // asserts at encode.rs:92-93
     *err = "codeword offsets do not close";
-    rc = LCPC_B200_ERR_BAD_ARG;
+    return LCPC_B200_ERR_BAD_ARG;
   }
-  if (rc != LCPC_B200_OK) {
-    expander_free(c);
-    return rc;
-  }
+  c->nnz = 0;
   for (auto &m : c->mats) c->nnz += m.nnz;
   // innermost levels: grow the window outwards from the base code while it fits the shared-memory budget
   {
-    const size_t cap_elems = FUSED_SMEM_BYTES / field_bytes(field);
+    const size_t cap_elems = FUSED_SMEM_BYTES / field_bytes(c->field);
     const size_t q = t;  // index of the Reed-Solomon op: ops = pre_0..pre_{t-1}, RS, post_{t-1}..post_0
     size_t lo = q, hi = q;
     size_t wlo = c->ops[q].out_off, wend = c->ops[q].out_off + c->ops[q].out_len;
@@ -192,7 +151,24 @@ int expander_build(int field, size_t t, const CscView *pre, const CscView *post,
       if (nend - nlo + c->tmp_len > cap_elems || (hi - lo + 1) + 2 > (size_t)MAX_FUSED_OPS) break;
       lo--, hi++, wlo = nlo, wend = nend;
     }
+    c->fuse_lo = 1, c->fuse_hi = 0;
     if (hi > lo) c->fuse_lo = lo, c->fuse_hi = hi, c->win_lo = wlo, c->win_len = wend - wlo;
+  }
+  return LCPC_B200_OK;
+}
+
+int expander_build(int field, size_t t, const CscView *pre, const CscView *post, cudaStream_t stream,
+                   ExpanderCode **out, std::string *err) {
+  ExpanderCode *c = new ExpanderCode;
+  c->field = field;
+  c->mats.resize(2 * t);
+  int rc = LCPC_B200_OK;
+  for (size_t i = 0; i < t && rc == LCPC_B200_OK; i++) rc = upload_csr(field, pre[i], stream, &c->mats[i], err);
+  for (size_t i = 0; i < t && rc == LCPC_B200_OK; i++) rc = upload_csr(field, post[i], stream, &c->mats[t + i], err);
+  if (rc == LCPC_B200_OK) rc = expander_assemble(c, t, err);
+  if (rc != LCPC_B200_OK) {
+    expander_free(c);
+    return rc;
   }
   *out = c;
   return LCPC_B200_OK;

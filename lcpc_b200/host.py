@@ -235,6 +235,17 @@ class SdigEncoding(LcEncoding):
 
     def _init_dims(self, field, n_per_row, n_cols, seed, code, ctx):
         ctx = ctx or default_context()
+        if _device_matgen_enabled():
+            # matgen::generate on the device (csrc/device_matgen.cu), cached per context: no host matrices at all
+            h = C.c_void_p()
+            _check(_cabi.lib().lcpc_b200_sdig_new_seeded(ctx._h, field, code, n_per_row, seed, C.byref(h)), ctx)
+            self.code, self.seed, self._code_h, self._given = code, seed, None, None
+            LcEncoding.__init__(self, ctx, h, field)
+            if n_cols and self.n_cols != n_cols:  # assert_eq! at :129
+                cw = self.n_cols
+                self.close()
+                raise LcpcError(_cabi.ERR_BAD_ARG, f"codeword length {cw} != n_cols {n_cols}")
+            return
         ch = C.c_void_p()
         _check(_cabi.lib().lcpc_b200_sdig_code_generate(field, code, n_per_row, seed, C.byref(ch)))
         self._code_h = ch
@@ -261,8 +272,34 @@ class SdigEncoding(LcEncoding):
         if getattr(self, "_given", None) is not None:
             return self._given
         if not self._code_h:
-            raise LcpcError(_cabi.ERR_BAD_ARG, "encoding is closed: no code matrices")
+            if not self._h:
+                raise LcpcError(_cabi.ERR_BAD_ARG, "encoding is closed: no code matrices")
+            return device_code_matrices(self, self.L)
         return host_code_matrices(self._code_h, self.L)
+
+
+def _device_matgen_enabled() -> bool:
+    """LCPC_B200_MATGEN=host keeps the round-1 path (host generator + upload) for A/B runs and for the tests that
+    compare the two generators; default: on the device."""
+    import os
+    return os.environ.get("LCPC_B200_MATGEN", "device") != "host"
+
+
+def device_code_matrices(enc, L):
+    """The matrices of a device-generated code, downloaded in the reference's CSC form (matgen.rs:187)."""
+    lib = _cabi.lib()
+    t = lib.lcpc_b200_enc_sdig_levels(enc._h)
+    out = ([], [])
+    for is_post in (0, 1):
+        for i in range(t):
+            m, n, d = C.c_size_t(), C.c_size_t(), C.c_size_t()
+            _check(lib.lcpc_b200_enc_sdig_matrix(enc._h, i, is_post, C.byref(m), C.byref(n), C.byref(d), None, None), enc.ctx)
+            nnz = n.value * d.value
+            idxs, data = np.empty(nnz, np.uint64), np.empty((nnz, L), np.uint64)
+            _check(lib.lcpc_b200_enc_sdig_matrix(enc._h, i, is_post, None, None, None, _ptr(idxs), _ptr(data)), enc.ctx)
+            ptrs = np.arange(n.value + 1, dtype=np.uint64) * np.uint64(d.value)
+            out[is_post].append(dict(m=m.value, n=n.value, ptrs=ptrs, idxs=idxs, data=data))
+    return out
 
 
 def host_code_matrices(code_h, L):

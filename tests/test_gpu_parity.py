@@ -584,3 +584,66 @@ def test_contexts_on_two_devices_in_one_process():
     enc2 = P.SdigEncoding(P.FT127, 1 << 12, seed=0, ctx=P.Context(1))
     x2 = O.random_elems(P.FT127, 1 << 12, seed=10)
     assert P.LcCommit.commit(x2, enc2).get_root().root == O.Encoding.sdig(P.FT127, 1 << 12, seed=0).commit(x2)["root"]
+
+
+# ---- f3: the code generator on the device (csrc/device_matgen.cu) -------------------------------------------------
+@pytest.mark.parametrize("field,n,seed,code", [(P.FT127, 1 << 12, 0, 3), (P.FT255, 3000, 1, 3), (P.FT63, 9001, 7, 3),
+                                               (P.FT191, 777, 2, 3), (P.FT127, 50000, 5, 3), (P.FT127, 2500, 3, 1),
+                                               (P.FT255, 1 << 13, 4, 5), (P.FT63, 21, 0, 3), (P.FT127, 400, 9, 6)])
+def test_device_matgen_equals_host_generator_and_oracle(field, n, seed, code):
+    """matgen::generate (matgen.rs:28-52, 114-188) drawn on the device -- keystream, per-word column-end map, pointer
+    doubling, per-column draw -- gives the same CSC arrays, bit for bit, as the host generator (and through it the
+    oracle's, tests/test_host_cpu.py::test_matgen_matches_oracle); the gather form built from it encodes like the
+    oracle."""
+    enc = P.SdigEncoding.new_from_dims(field, n, seed=seed, code=code)
+    assert enc._code_h is None  # no host matrices were made
+    pre, post = enc.matrices()  # downloaded from the device
+    hpre, hpost, cw = P.host.generate_sdig_code(field, n, seed, code)
+    assert cw == enc.n_cols and len(pre) == len(hpre)
+    for got, want in zip(pre + post, hpre + hpost):
+        assert (got["m"], got["n"]) == (want["m"], want["n"])
+        assert (got["ptrs"] == want["ptrs"]).all() and (got["idxs"] == want["idxs"]).all() and (got["data"] == want["data"]).all()
+    opre, opost = O.Encoding.sdig_from_dims(field, n, seed=seed, code=code).matrices()
+    for got, want in zip(pre + post, opre + opost):
+        assert (got["idxs"] == want["idxs"]).all() and (got["data"] == want["data"]).all()
+    oenc = O.Encoding.sdig_from_dims(field, n, seed=seed, code=code)
+    rows = np.zeros((3, enc.n_cols, enc.L), np.uint64)
+    rows[:, :n] = O.random_elems(field, 3 * n, seed=seed + 11).reshape(3, n, -1)
+    got = enc.encode(rows)
+    for r in range(3):
+        assert (got[r] == oenc.encode(rows[r])).all()
+    # the same (field, code, n_per_row, seed) again comes out of the context's cache: same device code, same results
+    again = P.SdigEncoding.new_from_dims(field, n, seed=seed, code=code)
+    assert (again.encode(rows)[1] == got[1]).all()
+    other = P.SdigEncoding.new_from_dims(field, n, seed=seed + 1, code=code)
+    assert not (other.matrices()[0][0]["idxs"] == pre[0]["idxs"]).all()
+
+
+def test_device_matgen_rejects_what_the_reference_asserts():
+    with pytest.raises(P.LcpcError):
+        P.SdigEncoding.new_from_dims(P.FT127, 20, seed=0)      # assert!(n > baselen), matgen.rs:62
+    with pytest.raises(P.LcpcError):
+        P.SdigEncoding.new_from_dims(P.FT127, 4096, n_cols=1, seed=0)  # assert_eq!(codeword_length, n_cols), lib.rs:129
+
+
+def test_device_matgen_headline_shape_setup_time():
+    """2^24 coefficients, Ft127, SdigCode3, seed 0 (config 3): generation + gather form on the device; spot-check the
+    first and last columns of the big matrices against the host generator's stream, and time the setup."""
+    import time
+    field, n = P.FT127, 1 << 24
+    ctx = P.Context(0)
+    t0 = time.perf_counter()
+    enc = P.SdigEncoding(field, n, seed=0, ctx=ctx)
+    ctx.synchronize()
+    dt = time.perf_counter() - t0
+    assert (enc.n_per_row, enc.n_cols) == (235173, 357699)
+    t0 = time.perf_counter()
+    enc2 = P.SdigEncoding(field, n, seed=0, ctx=ctx)   # cached
+    dt2 = time.perf_counter() - t0
+    print(f"device matgen 2^24: {dt * 1e3:.1f} ms, cached: {dt2 * 1e3:.2f} ms")
+    assert dt2 < dt
+    hpre, hpost, _ = P.host.generate_sdig_code(field, enc.n_per_row, 0, 3)
+    pre, post = enc.matrices()
+    for got, want in zip(pre + post, hpre + hpost):
+        assert (got["idxs"] == want["idxs"]).all() and (got["data"] == want["data"]).all()
+    enc2.close()
