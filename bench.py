@@ -405,6 +405,16 @@ def bench_single(args, ctx, enc, field, n, torch, P, cpu_budget=0.0):
         r = commit.get_root()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     assert r == root0
+    # the floor under e2e: the same host->device copy alone
+    scratch = torch.empty_like(dev)
+    scratch.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        scratch.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_only_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+    del scratch
     # the eager variant of the same call: every LcCommit field back in (pinned) host memory, as the reference's
     # commit() returns them -- comm + coeffs + hashes cross PCIe too
     eager = None
@@ -523,7 +533,9 @@ def bench_single(args, ctx, enc, field, n, torch, P, cpu_budget=0.0):
                 dominant=dominant, code_bytes=code_bytes, prove=prove, e2e_eager=eager, root_check=root_check,
                 cpu_baseline=cpu_baseline,
                 e2e={"value": n / e2e_s, "unit": "field-elts/s", "h2d_bytes_per_step": int(n * B), "d2h_bytes_per_step": 32,
-                     "ms_per_step": e2e_s * 1e3, "mode": "device-resident LcCommit; host receives the LcRoot"})
+                     "ms_per_step": e2e_s * 1e3, "h2d_only_ms": h2d_only_ms,
+                     "mode": "device-resident LcCommit; host receives the LcRoot; h2d_only_ms = the same copy with no "
+                             "compute (the PCIe floor of this box)"})
 
 
 def sampled_commit_check(sc, enc, field, n, root0, world, rank, dist, P):
@@ -643,6 +655,23 @@ def bench_sharded(args, ctx, enc, field, n, torch, P):
     clocks = sampler.stop()
     for k in range(e2e_steps + 2):
         assert roots[k].numpy().tobytes() == root0.root, "e2e: a step's LcRoot differs"
+    # the floor under e2e on this box: the same host->device copies alone, all ranks at once (PCIe + host memory)
+    h2d_only_ms = None
+    if host.numel():
+        scratch = torch.empty_like(host, device="cuda")
+        for _ in range(2):
+            scratch.copy_(host, non_blocking=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            scratch.copy_(host, non_blocking=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        h2d = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device="cuda")
+        dist.all_reduce(h2d, op=dist.ReduceOp.MAX)
+        h2d_only_ms = float(h2d.item()) * 1e3
+        del scratch
     ms_per_step = float(ms.item()) / args.steps
     e2e_s = float(e2e.item())
     # parity at the benchmarked size: the sharded LcRoot == the oracle's commit of the same polynomial (rank 0
@@ -708,9 +737,10 @@ def bench_sharded(args, ctx, enc, field, n, torch, P):
                   phases_ms={"encode_and_scatter": float(ph[0]), "exchange_wait": float(ph[1]), "hash_merkle_root": float(ph[2])},
                   dominant=dominant,
                   e2e={"value": n / e2e_s, "unit": "field-elts/s", "h2d_bytes_per_step": int(n * B),
-                       "d2h_bytes_per_step": 32 * world, "ms_per_step": e2e_s * 1e3,
+                       "d2h_bytes_per_step": 32 * world, "ms_per_step": e2e_s * 1e3, "h2d_only_ms": h2d_only_ms,
                        "mode": "row blocks from pinned host memory on every rank, LcRoot back to pinned host memory "
-                               "on every rank, every step; steps pipelined on the device streams"})
+                               "on every rank, every step; steps pipelined on the device streams; h2d_only_ms = the same "
+                               "copies with no compute, all ranks at once (the floor this box's PCIe / host memory sets)"})
     sc.enc.ctx.synchronize()
     dist.barrier()
     sc.close()

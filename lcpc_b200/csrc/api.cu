@@ -657,6 +657,7 @@ static int commit_run(lcpc_b200_commit *c, const void *src, size_t len, cudaMemc
   const size_t padded = c->n_rows * c->n_per_row;
   uint64_t l0 = ctx->launches;
   HashTrail trail{c->d_hashes, c->d_hash_scratch, 0, leaf_chunk_count(enc->field, c->n_rows), 0};
+  size_t early_cols = 0;  // leading columns whose leaf chunks were hashed on the side stream already
   if (kind == cudaMemcpyHostToDevice && c->n_rows > 1) {
     if (int rc = encode_rows_from_host(enc, src, len, c->d_coeffs, c->d_comm, c->n_rows, c->d_enc_scratch, c->ev[1], nullptr,
                                        &trail, host_out))
@@ -706,6 +707,21 @@ static int commit_run(lcpc_b200_commit *c, const void *src, size_t len, cudaMemc
     // the same for the expander code: the transpose into the work buffer stores the copy and supplies the
     // zero padding of a short last row
     CU(ctx, cudaEventRecord(c->ev[1], st));
+    // The code is systematic: columns [0, n_per_row) of comm ARE the coefficient rows (encode.rs: the codeword starts
+    // with x_0), two thirds of all columns.  Their leaf digests do not depend on the sparse products at all, so they
+    // are hashed straight from the caller's rows on the side stream while the chain runs: BLAKE3 lives on the ALU
+    // pipe, the chain is bound by L2 gather bandwidth.  (A ragged last row would be read past its end: then the
+    // columns wait for the commit's zero-padded copy like the rest.)
+    if (padded == len && trail.n_chunks >= 1 && tunable("SDIG_EARLY_HASH", 1) != 0) {
+      CU(ctx, cudaEventRecord(ctx->lane_fork, st));
+      CU(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->lane_fork, 0));
+      cudaError_t he = launch_leaf_chunks_range(enc->field, (const uint32_t *)src, c->n_rows, c->n_per_row, c->n_per_row, c->d_hashes,
+                                                c->d_hash_scratch, 0, trail.n_chunks, c->n_cols, 0, ctx->side_stream);
+      if (he != cudaSuccess) return cuda_fail(ctx, he, "hash_columns (systematic part)");
+      CU(ctx, cudaEventRecord(ctx->side_done, ctx->side_stream));
+      ctx->launches += 1, trail.launches += 1;
+      early_cols = c->n_per_row;
+    }
     int nl = 0;
     cudaError_t ce = expander_encode_rows(enc->code, (const uint32_t *)src, c->n_per_row, c->n_per_row, c->d_comm, c->n_cols,
                                           c->n_rows, c->d_enc_scratch, st, &nl, nullptr, c->d_coeffs, c->n_per_row, len);
@@ -725,8 +741,10 @@ static int commit_run(lcpc_b200_commit *c, const void *src, size_t len, cudaMemc
   if (c->np2 > c->n_cols) CU(ctx, cudaMemsetAsync(c->d_hashes + c->n_cols * 32, 0, (c->np2 - c->n_cols) * 32, st));
   // column leaves (:706-745): whatever chunks did not already trail the encode, then the per-column chunk merge
   int nl = 0;
-  cudaError_t ce = launch_leaf_chunks(enc->field, c->d_comm, c->n_rows, c->n_cols, c->n_cols, c->d_hashes, c->d_hash_scratch,
-                                      trail.next_chunk, trail.n_chunks - trail.next_chunk, st);
+  cudaError_t ce = launch_leaf_chunks_range(enc->field, c->d_comm + early_cols * (B / 4), c->n_rows, c->n_cols - early_cols, c->n_cols,
+                                            c->d_hashes, c->d_hash_scratch, trail.next_chunk, trail.n_chunks - trail.next_chunk,
+                                            c->n_cols, early_cols, st);
+  if (early_cols) CU(ctx, cudaStreamWaitEvent(st, ctx->side_done, 0));
   if (ce == cudaSuccess) ce = launch_leaf_merge(enc->field, c->n_rows, c->n_cols, c->d_hashes, c->d_hash_scratch, st, &nl);
   nl += 1;
   ctx->launches += nl;

@@ -470,6 +470,172 @@ spmm_pipe_kernel(const uint32_t *__restrict__ seg_lo, const uint32_t *__restrict
   stv<N>(yp, out.v);
 }
 
+// ---- the same product with the gathers done by the SM's bulk-copy engine (TMA, cp.async.bulk) -----------------------
+// A gather of input position j for the whole batch is ONE contiguous run of n_rows * B bytes of the work buffer
+// (1152 B at 2^24): exactly what a 1-D bulk copy moves.  A producer warp walks the non-zero stream of each group of
+// threads (the outputs [i0, i1) of a group are consecutive, so their (column, value) pairs are consecutive in the
+// row-compressed arrays) and keeps a ring of STAGES x U gathers per group in flight -- global -> shared memory,
+// completion counted in bytes on an mbarrier -- while the consumer threads (one per output-in-progress and batch
+// row) multiply out of shared memory.  No registers are held by loads in flight, the depth does not depend on
+// occupancy, and a thread never waits for its own gather.  Fields whose element is a multiple of 16 bytes only
+// (Ft127, Ft255: what the reference benchmarks); the others keep spmm_kernel.
+namespace bulk {
+constexpr int U = 4;        // non-zeros per stage
+constexpr int STAGES = 4;   // ring depth per group
+constexpr int MAX_GROUPS = 32;
+constexpr int CONSUMERS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+}  // namespace bulk
+
+// grid.x: CTAs over groups of outputs; grid.y: batch-row tiles of RT rows.  Block = 32 producer lanes + CONSUMERS.
+// Dynamic shared memory: [full barriers G*STAGES | empty barriers G*STAGES | per group, per stage: U*RT elements, U values]
+template <int FID>
+__global__ void __launch_bounds__(32 + bulk::CONSUMERS)
+spmm_bulk_kernel(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ colidx, const uint32_t *__restrict__ vals,
+                 const uint32_t *__restrict__ x, uint32_t *__restrict__ y, uint32_t m, uint32_t n_rows, uint32_t RT, uint32_t G,
+                 uint32_t outs_per_group) {
+  using F = Field<FID>;
+  constexpr int N = F::N;
+  constexpr int B = F::BYTES;
+  using namespace bulk;
+  extern __shared__ __align__(128) uint8_t bsm[];
+  uint64_t *full = reinterpret_cast<uint64_t *>(bsm);
+  uint64_t *empty = full + G * STAGES;
+  const uint32_t stage_bytes = (U * RT * B + U * B + 127) & ~127u;  // x[U][RT] then vals[U]
+  uint8_t *ring = bsm + ((2 * G * STAGES * 8 + 127) & ~127u);
+  const uint32_t r0 = blockIdx.y * RT;
+  const uint32_t rt = min(RT, n_rows - r0);  // rows of this tile
+  const uint32_t tid = threadIdx.x;
+  if (tid == 0) {
+    for (uint32_t q = 0; q < G * STAGES; q++) {
+      mbar_init(full + q, 1);
+      mbar_init(empty + q, rt);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  // group g of this CTA works on outputs [i0, i1) = non-zeros [K0, K1)
+  auto group_range = [&](uint32_t g, uint32_t &i0, uint32_t &i1) {
+    const uint64_t first = ((uint64_t)blockIdx.x * G + g) * outs_per_group;
+    i0 = (uint32_t)(first < m ? first : m);
+    i1 = (uint32_t)(first + outs_per_group < m ? first + outs_per_group : m);
+  };
+  if (tid < 32) {
+    // ---- producer: lane = (group within a batch of 8, non-zero within the stage) ----
+    const uint32_t lane = tid, u = lane & 3;
+    const uint32_t n_batches = (G + 7) / 8;
+    uint32_t K0[MAX_GROUPS / 8], K1[MAX_GROUPS / 8], s_idx[MAX_GROUPS / 8], jn[MAX_GROUPS / 8];
+#pragma unroll
+    for (uint32_t b = 0; b < MAX_GROUPS / 8; b++) {
+      K0[b] = K1[b] = 0, s_idx[b] = 0, jn[b] = 0;
+      const uint32_t g = b * 8 + (lane >> 2);
+      if (b < n_batches && g < G) {
+        uint32_t i0, i1;
+        group_range(g, i0, i1);
+        K0[b] = __ldg(rowptr + i0), K1[b] = __ldg(rowptr + i1);
+        const uint32_t k = K0[b] + u;
+        if (k < K1[b]) jn[b] = __ldg(colidx + k);
+      }
+    }
+    bool any = true;
+    while (any) {
+      any = false;
+#pragma unroll
+      for (uint32_t b = 0; b < MAX_GROUPS / 8; b++) {
+        if (b >= n_batches) break;
+        const uint32_t g = b * 8 + (lane >> 2);
+        const uint32_t kbase = K0[b] + s_idx[b] * U;
+        const bool live = g < G && kbase < K1[b];
+        if (live) {
+          const uint32_t slot = s_idx[b] % STAGES, round = s_idx[b] / STAGES;
+          uint64_t *fb = full + g * STAGES + slot, *eb = empty + g * STAGES + slot;
+          if (round > 0) mbar_wait(eb, (round - 1) & 1);  // the consumers are done with what this slot held
+          const uint32_t n_valid = min((uint32_t)U, K1[b] - kbase);
+          uint8_t *st = ring + (size_t)(g * STAGES + slot) * stage_bytes;
+          if (u == 0) mbar_expect_tx(fb, n_valid * rt * B + n_valid * B);
+          __syncwarp(__activemask());
+          if (u < n_valid) bulk_g2s(st + (size_t)u * RT * B, x + ((size_t)jn[b] * n_rows + r0) * N, rt * B, fb);
+          if (u == 0) bulk_g2s(st + (size_t)U * RT * B, vals + (size_t)kbase * N, n_valid * B, fb);
+          s_idx[b]++;
+          const uint32_t kn = kbase + U + u;
+          if (kn < K1[b]) jn[b] = __ldg(colidx + kn);  // next stage's column, in flight until the next visit
+          if (kbase + U < K1[b]) any = true;
+        }
+      }
+      any = __any_sync(0xffffffffu, any);
+    }
+  } else {
+    // ---- consumers: thread = (group, batch row) ----
+    const uint32_t ct = tid - 32;
+    const uint32_t g = ct / rt, r = ct % rt;
+    if (g < G) {
+      uint32_t i0, i1;
+      group_range(g, i0, i1);
+      if (i0 < i1) {
+        const uint32_t K0 = __ldg(rowptr + i0), K1 = __ldg(rowptr + i1);
+        uint32_t i = i0, row_end = __ldg(rowptr + i0 + 1);
+        typename F::Wide acc = F::wide_zero();
+        auto finish_row = [&]() {
+          typename F::Elem out = F::template redc<2>(acc);
+          stv<N>(y + ((size_t)i * n_rows + r0 + r) * N, out.v);
+          acc = F::wide_zero();
+          i++;
+          if (i < i1) row_end = __ldg(rowptr + i + 1);
+        };
+        uint32_t s_idx = 0;
+        for (uint32_t kbase = K0; kbase < K1; kbase += U, s_idx++) {
+          const uint32_t slot = s_idx % STAGES, round = s_idx / STAGES;
+          uint64_t *fb = full + g * STAGES + slot, *eb = empty + g * STAGES + slot;
+          mbar_wait(fb, round & 1);
+          const uint8_t *st = ring + (size_t)(g * STAGES + slot) * stage_bytes;
+          const uint32_t n_valid = min((uint32_t)U, K1 - kbase);
+#pragma unroll
+          for (int uu = 0; uu < U; uu++) {
+            if ((uint32_t)uu < n_valid) {
+              while (kbase + uu == row_end && i < i1) finish_row();
+              typename F::Elem a, xv;
+              ldv<N>(a.v, reinterpret_cast<const uint32_t *>(st + (size_t)U * RT * B) + uu * N);
+              ldv<N>(xv.v, reinterpret_cast<const uint32_t *>(st) + ((size_t)uu * RT + r) * N);
+              F::mac_wide(acc, a, xv);
+            }
+          }
+          mbar_arrive(eb);
+        }
+        while (i < i1) finish_row();  // the last output, and any empty rows behind it
+      }
+    }
+  }
+}
+
 // seg[q * m + i] = first k in [rowptr[i], rowptr[i+1]) with colidx[k] >= q * n / Q  (q = 0 .. Q)
 __global__ void __launch_bounds__(256)
 spmm_segments_kernel(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ colidx, size_t m, size_t n,
@@ -696,6 +862,12 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
       // rounds; the hints change nothing measurable.  Both therefore default to off here.
       const bool hints = tunable("SPMM_HINTS", 0) != 0;
       const bool pipe = tunable("SPMM_PIPE", 0) != 0;  // software-pipelined gathers (spmm_pipe_kernel)
+      // A/B knob: unused dynamic shared memory that lowers the resident CTAs per SM (room for a co-resident hash kernel)
+      const size_t spmm_pad = (size_t)std::min<long>(100, std::max<long>(0, tunable("SPMM_SMEM_PAD_KB", 0))) << 10;
+      if (spmm_pad > ((size_t)47 << 10)) {
+        cudaError_t e = cudaFuncSetAttribute(spmm_kernel<FID, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 << 10);
+        if (e != cudaSuccess) return e;
+      }
       const size_t cap = (size_t)std::max<long>(0, tunable("SPMM_WINDOW_KB", 0)) << 10;
       const size_t slice_cap = (size_t)std::max<long>(0, tunable("SPMM_SLICE_KB", 0)) << 10;
       const size_t window = M.n * n_rows * F::BYTES;
@@ -715,6 +887,36 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
       }
       const size_t eff_window = Q > 1 ? window / Q : (rg < n_rows ? M.n * rg * F::BYTES : window);
       const float keep = (!cap || eff_window <= cap) ? 1.0f : (float)((double)cap / (double)eff_window);
+      // SPMM_BULK 1: gathers by the bulk-copy engine (spmm_bulk_kernel), 16-byte-multiple elements and whole levels only
+      if (tunable("SPMM_BULK", 0) != 0 && N % 4 == 0 && Q == 1 && rg == n_rows && M.m && M.nnz) {
+        const unsigned rt_count = (unsigned)((n_rows + bulk::CONSUMERS - 1) / bulk::CONSUMERS);
+        const unsigned RT = (unsigned)((n_rows + rt_count - 1) / rt_count);
+        unsigned G = std::min<unsigned>(bulk::MAX_GROUPS, std::max<unsigned>(1, bulk::CONSUMERS / RT));
+        const size_t stage_bytes = ((size_t)bulk::U * RT * F::BYTES + bulk::U * F::BYTES + 127) & ~(size_t)127;
+        auto smem_of = [&](unsigned g) { return (((size_t)2 * g * bulk::STAGES * 8 + 127) & ~(size_t)127) + (size_t)g * bulk::STAGES * stage_bytes; };
+        while (G > 1 && smem_of(G) > (size_t)100 << 10) G--;
+        const size_t smem = smem_of(G);
+        if (smem <= (size_t)200 << 10) {
+          static bool attr_set_dev[64] = {};
+          int dev_id = 0;
+          cudaGetDevice(&dev_id);
+          if (!attr_set_dev[dev_id & 63]) {
+            cudaError_t e = cudaFuncSetAttribute(spmm_bulk_kernel<FID>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10);
+            if (e != cudaSuccess) return e;
+            attr_set_dev[dev_id & 63] = true;
+          }
+          const unsigned ctas_per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(7, ((size_t)220 << 10) / (smem + 1024)));
+          const size_t groups_target = (size_t)148 * ctas_per_sm * G * 4;  // about four waves of groups
+          const unsigned opg = (unsigned)std::max<size_t>(1, (M.m + groups_target - 1) / groups_target);
+          dim3 grid((unsigned)((M.m + (size_t)G * opg - 1) / ((size_t)G * opg)), rt_count);
+          spmm_bulk_kernel<FID><<<grid, 32 + bulk::CONSUMERS, smem, st>>>(M.rowptr, M.colidx, M.vals, x, y, (uint32_t)M.m, (uint32_t)n_rows,
+                                                                          RT, G, opg);
+          launches++;
+          cudaError_t e = cudaGetLastError();
+          if (e != cudaSuccess) return e;
+          continue;
+        }
+      }
       for (unsigned q = 0; q < Q; q++) {
         const uint32_t *lo = Q > 1 ? M.seg + (size_t)q * M.m : M.rowptr;
         const uint32_t *hi = Q > 1 ? M.seg + (size_t)(q + 1) * M.m : M.rowptr + 1;
@@ -722,7 +924,7 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
           const size_t cnt = std::min(rg, n_rows - r0), items = M.m * cnt;
           const unsigned grid = (unsigned)((items + 255) / 256);
 #define LCPC_SPMM_LAUNCH(H, A) \
-  spmm_kernel<FID, H, A><<<grid, 256, 0, st>>>(lo, hi, M.colidx, M.vals, x, y, M.m, n_rows, (unsigned)r0, (unsigned)cnt, keep)
+  spmm_kernel<FID, H, A><<<grid, 256, spmm_pad, st>>>(lo, hi, M.colidx, M.vals, x, y, M.m, n_rows, (unsigned)r0, (unsigned)cnt, keep)
           if (pipe && q) spmm_pipe_kernel<FID, true><<<grid, 256, 0, st>>>(lo, hi, M.colidx, M.vals, x, y, M.m, n_rows, (unsigned)r0, (unsigned)cnt);
           else if (pipe) spmm_pipe_kernel<FID, false><<<grid, 256, 0, st>>>(lo, hi, M.colidx, M.vals, x, y, M.m, n_rows, (unsigned)r0, (unsigned)cnt);
           else if (hints && q) LCPC_SPMM_LAUNCH(true, true);

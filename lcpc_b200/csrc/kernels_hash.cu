@@ -43,7 +43,7 @@ __device__ __forceinline__ void gload_elem(uint32_t (&v)[N], const uint32_t *p) 
 template <int FID>
 __global__ void __launch_bounds__(HASH_THREADS)
 leaf_chunk_kernel(const uint32_t *__restrict__ comm, size_t n_rows, size_t n_cols, size_t row_stride,
-                  uint32_t *__restrict__ out, unsigned n_chunks, unsigned k_first) {
+                  uint32_t *__restrict__ out, unsigned n_chunks, unsigned k_first, size_t out_cols, size_t col0) {
   using F = Field<FID>;
   constexpr int N = F::N;
   constexpr int B = F::BYTES;
@@ -82,7 +82,7 @@ leaf_chunk_kernel(const uint32_t *__restrict__ comm, size_t n_rows, size_t n_col
     b3::compress(cv, m, k, block_len, flags);
   }
   // single chunk: this is the digest; else the chunk chaining value for the merge kernel
-  uint32_t *o = out + ((size_t)k * n_cols + col) * 8;
+  uint32_t *o = out + ((size_t)k * out_cols + col0 + col) * 8;
   reinterpret_cast<uint4 *>(o)[0] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
   reinterpret_cast<uint4 *>(o)[1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
 }
@@ -92,7 +92,7 @@ leaf_chunk_kernel(const uint32_t *__restrict__ comm, size_t n_rows, size_t n_col
 template <int FID>
 __global__ void __launch_bounds__(HASH_THREADS)
 leaf_chunk_kernel_generic(const uint32_t *__restrict__ comm, size_t n_rows, size_t n_cols, size_t row_stride,
-                          uint32_t *__restrict__ out, unsigned n_chunks, unsigned k_first) {
+                          uint32_t *__restrict__ out, unsigned n_chunks, unsigned k_first, size_t out_cols, size_t col0) {
   using F = Field<FID>;
   constexpr int N = F::N;
   constexpr int B = F::BYTES;
@@ -138,7 +138,7 @@ leaf_chunk_kernel_generic(const uint32_t *__restrict__ comm, size_t n_rows, size
     if (lastb && n_chunks == 1) flags |= b3::ROOT;
     b3::compress(cv, m, k, block_len, flags);
   }
-  uint32_t *o = out + ((size_t)k * n_cols + col) * 8;
+  uint32_t *o = out + ((size_t)k * out_cols + col0 + col) * 8;
   reinterpret_cast<uint4 *>(o)[0] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
   reinterpret_cast<uint4 *>(o)[1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
 }
@@ -213,23 +213,33 @@ size_t leaf_chunk_rows_end(int field, size_t n_rows, unsigned k) {
 }
 unsigned leaf_chunk_count(int field, size_t n_rows) { return leaf_chunks(field, n_rows); }
 
-// chunk chaining values (or, for single-chunk leaves, the digests) of chunks [k_first, k_first + k_count)
-cudaError_t launch_leaf_chunks(int field, const uint32_t *comm, size_t n_rows, size_t n_cols, size_t row_stride,
-                               uint8_t *leaves, void *scratch, unsigned k_first, unsigned k_count, cudaStream_t stream) {
+// chunk chaining values (or, for single-chunk leaves, the digests) of chunks [k_first, k_first + k_count) of the
+// n_cols columns that start at `comm`; they are columns [col0, col0 + n_cols) of a commitment with total_cols
+// columns (the slots of `leaves` / `scratch` they fill).  A commit can therefore hash column ranges from
+// different matrices -- Brakedown's systematic columns straight from the coefficient rows, before the code's
+// sparse products have produced the rest.
+cudaError_t launch_leaf_chunks_range(int field, const uint32_t *comm, size_t n_rows, size_t n_cols, size_t row_stride,
+                                     uint8_t *leaves, void *scratch, unsigned k_first, unsigned k_count, size_t total_cols,
+                                     size_t col0, cudaStream_t stream) {
   if (n_cols == 0 || k_count == 0) return cudaSuccess;
   const unsigned n_chunks = leaf_chunks(field, n_rows);
-  if (n_chunks > 65535u || k_first + k_count > n_chunks) return cudaErrorInvalidValue;
+  if (n_chunks > 65535u || k_first + k_count > n_chunks || col0 + n_cols > total_cols) return cudaErrorInvalidValue;
   uint32_t *out = n_chunks > 1 ? (uint32_t *)scratch : (uint32_t *)leaves;
   if (n_chunks > 1 && !scratch) return cudaErrorInvalidValue;
   dim3 grid((unsigned)((n_cols + HASH_THREADS - 1) / HASH_THREADS), k_count);
   switch (field) {
-    case FT63: leaf_chunk_kernel<FT63><<<grid, HASH_THREADS, 0, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first); break;
-    case FT127: leaf_chunk_kernel<FT127><<<grid, HASH_THREADS, 0, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first); break;
-    case FT191: leaf_chunk_kernel_generic<FT191><<<grid, HASH_THREADS, 0, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first); break;
-    case FT255: leaf_chunk_kernel<FT255><<<grid, HASH_THREADS, 0, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first); break;
+    case FT63: leaf_chunk_kernel<FT63><<<grid, HASH_THREADS, 0, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0); break;
+    case FT127: leaf_chunk_kernel<FT127><<<grid, HASH_THREADS, 0, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0); break;
+    case FT191: leaf_chunk_kernel_generic<FT191><<<grid, HASH_THREADS, 0, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0); break;
+    case FT255: leaf_chunk_kernel<FT255><<<grid, HASH_THREADS, 0, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
+}
+
+cudaError_t launch_leaf_chunks(int field, const uint32_t *comm, size_t n_rows, size_t n_cols, size_t row_stride,
+                               uint8_t *leaves, void *scratch, unsigned k_first, unsigned k_count, cudaStream_t stream) {
+  return launch_leaf_chunks_range(field, comm, n_rows, n_cols, row_stride, leaves, scratch, k_first, k_count, n_cols, 0, stream);
 }
 
 // BLAKE3 tree over the chunk chaining values of every column (no-op for single-chunk leaves)

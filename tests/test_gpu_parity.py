@@ -236,14 +236,16 @@ def test_sdig_encode_vs_oracle(field, n, seed):
 
 
 @pytest.mark.parametrize("hints,window_kb,slice_kb,pipe", [(1, 8, 0, 0), (0, 8, 0, 0), (1, 64, 0, 0), (1, 0, 0, 0), (0, 0, 16, 0),
-                                                          (1, 1 << 20, 0, 0), (0, 0, 0, 1), (0, 8, 0, 1), (0, 64, 0, 1), (0, 0, 16, 1)])
+                                                          (1, 1 << 20, 0, 0), (0, 0, 0, 1), (0, 8, 0, 1), (0, 64, 0, 1), (0, 0, 16, 1),
+                                                          (0, 0, 0, 2)])  # pipe == 2: the bulk-copy (TMA) gather kernel
 @pytest.mark.parametrize("field,n,seed", [(P.FT127, 4000, 4), (P.FT255, 1500, 5), (P.FT63, 9000, 6), (P.FT191, 700, 7)])
 def test_sdig_encode_schedules_are_result_neutral(field, n, seed, hints, window_kb, slice_kb, pipe):
     """The sparse products' schedule knobs (L2 eviction hints, column chunks with accumulation onto y, batch-row
     slices) must not change a single limb: windows of 8 KB force up to 16 column chunks on these small codes."""
     from lcpc_b200 import _cabi
     lib = _cabi.lib()
-    knobs = {b"SPMM_HINTS": hints, b"SPMM_WINDOW_KB": window_kb, b"SPMM_SLICE_KB": slice_kb, b"SPMM_PIPE": pipe}
+    knobs = {b"SPMM_HINTS": hints, b"SPMM_WINDOW_KB": window_kb, b"SPMM_SLICE_KB": slice_kb, b"SPMM_PIPE": int(pipe == 1),
+             b"SPMM_BULK": int(pipe == 2)}
     try:
         for k, v in knobs.items():
             lib.lcpc_b200_set_tunable(k, v)
@@ -262,6 +264,7 @@ def test_sdig_encode_schedules_are_result_neutral(field, n, seed, hints, window_
         lib.lcpc_b200_set_tunable(b"SPMM_WINDOW_KB", 0)
         lib.lcpc_b200_set_tunable(b"SPMM_SLICE_KB", 0)
         lib.lcpc_b200_set_tunable(b"SPMM_PIPE", 0)
+        lib.lcpc_b200_set_tunable(b"SPMM_BULK", 0)
 
 
 @pytest.mark.parametrize("field,length,seed", [(P.FT127, 1 << 14, 0), (P.FT127, (1 << 16) - 11, 1), (P.FT255, 1 << 13, 0),
@@ -616,7 +619,7 @@ def test_device_matgen_equals_host_generator_and_oracle(field, n, seed, code):
     again = P.SdigEncoding.new_from_dims(field, n, seed=seed, code=code)
     assert (again.encode(rows)[1] == got[1]).all()
     other = P.SdigEncoding.new_from_dims(field, n, seed=seed + 1, code=code)
-    assert not (other.matrices()[0][0]["idxs"] == pre[0]["idxs"]).all()
+    assert not (other.matrices()[0][0]["data"] == pre[0]["data"]).all()  # another seed, another code
 
 
 def test_device_matgen_rejects_what_the_reference_asserts():
