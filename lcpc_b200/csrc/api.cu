@@ -436,6 +436,14 @@ int encode_rows_from_host(lcpc_b200_enc *enc, const void *src, size_t len, uint3
   const size_t row_bytes = n_per_row * B;
   size_t n_chunks = std::min<size_t>(enc->kind == LCPC_B200_ENC_LIGERO ? 16 : 4, n_rows);
   while (n_chunks > 1 && (n_rows / n_chunks) * row_bytes < ((size_t)4 << 20)) n_chunks--;
+  if (enc->kind == LCPC_B200_ENC_LIGERO) {
+    // a row-chunk is one launch per transform pass, n_cols / 1024 CTAs per row: chunks of fewer rows than about two
+    // waves of the 592 resident CTA slots leave the GPU half empty and make the encode, not the copy, the long pole
+    // (a rank of the 8-GPU commit holds 32 rows: 16 chunks of 2 rows ran at 2.95 ms end to end)
+    const size_t ctas_per_row = std::max<size_t>(1, enc->n_cols >> 10);
+    const size_t min_rows = std::max<size_t>(1, (size_t)tunable("H2D_MIN_CHUNK_CTAS", 1184) / ctas_per_row);
+    while (n_chunks > 1 && n_rows / n_chunks < min_rows) n_chunks--;
+  }
   if (coeffs_free_ev) {
     // the caller knows when the last reader of d_coeffs finished (an event recorded behind it): the copy may start
     // then, under whatever the engine stream still has queued behind that reader (hashing of the previous commit)
@@ -575,22 +583,20 @@ int lcpc_b200_encode(lcpc_b200_enc *enc, uint64_t *rows, size_t n_rows) {
   lcpc_b200_ctx *ctx = enc->ctx;
   std::lock_guard<std::mutex> g(ctx->mu);
   if (int rc = bind_device(ctx)) return rc;
+  // rows and the encoder's own scratch share the context's grow-only pool: the verifier calls this once per proof
+  // with one or two rows (lcpc-2d/src/lib.rs:886, :918), so after the first call nothing is allocated or freed
   const size_t bytes = n_rows * enc->n_cols * field_bytes(enc->field);
-  uint32_t *d = nullptr;
-  CU(ctx, cudaMalloc(&d, bytes));
-  int rc = ensure_scratch(ctx, enc_scratch_bytes(enc, n_rows));
-  cudaError_t ce = cudaSuccess;
-  if (rc == LCPC_B200_OK) {
-    ce = cudaMemcpyAsync(d, rows, bytes, cudaMemcpyHostToDevice, ctx->stream);
-    // the reference transforms the whole row: Ligero reads all n_cols entries, Brakedown the first n_per_row
-    size_t valid = enc->kind == LCPC_B200_ENC_LIGERO ? enc->n_cols : enc->n_per_row;
-    if (ce == cudaSuccess) rc = encode_rows(enc, d, enc->n_cols, valid, d, n_rows, ctx->scratch);
-    if (ce == cudaSuccess && rc == LCPC_B200_OK) ce = cudaMemcpyAsync(rows, d, bytes, cudaMemcpyDeviceToHost, ctx->stream);
-    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
-  }
-  cudaFree(d);
-  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "encode");
-  return rc;
+  const size_t rows_al = (bytes + 255) & ~(size_t)255;
+  if (int rc = ensure_scratch(ctx, rows_al + enc_scratch_bytes(enc, n_rows))) return rc;
+  uint32_t *d = (uint32_t *)ctx->scratch;
+  void *enc_scratch = (uint8_t *)ctx->scratch + rows_al;
+  CU(ctx, cudaMemcpyAsync(d, rows, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  // the reference transforms the whole row: Ligero reads all n_cols entries, Brakedown the first n_per_row
+  const size_t valid = enc->kind == LCPC_B200_ENC_LIGERO ? enc->n_cols : enc->n_per_row;
+  if (int rc = encode_rows(enc, d, enc->n_cols, valid, d, n_rows, enc_scratch)) return rc;
+  CU(ctx, cudaMemcpyAsync(rows, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return LCPC_B200_OK;
 }
 
 // ------------------------------------------------------------------------------------------ commit
@@ -710,13 +716,16 @@ static int commit_run(lcpc_b200_commit *c, const void *src, size_t len, cudaMemc
     // The code is systematic: columns [0, n_per_row) of comm ARE the coefficient rows (encode.rs: the codeword starts
     // with x_0), two thirds of all columns.  Their leaf digests do not depend on the sparse products at all, so they
     // are hashed straight from the caller's rows on the side stream while the chain runs: BLAKE3 lives on the ALU
-    // pipe, the chain is bound by L2 gather bandwidth.  (A ragged last row would be read past its end: then the
-    // columns wait for the commit's zero-padded copy like the rest.)
-    if (padded == len && trail.n_chunks >= 1 && tunable("SDIG_EARLY_HASH", 1) != 0) {
+    // pipe, the chain is bound by L2 gather bandwidth.  (A short last row reads as zeros past the caller's `len`
+    // coefficients, exactly the padding of lcpc-2d/src/lib.rs:636-645.)
+    // Measured at 2^24 (profiles/r02_ab_brakedown_early_hash.jsonl): the systematic columns' hash moves into the encode
+    // phase (+0.17 ms) and out of the leaf phase (-0.15 ms) -- the sparse products hold every register of the SM, so
+    // the two kernels take turns instead of sharing it; 1.675 ms per commit against 1.652.  Off by default.
+    if (trail.n_chunks >= 1 && tunable("SDIG_EARLY_HASH", 0) != 0) {
       CU(ctx, cudaEventRecord(ctx->lane_fork, st));
       CU(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->lane_fork, 0));
       cudaError_t he = launch_leaf_chunks_range(enc->field, (const uint32_t *)src, c->n_rows, c->n_per_row, c->n_per_row, c->d_hashes,
-                                                c->d_hash_scratch, 0, trail.n_chunks, c->n_cols, 0, ctx->side_stream);
+                                                c->d_hash_scratch, 0, trail.n_chunks, c->n_cols, 0, ctx->side_stream, len);
       if (he != cudaSuccess) return cuda_fail(ctx, he, "hash_columns (systematic part)");
       CU(ctx, cudaEventRecord(ctx->side_done, ctx->side_stream));
       ctx->launches += 1, trail.launches += 1;

@@ -326,42 +326,52 @@ int device_matgen(int field, uint64_t seed, size_t t, const MatgenDims *pre, con
           dim.n * dim.d >= 0xffffffffull)
         return bail(LCPC_B200_ERR_BAD_ARG, "matgen: level dimensions out of range");
     }
-    double slack = 1.08;
-    for (int attempt = 0;; attempt++, slack *= 1.5) {
-      Scratch tmp;
+  }
+  // scratch is sized once for the largest level (levels shrink geometrically) and reused: device allocations cost
+  // more than the kernels here
+  size_t max_n = 0, max_m = 0, max_nnz = 0;
+  for (size_t lvl = 0; lvl < t; lvl++)
+    for (const MatgenDims &dim : {pre[lvl], post[lvl]})
+      max_n = std::max(max_n, dim.n), max_m = std::max(max_m, dim.m), max_nnz = std::max(max_nnz, dim.n * dim.d);
+  double slack = 1.08;
+  for (int attempt = 0;; attempt++, slack *= 1.5) {
+    size_t max_T = 0;
+    for (size_t lvl = 0; lvl < t; lvl++)
+      max_T = std::max(max_T, words_bound(pre[lvl], f, accept, slack) + words_bound(post[lvl], f, accept, slack));
+    if (max_T >= 0xfffffff0ull) return bail(LCPC_B200_ERR_TOO_BIG, "matgen: keystream too long for 32-bit word offsets");
+    Scratch tmp;
+    uint32_t *d_S = nullptr, *d_status = nullptr, *d_first = nullptr, *d_next = nullptr, *d_ja = nullptr, *d_jb = nullptr;
+    uint32_t *d_hop = nullptr, *d_start = nullptr, *d_count = nullptr, *d_fill = nullptr, *d_src = nullptr;
+    cudaError_t ce = tmp.alloc(&d_S, ((max_T + 7) / 8) * 16);
+    if (ce == cudaSuccess) ce = tmp.alloc(&d_status, 1);
+    if (ce == cudaSuccess) ce = tmp.alloc(&d_first, 1);
+    if (ce == cudaSuccess) ce = tmp.alloc(&d_next, max_T);
+    if (ce == cudaSuccess) ce = tmp.alloc(&d_ja, max_T);
+    if (ce == cudaSuccess) ce = tmp.alloc(&d_jb, max_T);
+    if (ce == cudaSuccess) ce = tmp.alloc(&d_hop, (max_n >> LOG_HOP) + 1);
+    if (ce == cudaSuccess) ce = tmp.alloc(&d_start, max_n + 1);
+    if (ce == cudaSuccess) ce = tmp.alloc(&d_count, max_m);
+    if (ce == cudaSuccess) ce = tmp.alloc(&d_fill, max_m);
+    if (ce == cudaSuccess) ce = tmp.alloc(&d_src, max_nnz);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(d_status, 0, 4, st);
+    if (ce != cudaSuccess) return bail(ce == cudaErrorMemoryAllocation ? LCPC_B200_ERR_OOM : LCPC_B200_ERR_CUDA, "matgen: scratch", ce);
+    for (size_t lvl = 0; lvl < t; lvl++) {
       const size_t T = words_bound(pre[lvl], f, accept, slack) + words_bound(post[lvl], f, accept, slack);
-      if (T >= 0xfffffff0ull) return bail(LCPC_B200_ERR_TOO_BIG, "matgen: keystream too long for 32-bit word offsets");
       const size_t n_blocks = (T + 7) / 8;  // 16 u32 = 8 u64 per ChaCha20 block
-      uint32_t *d_S = nullptr, *d_status = nullptr, *d_first = nullptr, *d_next = nullptr, *d_ja = nullptr, *d_jb = nullptr;
-      cudaError_t ce = tmp.alloc(&d_S, n_blocks * 16);
-      if (ce == cudaSuccess) ce = tmp.alloc(&d_status, 1);
-      if (ce == cudaSuccess) ce = tmp.alloc(&d_first, 1);
-      if (ce == cudaSuccess) ce = tmp.alloc(&d_next, T);
-      if (ce == cudaSuccess) ce = tmp.alloc(&d_ja, T);
-      if (ce == cudaSuccess) ce = tmp.alloc(&d_jb, T);
-      if (ce == cudaSuccess) ce = cudaMemsetAsync(d_status, 0, 4, st);
-      if (ce == cudaSuccess) ce = cudaMemsetAsync(d_first, 0, 4, st);
-      if (ce != cudaSuccess) return bail(ce == cudaErrorMemoryAllocation ? LCPC_B200_ERR_OOM : LCPC_B200_ERR_CUDA, "matgen: scratch", ce);
+      ce = cudaMemsetAsync(d_first, 0, 4, st);
       matgen_keystream_kernel<<<grid_for(n_blocks, 256), 256, 0, st>>>(key, (uint64_t)lvl, n_blocks, d_S);
       const uint64_t *S = reinterpret_cast<const uint64_t *>(d_S);
       const uint32_t T32 = (uint32_t)T;
-      bool ok = true;
-      for (int which = 0; which < 2 && ok; which++) {
+      for (int which = 0; which < 2; which++) {
         const MatgenDims &dim = which ? post[lvl] : pre[lvl];
         DeviceCsr &M = c->mats[which ? t + lvl : lvl];
         const uint32_t n = (uint32_t)dim.n, m = (uint32_t)dim.m, d = (uint32_t)dim.d;
         const size_t nnz = (size_t)n * d;
         M.m = m, M.n = n, M.nnz = nnz, M.csc_d = d;
-        // a retry regenerates this level's matrices from scratch
+        // a retry regenerates every matrix from scratch
         cudaFree(M.rowptr), cudaFree(M.colidx), cudaFree(M.vals), cudaFree(M.csc_idx), cudaFree(M.csc_data);
         M.rowptr = M.colidx = M.vals = M.csc_idx = M.csc_data = nullptr;
-        uint32_t *d_hop = nullptr, *d_start = nullptr, *d_count = nullptr, *d_fill = nullptr, *d_src = nullptr;
         const uint32_t n_hops = (n >> LOG_HOP) + 1;
-        ce = tmp.alloc(&d_hop, n_hops);
-        if (ce == cudaSuccess) ce = tmp.alloc(&d_start, (size_t)n + 1);
-        if (ce == cudaSuccess) ce = tmp.alloc(&d_count, m);
-        if (ce == cudaSuccess) ce = tmp.alloc(&d_fill, m);
-        if (ce == cudaSuccess) ce = tmp.alloc(&d_src, nnz);
         if (ce == cudaSuccess) ce = cudaMalloc(&M.rowptr, ((size_t)m + 1) * 4);
         if (ce == cudaSuccess) ce = cudaMalloc(&M.colidx, std::max<size_t>(nnz, 1) * 4);
         if (ce == cudaSuccess) ce = cudaMalloc(&M.vals, std::max<size_t>(nnz, 1) * L * 8);
@@ -394,15 +404,17 @@ int device_matgen(int field, uint64_t seed, size_t t, const MatgenDims *pre, con
           matgen_gather_vals_kernel<uint2><<<grid_for(nnz * L, 256), 256, 0, st>>>(reinterpret_cast<const uint2 *>(M.csc_data), d_src, nnz,
                                                                                   (unsigned)L, reinterpret_cast<uint2 *>(M.vals));
         if (ce == cudaSuccess) ce = cudaGetLastError();
-        uint32_t status = 0;
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(&status, d_status, 4, cudaMemcpyDeviceToHost, st);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
         if (ce != cudaSuccess) return bail(LCPC_B200_ERR_CUDA, "matgen: kernels", ce);
-        if (status) ok = false;  // the keystream was too short for this draw: retry the level with more
       }
-      if (ok) break;
-      if (attempt >= 4) return bail(LCPC_B200_ERR_CUDA, "matgen: keystream bound exceeded repeatedly");
     }
+    // one look at the status word for the whole code: a keystream that was too short for some level's draw (an
+    // unlucky run of rejections) makes everything be drawn again with more headroom
+    uint32_t status = 0;
+    ce = cudaMemcpyAsync(&status, d_status, 4, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce != cudaSuccess) return bail(LCPC_B200_ERR_CUDA, "matgen: kernels", ce);
+    if (!status) break;
+    if (attempt >= 4) return bail(LCPC_B200_ERR_CUDA, "matgen: keystream bound exceeded repeatedly");
   }
   int rc = expander_assemble(c, t, err);
   if (rc != LCPC_B200_OK) {

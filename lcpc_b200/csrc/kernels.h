@@ -62,10 +62,11 @@ size_t leaf_chunk_rows_end(int field, size_t n_rows, unsigned k);
 cudaError_t launch_leaf_chunks(int field, const uint32_t *comm, size_t n_rows, size_t n_cols, size_t row_stride,
                                uint8_t *leaves, void *scratch, unsigned k_first, unsigned k_count, cudaStream_t stream);
 // the same for a column range: the n_cols columns at `comm` are columns [col0, col0 + n_cols) of a commitment with
-// total_cols columns
+// total_cols columns; element (r, c) of the source exists only if r * row_stride + c < src_total (beyond that: zero,
+// the padding of a short last row)
 cudaError_t launch_leaf_chunks_range(int field, const uint32_t *comm, size_t n_rows, size_t n_cols, size_t row_stride,
                                      uint8_t *leaves, void *scratch, unsigned k_first, unsigned k_count, size_t total_cols,
-                                     size_t col0, cudaStream_t stream);
+                                     size_t col0, cudaStream_t stream, size_t src_total = ~(size_t)0);
 cudaError_t launch_leaf_merge(int field, size_t n_rows, size_t n_cols, uint8_t *leaves, void *scratch, cudaStream_t stream,
                               int *n_launches);
 // hashes = [leaves(np2) | layer 1 | ... | root]; leaves given, upper layers computed

@@ -43,7 +43,8 @@ __device__ __forceinline__ void gload_elem(uint32_t (&v)[N], const uint32_t *p) 
 template <int FID>
 __global__ void __launch_bounds__(HASH_THREADS)
 leaf_chunk_kernel(const uint32_t *__restrict__ comm, size_t n_rows, size_t n_cols, size_t row_stride,
-                  uint32_t *__restrict__ out, unsigned n_chunks, unsigned k_first, size_t out_cols, size_t col0) {
+                  uint32_t *__restrict__ out, unsigned n_chunks, unsigned k_first, size_t out_cols, size_t col0,
+                  size_t src_total) {
   using F = Field<FID>;
   constexpr int N = F::N;
   constexpr int B = F::BYTES;
@@ -60,6 +61,10 @@ leaf_chunk_kernel(const uint32_t *__restrict__ comm, size_t n_rows, size_t n_col
   uint32_t cv[8];
   b3::set_iv(cv);
   const uint32_t *cp = comm + col * N;
+  // rows of this column that exist in the source: all of them, unless the source ends inside the last row (element
+  // (r, c) exists iff r * row_stride + c < src_total; beyond that the commit's zero padding is hashed)
+  const size_t rows_here = src_total == ~(size_t)0 ? n_rows
+                           : (src_total > col ? min(n_rows, (src_total - col + row_stride - 1) / row_stride) : 0);
   for (unsigned b = 0; b < n_blocks; b++) {
     uint32_t m[16];
     const size_t slot0 = (chunk_off + (size_t)b * 64) / B;
@@ -67,10 +72,10 @@ leaf_chunk_kernel(const uint32_t *__restrict__ comm, size_t n_rows, size_t n_col
     for (int i = 0; i < SPB; i++) {
       const size_t slot = slot0 + i;
       typename F::Elem x = F::zero();
-      if (slot >= PRE && slot - PRE < n_rows) {
+      if (slot >= PRE && slot - PRE < rows_here) {
         typename F::Elem raw;
         gload_elem<N>(raw.v, cp + (slot - PRE) * row_stride * N);
-        x = F::from_mont(raw);
+        x = F::from_mont(raw);  // (positions past src_total are the zero padding of a short last row: canonical zero)
       }
 #pragma unroll
       for (int l = 0; l < N; l++) m[i * N + l] = x.v[l];
@@ -92,7 +97,8 @@ leaf_chunk_kernel(const uint32_t *__restrict__ comm, size_t n_rows, size_t n_col
 template <int FID>
 __global__ void __launch_bounds__(HASH_THREADS)
 leaf_chunk_kernel_generic(const uint32_t *__restrict__ comm, size_t n_rows, size_t n_cols, size_t row_stride,
-                          uint32_t *__restrict__ out, unsigned n_chunks, unsigned k_first, size_t out_cols, size_t col0) {
+                          uint32_t *__restrict__ out, unsigned n_chunks, unsigned k_first, size_t out_cols, size_t col0,
+                          size_t src_total) {
   using F = Field<FID>;
   constexpr int N = F::N;
   constexpr int B = F::BYTES;
@@ -117,8 +123,8 @@ leaf_chunk_kernel_generic(const uint32_t *__restrict__ comm, size_t n_rows, size
         const size_t row = (off - 32) / B;
         const unsigned limb = (unsigned)(((off - 32) % B) / 4);
         if (row != cached_row) {
-          typename F::Elem raw;
-          gload_elem<N>(raw.v, cp + row * row_stride * N);
+          typename F::Elem raw = F::zero();
+          if (row * row_stride + col < src_total) gload_elem<N>(raw.v, cp + row * row_stride * N);
           typename F::Elem c = F::from_mont(raw);
 #pragma unroll
           for (int l = 0; l < N; l++) canon[l] = c.v[l];
@@ -220,18 +226,21 @@ unsigned leaf_chunk_count(int field, size_t n_rows) { return leaf_chunks(field, 
 // sparse products have produced the rest.
 cudaError_t launch_leaf_chunks_range(int field, const uint32_t *comm, size_t n_rows, size_t n_cols, size_t row_stride,
                                      uint8_t *leaves, void *scratch, unsigned k_first, unsigned k_count, size_t total_cols,
-                                     size_t col0, cudaStream_t stream) {
+                                     size_t col0, cudaStream_t stream, size_t src_total) {
   if (n_cols == 0 || k_count == 0) return cudaSuccess;
   const unsigned n_chunks = leaf_chunks(field, n_rows);
   if (n_chunks > 65535u || k_first + k_count > n_chunks || col0 + n_cols > total_cols) return cudaErrorInvalidValue;
   uint32_t *out = n_chunks > 1 ? (uint32_t *)scratch : (uint32_t *)leaves;
   if (n_chunks > 1 && !scratch) return cudaErrorInvalidValue;
   dim3 grid((unsigned)((n_cols + HASH_THREADS - 1) / HASH_THREADS), k_count);
+  // A/B knob: unused dynamic shared memory caps the resident hash CTAs per SM, so that a column range hashed on a side
+  // stream leaves registers for the kernels it runs beside (only applied to ranges, i.e. col0 or total_cols set)
+  const size_t pad = (total_cols != n_cols) ? (size_t)std::min<long>(47, std::max<long>(0, tunable("LEAF_SMEM_PAD_KB", 0))) << 10 : 0;
   switch (field) {
-    case FT63: leaf_chunk_kernel<FT63><<<grid, HASH_THREADS, 0, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0); break;
-    case FT127: leaf_chunk_kernel<FT127><<<grid, HASH_THREADS, 0, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0); break;
-    case FT191: leaf_chunk_kernel_generic<FT191><<<grid, HASH_THREADS, 0, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0); break;
-    case FT255: leaf_chunk_kernel<FT255><<<grid, HASH_THREADS, 0, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0); break;
+    case FT63: leaf_chunk_kernel<FT63><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total); break;
+    case FT127: leaf_chunk_kernel<FT127><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total); break;
+    case FT191: leaf_chunk_kernel_generic<FT191><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total); break;
+    case FT255: leaf_chunk_kernel<FT255><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -239,7 +248,7 @@ cudaError_t launch_leaf_chunks_range(int field, const uint32_t *comm, size_t n_r
 
 cudaError_t launch_leaf_chunks(int field, const uint32_t *comm, size_t n_rows, size_t n_cols, size_t row_stride,
                                uint8_t *leaves, void *scratch, unsigned k_first, unsigned k_count, cudaStream_t stream) {
-  return launch_leaf_chunks_range(field, comm, n_rows, n_cols, row_stride, leaves, scratch, k_first, k_count, n_cols, 0, stream);
+  return launch_leaf_chunks_range(field, comm, n_rows, n_cols, row_stride, leaves, scratch, k_first, k_count, n_cols, 0, stream, ~(size_t)0);
 }
 
 // BLAKE3 tree over the chunk chaining values of every column (no-op for single-chunk leaves)
