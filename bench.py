@@ -42,12 +42,16 @@ def parse():
                     help="default: the Ligero/Ft255 headline line plus a Brakedown/Ft127 block in the same JSON line")
     ap.add_argument("--lgl", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rho-den", type=int, default=2, choices=[2, 4],
+                    help="Ligero code rate 1/rho-den: 2 = the public alias LigeroEncoding (lcpc-ligero-pc/src/lib.rs:189), "
+                         "4 = the rate the reference's own benches use (lcpc-ligero-pc/src/bench.rs:19,43)")
     return ap.parse_args()
 
 
 def workload_desc(args):
     if (args.workload or "ligero") == "ligero":
-        return dict(kind="ligero", field=4, name=f"lcpc-ligero-pc commit, Ft255, 2^{args.lgl} coeffs (rho=1/2, BLAKE3)")
+        return dict(kind="ligero", field=4,
+                    name=f"lcpc-ligero-pc commit, Ft255, 2^{args.lgl} coeffs (rho=1/{getattr(args, 'rho_den', 2)}, BLAKE3)")
     return dict(kind="brakedown", field=2,
                 name=f"lcpc-brakedown-pc commit, Ft127, 2^{args.lgl} coeffs (SdigCode3, seed 0, BLAKE3)")
 
@@ -124,8 +128,9 @@ def cpu_commit_rate(args, seconds_budget=20.0, x=None, oenc=None):
     if oenc is not None:
         enc, npr = oenc, oenc.n_per_row
     elif wl["kind"] == "ligero":
-        _, npr, nc = O.ligero_get_dims(field, n)
-        enc = O.Encoding.ligero_from_dims(field, npr, nc)
+        rho = (1, getattr(args, "rho_den", 2))
+        _, npr, nc = O.ligero_get_dims(field, n, rho)
+        enc = O.Encoding.ligero_from_dims(field, npr, nc, rho)
     else:
         enc = O.Encoding.sdig(field, n, seed=0)
         npr = enc.n_per_row
@@ -166,7 +171,7 @@ def oracle_root(enc, field, x):
     """LcRoot of the oracle's commit of `x` under the same encoding (checker leg; called by the N>1 arm on rank 0)."""
     import oracle as O
     if enc.__class__.__name__ == "LigeroEncoding":
-        oenc = O.Encoding.ligero_from_dims(field, enc.n_per_row, enc.n_cols)
+        oenc = O.Encoding.ligero_from_dims(field, enc.n_per_row, enc.n_cols, enc.rho)
     else:
         pre, post = enc.matrices()
         oenc = O.Encoding.sdig_from_matrices(field, pre, post)
@@ -185,8 +190,9 @@ def run_reference(args):
     n = 1 << args.lgl
     field = wl["field"]
     if wl["kind"] == "ligero":
-        _, npr, nc = O.ligero_get_dims(field, n)
-        oenc = O.Encoding.ligero_from_dims(field, npr, nc)
+        rho = (1, args.rho_den)
+        _, npr, nc = O.ligero_get_dims(field, n, rho)
+        oenc = O.Encoding.ligero_from_dims(field, npr, nc, rho)
     else:
         oenc = O.Encoding.sdig(field, n, seed=0)
         npr, nc = oenc.n_per_row, oenc.n_cols
@@ -235,7 +241,7 @@ def run_workload(args, kind, ctx, world, rank, torch, P, cpu_budget):
     L = P.FIELD_LIMBS[field]
     hbm_peak, peak_src = load_peaks()
     if kind == "ligero":
-        enc = P.LigeroEncoding(field, n, ctx=ctx)
+        enc = P.LigeroEncoding(field, n, rho=(1, args.rho_den), ctx=ctx)
     else:
         enc = P.SdigEncoding(field, n, seed=0, ctx=ctx)
     n_rows, n_per_row, n_cols = enc.get_dims(n)

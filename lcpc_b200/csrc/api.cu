@@ -443,6 +443,10 @@ int encode_rows_from_host(lcpc_b200_enc *enc, const void *src, size_t len, uint3
     const size_t ctas_per_row = std::max<size_t>(1, enc->n_cols >> 10);
     const size_t min_rows = std::max<size_t>(1, (size_t)tunable("H2D_MIN_CHUNK_CTAS", 1184) / ctas_per_row);
     while (n_chunks > 1 && n_rows / n_chunks < min_rows) n_chunks--;
+  } else {
+    // the expander chain has a dozen launches per chunk, some of them one CTA per batch row: below ~16 rows a chunk
+    // is launch- and occupancy-bound, and a rank of the 8-GPU commit holds only 9 rows at 2^24
+    while (n_chunks > 1 && n_rows / n_chunks < (size_t)std::max<long>(1, tunable("H2D_MIN_CHUNK_ROWS_SDIG", 16))) n_chunks--;
   }
   if (coeffs_free_ev) {
     // the caller knows when the last reader of d_coeffs finished (an event recorded behind it): the copy may start
