@@ -300,6 +300,11 @@ int lcpc_b200_shard_dims(const lcpc_b200_shard *s, size_t *n_rows, size_t *n_per
 int lcpc_b200_shard_commit(lcpc_b200_shard *s, const uint64_t *rows, size_t n_elems);
 int lcpc_b200_shard_commit_dev(lcpc_b200_shard *s, const uint64_t *d_rows, size_t n_elems);
 int lcpc_b200_shard_load_rows(lcpc_b200_shard *s, const uint64_t *rows, size_t n_elems);
+/* one commit of the loaded rows in its three enqueue steps (1: encode + peer stores + "tiles landed"; 2: wait, hash,
+ * subtree roots to all, "roots landed"; 3: wait, top tree).  A single process that drives several shards itself must
+ * run step k on EVERY shard before step k+1 on any (lcpc_b200_multi_rerun does exactly that), so that no wait is
+ * enqueued in front of a signal it depends on. */
+int lcpc_b200_shard_commit_step(lcpc_b200_shard *s, int step);
 /* LcCommit::get_root (:276-281): synchronises this rank's stream; every rank returns the same digest */
 int lcpc_b200_shard_root(lcpc_b200_shard *s, uint8_t root[32]);
 /* the same without the synchronisation: the 32 bytes land in `root` (page-locked host memory) when the stream

@@ -118,6 +118,7 @@ SIGNATURES = {
     "lcpc_b200_shard_commit": (_i, [_vp, _vp, _sz]),
     "lcpc_b200_shard_commit_dev": (_i, [_vp, _vp, _sz]),
     "lcpc_b200_shard_load_rows": (_i, [_vp, _vp, _sz]),
+    "lcpc_b200_shard_commit_step": (_i, [_vp, _i]),
     "lcpc_b200_shard_root": (_i, [_vp, _vp]),
     "lcpc_b200_shard_root_enqueue": (_i, [_vp, _vp]),
     "lcpc_b200_shard_phase_times": (_i, [_vp, _vp]),

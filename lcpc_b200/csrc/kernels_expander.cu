@@ -888,7 +888,7 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
       const size_t eff_window = Q > 1 ? window / Q : (rg < n_rows ? M.n * rg * F::BYTES : window);
       const float keep = (!cap || eff_window <= cap) ? 1.0f : (float)((double)cap / (double)eff_window);
       // SPMM_BULK 1: gathers by the bulk-copy engine (spmm_bulk_kernel), 16-byte-multiple elements and whole levels only
-      if (tunable("SPMM_BULK", 0) != 0 && N % 4 == 0 && Q == 1 && rg == n_rows && M.m && M.nnz) {
+      if constexpr (N % 4 == 0) if (tunable("SPMM_BULK", 0) != 0 && Q == 1 && rg == n_rows && M.m && M.nnz) {
         const unsigned rt_count = (unsigned)((n_rows + bulk::CONSUMERS - 1) / bulk::CONSUMERS);
         const unsigned RT = (unsigned)((n_rows + rt_count - 1) / rt_count);
         unsigned G = std::min<unsigned>(bulk::MAX_GROUPS, std::max<unsigned>(1, bulk::CONSUMERS / RT));

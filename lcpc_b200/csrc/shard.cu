@@ -354,7 +354,28 @@ int commit_step1(lcpc_b200_shard *s, const void *rows, size_t n_elems, bool rows
         const size_t padded = s->my_rows * p.n_per_row;
         if (padded > n_elems) CU(ctx, cudaMemsetAsync((uint8_t *)s->d_coeffs + n_elems * s->B, 0, (padded - n_elems) * s->B, st));
       }
-      if (int rc = encode_rows(enc, s->d_coeffs, p.n_per_row, p.n_per_row, s->d_tmp, s->my_rows, s->d_enc_scratch, &sc)) return rc;
+      // A/B knob SHARD_ENC_CHUNKS (Ligero): the row block in chunks that alternate between the engine and the side
+      // stream, so that one chunk's last pass (the one that stores over NVLink) runs beside the next chunk's first
+      const size_t chunks = std::min<size_t>((size_t)std::max<long>(1, tunable("SHARD_ENC_CHUNKS", 1)), s->my_rows);
+      if (chunks > 1 && enc->kind == LCPC_B200_ENC_LIGERO) {
+        CU(ctx, cudaEventRecord(ctx->lane_fork, st));
+        CU(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->lane_fork, 0));
+        for (size_t k = 0; k < chunks; k++) {
+          const size_t q0 = k * s->my_rows / chunks, q1 = (k + 1) * s->my_rows / chunks;
+          Scatter sk = sc;
+          sk.row0 += q0;
+          int nl = 0;
+          cudaError_t ce = launch_ntt_rows(enc->field, s->d_coeffs + q0 * p.n_per_row * s->N, p.n_per_row, p.n_per_row,
+                                           s->d_tmp + q0 * p.n_cols * s->N, p.n_cols, enc->d_roots, enc->log_n, q1 - q0,
+                                           (k & 1) ? ctx->side_stream : st, &nl, &sk);
+          ctx->launches += nl;
+          if (ce != cudaSuccess) return cuda_fail(ctx, ce, "shard: encode");
+        }
+        CU(ctx, cudaEventRecord(ctx->lane_join, ctx->side_stream));
+        CU(ctx, cudaStreamWaitEvent(st, ctx->lane_join, 0));
+      } else if (int rc = encode_rows(enc, s->d_coeffs, p.n_per_row, p.n_per_row, s->d_tmp, s->my_rows, s->d_enc_scratch, &sc)) {
+        return rc;
+      }
     }
   }
   CU(ctx, cudaEventRecord(s->ev[1], st));
@@ -617,6 +638,16 @@ int lcpc_b200_shard_commit_dev(lcpc_b200_shard *s, const uint64_t *d_rows, size_
   std::lock_guard<std::mutex> g(ctx->mu);
   if (int rc = bind_device(ctx)) return rc;
   return commit_enqueue(s, d_rows, d_rows ? n_elems : 0, false);
+}
+
+int lcpc_b200_shard_commit_step(lcpc_b200_shard *s, int step) {
+  if (!s || step < 1 || step > 3) return LCPC_B200_ERR_BAD_ARG;
+  lcpc_b200_ctx *ctx = s->enc->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (int rc = bind_device(ctx)) return rc;
+  if (step == 1) return commit_step1(s, nullptr, 0, false);
+  if (s->epoch == 0) return fail(ctx, LCPC_B200_ERR_BAD_ARG, "shard: step %d before step 1", step);
+  return step == 2 ? commit_step2(s) : commit_step3(s);
 }
 
 int lcpc_b200_shard_load_rows(lcpc_b200_shard *s, const uint64_t *rows, size_t n_elems) {

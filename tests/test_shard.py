@@ -212,3 +212,37 @@ def test_c_host_drives_n_gpus_through_the_header_alone(c_exe, n_gpus, kind, lg):
         assert out.returncode == 0 and out.stdout.strip().endswith("ok"), (devices, out.stdout, out.stderr)
         if n_dev < 2:
             break
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunks", [2, 3, 5])
+def test_two_stream_chunked_encode_is_result_neutral(chunks):
+    """SHARD_ENC_CHUNKS: a shard's row block encoded in chunks that alternate between two streams must leave the same
+    column blocks and LcRoot (rows of a chunk go to their own rows of the owners' matrices)."""
+    import oracle as O
+    from lcpc_b200 import _cabi
+    field, length, world = P.FT255, 1 << 16, 2
+    lib = _cabi.lib()
+    try:
+        lib.lcpc_b200_set_tunable(b"SHARD_ENC_CHUNKS", chunks)
+        encs = _encodings("ligero", field, length, [0] * world)
+        x = O.random_elems(field, length, seed=chunks)
+        oc = O.Encoding.ligero(field, length).commit(x)
+        mc = P.MultiCommit.commit(x, encs)
+        for g in range(world):
+            s = mc.shard(g)
+            s.load_rows(x[s.row_lo * s.n_per_row:s.row_lo * s.n_per_row + s.n_elems])
+        # device-resident rows take the chunked route
+        for g in range(world):
+            mc.shard(g).enc.ctx.synchronize()
+        shards = [mc.shard(g) for g in range(world)]
+        for step in (1, 2, 3):
+            for s in shards:
+                assert _cabi.lib().lcpc_b200_shard_commit_step(s._h, step) == 0
+        comm = oc["comm"].reshape(mc.n_rows, mc.n_cols, -1)
+        for s in shards:
+            assert s.get_root().root == oc["root"]
+            assert (s.local_columns() == comm[:, s.col_lo:s.col_hi]).all()
+        mc.close()
+    finally:
+        lib.lcpc_b200_set_tunable(b"SHARD_ENC_CHUNKS", 1)
