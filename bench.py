@@ -620,6 +620,7 @@ def bench_sharded(args, ctx, enc, field, n, torch, P):
     ev0.record(stream)
     for _ in range(args.steps):
         sc.commit()
+    sc.join()  # pipelined mode: the engine stream waits for the last commit's hash stream before the end event
     ev1.record(stream)
     ctx.synchronize()
     torch.cuda.synchronize()
@@ -646,6 +647,7 @@ def bench_sharded(args, ctx, enc, field, n, torch, P):
     for k in range(2):
         sc.commit_host_ptr(host.data_ptr(), sc.n_elems)
         sc.root_enqueue(roots[e2e_steps + k].data_ptr())
+    sc.join()
     ctx.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
@@ -653,6 +655,7 @@ def bench_sharded(args, ctx, enc, field, n, torch, P):
     for k in range(e2e_steps):
         sc.commit_host_ptr(host.data_ptr(), sc.n_elems)
         sc.root_enqueue(roots[k].data_ptr())
+    sc.join()
     ctx.synchronize()
     torch.cuda.synchronize()
     dist.barrier()

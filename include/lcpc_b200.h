@@ -310,6 +310,11 @@ int lcpc_b200_shard_root(lcpc_b200_shard *s, uint8_t root[32]);
 /* the same without the synchronisation: the 32 bytes land in `root` (page-locked host memory) when the stream
  * gets there; a pipelined caller enqueues the next commit right behind it and reads the roots later */
 int lcpc_b200_shard_root_enqueue(lcpc_b200_shard *s, uint8_t *root);
+/* Tunable SHARD_PIPELINE=1 (read at lcpc_b200_shard_new) runs a commit's exchange wait, hashing and tree on a second
+ * stream so that the next commit's encode follows this one's directly.  lcpc_b200_shard_join makes the context's
+ * stream (lcpc_b200_ctx_stream, what callers time and synchronise) wait for that second stream; every call that
+ * reads a commit's results joins by itself.  Enqueue only. */
+int lcpc_b200_shard_join(lcpc_b200_shard *s);
 /* device times of the last commit on this rank: ms[0] encode + peer stores, ms[1] wait for the peers' tiles,
  * ms[2] column hashing, subtree roots, root exchange and top tree */
 int lcpc_b200_shard_phase_times(lcpc_b200_shard *s, float ms[3]);

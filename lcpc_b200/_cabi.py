@@ -121,6 +121,7 @@ SIGNATURES = {
     "lcpc_b200_shard_commit_step": (_i, [_vp, _i]),
     "lcpc_b200_shard_root": (_i, [_vp, _vp]),
     "lcpc_b200_shard_root_enqueue": (_i, [_vp, _vp]),
+    "lcpc_b200_shard_join": (_i, [_vp]),
     "lcpc_b200_shard_phase_times": (_i, [_vp, _vp]),
     "lcpc_b200_shard_device_ptrs": (_i, [_vp, _pvp, _pvp, _pvp, _pvp]),
     "lcpc_b200_shard_download": (_i, [_vp, _vp, _vp]),

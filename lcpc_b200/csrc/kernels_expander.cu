@@ -725,12 +725,27 @@ fused_levels_kernel(FusedOps ops, uint32_t *__restrict__ W, size_t n_rows, uint3
         typename F::Wide acc = F::wide_zero();
         if (act) {
           const uint32_t k0 = __ldg(op.rowptr + i), k1 = __ldg(op.rowptr + i + 1);
-          for (uint32_t k = k0 + gl; k < k1; k += G) {
-            const uint32_t j = __ldg(op.colidx + k);
-            typename F::Elem a, xv;
-            ldv<N>(a.v, op.vals + (size_t)k * N);
-            ldv<N>(xv.v, in + (size_t)j * N);
-            F::mac_wide(acc, a, xv);
+          // column indices and values of up to FB non-zeros are requested before the first product: the matrices of
+          // these levels sit in L2, and a lane walks ~3..15 non-zeros, so one L2 round trip per non-zero was most
+          // of this kernel's time (it runs on n_rows CTAs only: pure latency)
+          constexpr int FB = N <= 4 ? 4 : 2;
+          for (uint32_t kb = k0 + gl; kb < k1; kb += FB * G) {
+            uint32_t j[FB];
+            typename F::Elem a[FB];
+#pragma unroll
+            for (int u = 0; u < FB; u++) {
+              const uint32_t k = min(kb + u * G, k1 - 1);
+              asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(j[u]) : "l"(op.colidx + k));
+              ldv_early<N>(a[u].v, op.vals + (size_t)k * N);
+            }
+#pragma unroll
+            for (int u = 0; u < FB; u++) {
+              if (kb + u * G < k1) {
+                typename F::Elem xv;
+                ldv<N>(xv.v, in + (size_t)j[u] * N);
+                F::mac_wide(acc, a[u], xv);
+              }
+            }
           }
         }
         for (unsigned d = G >> 1; d >= 1; d >>= 1) {

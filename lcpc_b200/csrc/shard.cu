@@ -240,6 +240,13 @@ struct lcpc_b200_shard {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t coeffs_free = nullptr;  // recorded behind the last enqueued reader of d_coeffs (encode pass, collapse)
   bool coeffs_free_valid = false;
+  // SHARD_PIPELINE: steps 2 and 3 of a commit (exchange wait, column hashing, roots, top tree) run on their own stream,
+  // so that the NEXT commit's encode starts right behind this commit's -- the hash phase of a small per-GPU share is
+  // a string of short, latency-bound launches that would otherwise leave the GPU mostly idle
+  bool pipelined = false;
+  cudaStream_t hash_stream = nullptr;
+  cudaEvent_t enc_done = nullptr, hash_done = nullptr;
+  bool hash_pending = false;
   unsigned long long timeout_ns = (unsigned long long)std::max<long>(1, tunable("SHARD_TIMEOUT_MS", 20000)) * 1000000ull;
 };
 
@@ -250,17 +257,17 @@ uint32_t *flags_of(lcpc_b200_shard *s, unsigned ch) {
 }
 size_t flag_off(const lcpc_b200_shard *s, unsigned ch) { return s->wl.flags + (size_t)ch * MAX_WORLD * 4; }
 
-int signal_all(lcpc_b200_shard *s, unsigned ch, uint32_t epoch) {
+int signal_all(lcpc_b200_shard *s, unsigned ch, uint32_t epoch, cudaStream_t st = nullptr) {
   lcpc_b200_ctx *ctx = s->enc->ctx;
-  shard_signal_kernel<<<1, 32, 0, ctx->stream>>>(s->peers, flag_off(s, ch), s->p.world, s->rank, epoch);
+  shard_signal_kernel<<<1, 32, 0, st ? st : ctx->stream>>>(s->peers, flag_off(s, ch), s->p.world, s->rank, epoch);
   ctx->launches += 1;
   CU(ctx, cudaGetLastError());
   return LCPC_B200_OK;
 }
 
-int wait_all(lcpc_b200_shard *s, unsigned ch, uint32_t epoch) {
+int wait_all(lcpc_b200_shard *s, unsigned ch, uint32_t epoch, cudaStream_t st = nullptr) {
   lcpc_b200_ctx *ctx = s->enc->ctx;
-  shard_wait_kernel<<<1, 32, 0, ctx->stream>>>(flags_of(s, ch), s->p.world, epoch,
+  shard_wait_kernel<<<1, 32, 0, st ? st : ctx->stream>>>(flags_of(s, ch), s->p.world, epoch,
                                                reinterpret_cast<uint32_t *>(s->window + s->wl.status), s->timeout_ns);
   ctx->launches += 1;
   CU(ctx, cudaGetLastError());
@@ -296,6 +303,12 @@ void shard_release(lcpc_b200_shard *s) {
   for (auto &e : s->ev)
     if (e) cudaEventDestroy(e);
   if (s->coeffs_free) cudaEventDestroy(s->coeffs_free);
+  if (s->enc_done) cudaEventDestroy(s->enc_done);
+  if (s->hash_done) cudaEventDestroy(s->hash_done);
+  if (s->hash_stream) {
+    cudaStreamSynchronize(s->hash_stream);
+    cudaStreamDestroy(s->hash_stream);
+  }
   delete s;
 }
 
@@ -319,6 +332,13 @@ int zero_subtree_root(lcpc_b200_shard *s, uint8_t out[32]) {
   return LCPC_B200_OK;
 }
 
+// the engine stream waits for whatever the hash stream still has in flight (pipelined mode); enqueue only
+int join_streams(lcpc_b200_shard *s) {
+  lcpc_b200_ctx *ctx = s->enc->ctx;
+  if (s->pipelined && s->hash_pending) CU(ctx, cudaStreamWaitEvent(ctx->stream, s->hash_done, 0));
+  return LCPC_B200_OK;
+}
+
 // One commit of this rank's row block, enqueued in three steps.  A one-process-per-GPU host runs them back to back;
 // a single process driving several shards runs step 1 on every shard, then step 2 on every shard, then step 3, so
 // that every wait kernel is enqueued behind all the signals it waits for -- whichever hardware queue the driver
@@ -338,6 +358,11 @@ int commit_step1(lcpc_b200_shard *s, const void *rows, size_t n_elems, bool rows
   cudaStream_t st = ctx->stream;
   const uint32_t e = ++s->epoch;
   const unsigned par = e & 1;
+  // pipelined mode: the engine stream itself never waits for this commit's exchange, so before it overwrites the
+  // receive matrices of two commits ago it makes sure every rank has finished hashing them ("roots landed" of e - 2
+  // is sent behind a rank's leaf hashing and subtree reduction); normally long satisfied
+  if (s->pipelined && e >= 3)
+    if (int rc = wait_all(s, CH_ROOTS, e - 2, st)) return rc;
   CU(ctx, cudaEventRecord(s->ev[0], st));
   if (s->my_rows) {
     Scatter sc;
@@ -354,9 +379,10 @@ int commit_step1(lcpc_b200_shard *s, const void *rows, size_t n_elems, bool rows
         const size_t padded = s->my_rows * p.n_per_row;
         if (padded > n_elems) CU(ctx, cudaMemsetAsync((uint8_t *)s->d_coeffs + n_elems * s->B, 0, (padded - n_elems) * s->B, st));
       }
-      // A/B knob SHARD_ENC_CHUNKS (Ligero): the row block in chunks that alternate between the engine and the side
-      // stream, so that one chunk's last pass (the one that stores over NVLink) runs beside the next chunk's first
-      const size_t chunks = std::min<size_t>((size_t)std::max<long>(1, tunable("SHARD_ENC_CHUNKS", 1)), s->my_rows);
+      // SHARD_ENC_CHUNKS (Ligero): the row block in chunks (of at least 8 rows) that alternate between the engine and
+      // the side stream, so that one chunk's last pass (the one that stores over NVLink) runs beside the next chunk's first
+      // (8 GPUs, 2^24: encode + peer stores 0.705 -> 0.672 ms with 2 or 4 chunks, profiles/r02_bench_g8_ligero_enc_chunks*.json)
+      const size_t chunks = std::min<size_t>((size_t)std::max<long>(1, tunable("SHARD_ENC_CHUNKS", 4)), std::max<size_t>(1, s->my_rows / 8));
       if (chunks > 1 && enc->kind == LCPC_B200_ENC_LIGERO) {
         CU(ctx, cudaEventRecord(ctx->lane_fork, st));
         CU(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->lane_fork, 0));
@@ -381,17 +407,20 @@ int commit_step1(lcpc_b200_shard *s, const void *rows, size_t n_elems, bool rows
   CU(ctx, cudaEventRecord(s->ev[1], st));
   CU(ctx, cudaEventRecord(s->coeffs_free, st));
   s->coeffs_free_valid = true;
-  return signal_all(s, CH_TILES, e);
+  if (int rc = signal_all(s, CH_TILES, e, st)) return rc;
+  if (s->pipelined) CU(ctx, cudaEventRecord(s->enc_done, st));
+  return LCPC_B200_OK;
 }
 
 int commit_step2(lcpc_b200_shard *s) {
   lcpc_b200_enc *enc = s->enc;
   lcpc_b200_ctx *ctx = enc->ctx;
   const ShardPlan &p = s->p;
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = s->pipelined ? s->hash_stream : ctx->stream;
   const uint32_t e = s->epoch;
   const unsigned par = e & 1;
-  if (int rc = wait_all(s, CH_TILES, e)) return rc;
+  if (s->pipelined) CU(ctx, cudaStreamWaitEvent(st, s->enc_done, 0));
+  if (int rc = wait_all(s, CH_TILES, e, st)) return rc;
   CU(ctx, cudaEventRecord(s->ev[2], st));
   if (s->my_cols) {
     int nl = 0;
@@ -415,10 +444,10 @@ int commit_step2(lcpc_b200_shard *s) {
 int commit_step3(lcpc_b200_shard *s) {
   lcpc_b200_ctx *ctx = s->enc->ctx;
   const ShardPlan &p = s->p;
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = s->pipelined ? s->hash_stream : ctx->stream;
   const uint32_t e = s->epoch;
   const unsigned par = e & 1;
-  if (int rc = wait_all(s, CH_ROOTS, e)) return rc;
+  if (int rc = wait_all(s, CH_ROOTS, e, st)) return rc;
   CU(ctx, cudaMemcpyAsync(s->d_top, s->window + s->wl.top[par], p.n_real_sub * 32, cudaMemcpyDeviceToDevice, st));
   if (p.n_sub > 1) {
     unsigned lg = 0;
@@ -429,6 +458,10 @@ int commit_step3(lcpc_b200_shard *s) {
     if (ce != cudaSuccess) return cuda_fail(ctx, ce, "shard: top tree");
   }
   CU(ctx, cudaEventRecord(s->ev[3], st));
+  if (s->pipelined) {
+    CU(ctx, cudaEventRecord(s->hash_done, st));
+    s->hash_pending = true;
+  }
   return LCPC_B200_OK;
 }
 
@@ -510,6 +543,10 @@ int lcpc_b200_shard_new(lcpc_b200_enc *enc, size_t len, unsigned world, unsigned
   for (auto &e : s->ev)
     if (ce == cudaSuccess) ce = cudaEventCreate(&e);
   if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&s->coeffs_free, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&s->enc_done, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&s->hash_done, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&s->hash_stream, cudaStreamNonBlocking);
+  s->pipelined = tunable("SHARD_PIPELINE", 0) != 0;
   if (ce == cudaSuccess) ce = cudaMemset(s->d_forest, 0, std::max<size_t>(s->forest_nodes * 32, 256));
   if (ce == cudaSuccess) ce = cudaMemset(s->d_top, 0, (2 * p.n_sub - 1) * 32);
   if (ce == cudaSuccess) ce = cudaMemset(s->d_coeffs, 0, std::max<size_t>(s->my_rows * n_per_row * B, 256));
@@ -656,6 +693,7 @@ int lcpc_b200_shard_load_rows(lcpc_b200_shard *s, const uint64_t *rows, size_t n
   std::lock_guard<std::mutex> g(ctx->mu);
   if (n_elems != s->my_elems) return fail(ctx, LCPC_B200_ERR_BAD_ARG, "shard %u holds %zu coefficients, %zu given", s->rank, s->my_elems, n_elems);
   if (int rc = bind_device(ctx)) return rc;
+  if (int rc = join_streams(s)) return rc;
   if (n_elems) CU(ctx, cudaMemcpyAsync(s->d_coeffs, rows, n_elems * s->B, cudaMemcpyHostToDevice, ctx->stream));
   const size_t padded = s->my_rows * s->p.n_per_row;
   if (padded > n_elems) CU(ctx, cudaMemsetAsync((uint8_t *)s->d_coeffs + n_elems * s->B, 0, (padded - n_elems) * s->B, ctx->stream));
@@ -669,9 +707,18 @@ int lcpc_b200_shard_root(lcpc_b200_shard *s, uint8_t root[32]) {
   std::lock_guard<std::mutex> g(ctx->mu);
   if (int rc = bind_device(ctx)) return rc;
   if (s->epoch == 0) return fail(ctx, LCPC_B200_ERR_BAD_ARG, "shard: no commit has run");
+  if (int rc = join_streams(s)) return rc;
   CU(ctx, cudaMemcpyAsync(root, s->d_top + (2 * s->p.n_sub - 2) * 32, 32, cudaMemcpyDeviceToHost, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   return check_status(s);
+}
+
+int lcpc_b200_shard_join(lcpc_b200_shard *s) {
+  if (!s) return LCPC_B200_ERR_BAD_ARG;
+  lcpc_b200_ctx *ctx = s->enc->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (int rc = bind_device(ctx)) return rc;
+  return join_streams(s);
 }
 
 int lcpc_b200_shard_root_enqueue(lcpc_b200_shard *s, uint8_t *root) {
@@ -680,7 +727,10 @@ int lcpc_b200_shard_root_enqueue(lcpc_b200_shard *s, uint8_t *root) {
   std::lock_guard<std::mutex> g(ctx->mu);
   if (int rc = bind_device(ctx)) return rc;
   if (s->epoch == 0) return fail(ctx, LCPC_B200_ERR_BAD_ARG, "shard: no commit has run");
-  CU(ctx, cudaMemcpyAsync(root, s->d_top + (2 * s->p.n_sub - 2) * 32, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  // behind the top tree of the last enqueued commit, on whichever stream computes it
+  CU(ctx, cudaMemcpyAsync(root, s->d_top + (2 * s->p.n_sub - 2) * 32, 32, cudaMemcpyDeviceToHost,
+                          s->pipelined ? s->hash_stream : ctx->stream));
+  if (s->pipelined) CU(ctx, cudaEventRecord(s->hash_done, s->hash_stream));
   return LCPC_B200_OK;
 }
 
@@ -709,6 +759,7 @@ int lcpc_b200_shard_download(lcpc_b200_shard *s, uint64_t *cols_out, uint8_t *le
   std::lock_guard<std::mutex> g(ctx->mu);
   if (int rc = bind_device(ctx)) return rc;
   if (s->epoch == 0) return fail(ctx, LCPC_B200_ERR_BAD_ARG, "shard: no commit has run");
+  if (int rc = join_streams(s)) return rc;
   if (cols_out && s->my_cols)
     CU(ctx, cudaMemcpyAsync(cols_out, s->window + s->wl.recv[s->epoch & 1], s->p.n_rows * s->my_cols * s->B, cudaMemcpyDeviceToHost, ctx->stream));
   if (leaves_out && s->my_cols) CU(ctx, cudaMemcpyAsync(leaves_out, s->d_forest, s->my_cols * 32, cudaMemcpyDeviceToHost, ctx->stream));
@@ -727,6 +778,7 @@ int lcpc_b200_shard_collapse_begin(lcpc_b200_shard *s, const uint64_t *tensor, c
   if (!s->connected) return fail(ctx, LCPC_B200_ERR_BAD_ARG, "shard: not connected");
   if (s->collapse_seq != s->collapse_done) return fail(ctx, LCPC_B200_ERR_BAD_ARG, "shard: a collapse is already in flight");
   if (int rc = bind_device(ctx)) return rc;
+  if (int rc = join_streams(s)) return rc;
   const ShardPlan &p = s->p;
   const int field = s->enc->field;
   cudaStream_t st = ctx->stream;
@@ -801,6 +853,7 @@ int lcpc_b200_shard_open_begin(lcpc_b200_shard *s, const uint64_t *cols, size_t 
   for (size_t i = 0; i < n; i++)
     if (cols[i] >= p.n_cols) return fail(ctx, LCPC_B200_ERR_COLUMN, "column %llu >= n_cols %zu", (unsigned long long)cols[i], p.n_cols);
   if (int rc = bind_device(ctx)) return rc;
+  if (int rc = join_streams(s)) return rc;
   cudaStream_t st = ctx->stream;
   const uint32_t k = ++s->open_seq;
   const unsigned par = k & 1;

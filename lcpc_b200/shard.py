@@ -120,6 +120,10 @@ class Shard(_ProveMixin):
         """Enqueue the D2H of the LcRoot into page-locked host memory at `host_ptr` (no synchronisation)."""
         _check(_cabi.lib().lcpc_b200_shard_root_enqueue(self._h, C.c_void_p(host_ptr)), self.enc.ctx)
 
+    def join(self):
+        """Make the context's stream wait for the shard's hash stream (pipelined mode); enqueue only."""
+        _check(_cabi.lib().lcpc_b200_shard_join(self._h), self.enc.ctx)
+
     def phase_times(self):
         ms = (C.c_float * 3)()
         _check(_cabi.lib().lcpc_b200_shard_phase_times(self._h, ms), self.enc.ctx)

@@ -1,8 +1,9 @@
 """Parity pin against the REAL reference, when its roots are available.
 
 tools/rust_golden/ runs conroi/lcpc itself (cargo) on seeded inputs; this image has no Rust toolchain, so the
-file tests/golden/rust_roots.json may not exist yet -- then the test is skipped and the parity status of
-DESIGN.md section 7 ("unpinned" for field repr / NTT order / matgen streams) stands.  Once the file is there,
+file tests/golden/rust_roots.json may not exist yet -- then the test is reported as XFAIL (an open gap, not a silent
+skip) and the parity status of DESIGN.md section 7 stands: ff_derive's random / to_repr and fffft's output order are
+held to published descriptions only, everything else to published vectors.  Once the file is there,
 the oracle has to reproduce every root and the dims the reference chose.
 """
 import importlib.util
@@ -40,7 +41,8 @@ def test_tool_inputs_are_canonical_and_reproducible(tmp_path):
 
 def test_oracle_reproduces_reference_roots():
     if not os.path.exists(GOLD):
-        pytest.skip("tests/golden/rust_roots.json absent: no Rust toolchain was available to run the reference")
+        pytest.xfail("tests/golden/rust_roots.json absent: no Rust toolchain was available to run the reference; parity "
+                     "against the real crates stays unpinned for ff_derive's random/to_repr and fffft's output order")
     mod = _cases()
     want = {}
     for line in open(GOLD):

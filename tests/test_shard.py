@@ -245,4 +245,42 @@ def test_two_stream_chunked_encode_is_result_neutral(chunks):
             assert (s.local_columns() == comm[:, s.col_lo:s.col_hi]).all()
         mc.close()
     finally:
-        lib.lcpc_b200_set_tunable(b"SHARD_ENC_CHUNKS", 1)
+        lib.lcpc_b200_set_tunable(b"SHARD_ENC_CHUNKS", 4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,field,length,world", [("ligero", P.FT255, 1 << 16, 2), ("sdig", P.FT127, 1 << 14, 3), ("ligero", P.FT127, 5000, 4)])
+def test_pipelined_hash_stream_is_result_neutral(kind, field, length, world):
+    """SHARD_PIPELINE=1: exchange wait, hashing and the tree of commit k run on a second stream under the encode of
+    commit k+1.  Several commits back to back with alternating inputs (so that a receive matrix overwritten too early,
+    or a root read too early, would show), then prove pieces, then a whole prove()."""
+    import oracle as O
+    from oracle import protocol as PR
+    from oracle.transcript import Transcript as OTranscript
+    from lcpc_b200 import _cabi
+    lib = _cabi.lib()
+    try:
+        lib.lcpc_b200_set_tunable(b"SHARD_PIPELINE", 1)
+        encs = _encodings(kind, field, length, [0] * world)
+        oenc = _oracle(kind, field, length)
+        xs = [O.random_elems(field, length, seed=40 + i) for i in range(2)]
+        ocs = [oenc.commit(x) for x in xs]
+        mc = P.MultiCommit.commit(xs[0], encs)
+        assert mc.get_root().root == ocs[0]["root"]
+        for i in range(1, 6):  # enqueue five commits without looking at any result in between
+            mc.rerun(xs[i % 2])
+        assert mc.get_root().root == ocs[1]["root"]
+        comm = ocs[1]["comm"].reshape(mc.n_rows, mc.n_cols, -1)
+        for g in range(world):
+            s = mc.shard(g)
+            assert (s.local_columns() == comm[:, s.col_lo:s.col_hi]).all()
+            assert (s.local_leaves() == ocs[1]["hashes"][s.col_lo:s.col_hi]).all()
+        outer = O.random_elems(field, mc.n_rows, seed=2)
+        proof = mc.prove(outer, encs[0], P.Transcript(b"pipelined"))
+        oproof = PR.prove(field, ocs[1], outer, oenc.get_n_degree_tests(), oenc.get_n_col_opens(), OTranscript(b"pipelined"))
+        assert P.serialize_proof(proof) == PR.wire_proof(oproof)
+        mc.rerun(xs[0])  # a commit after a prove: the streams are joined again
+        assert mc.get_root().root == ocs[0]["root"]
+        mc.close()
+    finally:
+        lib.lcpc_b200_set_tunable(b"SHARD_PIPELINE", 0)
