@@ -544,6 +544,11 @@ def bench_single(args, ctx, enc, field, n, torch, P, cpu_budget=0.0):
                              "compute (the PCIe floor of this box)"})
 
 
+def _cabi_tunable(P, name, dflt):
+    from lcpc_b200 import _cabi
+    return _cabi.lib().lcpc_b200_get_tunable(name.encode(), dflt)
+
+
 def sampled_commit_check(sc, enc, field, n, root0, world, rank, dist, P):
     """Parity of a sharded commit that is too large for a whole oracle commit (2^26 .. 2^28): checks whose cost does not
     grow with the matrix.  (1) two whole rows: their column slices are collected from the owners' receive matrices and
@@ -602,6 +607,9 @@ def bench_sharded(args, ctx, enc, field, n, torch, P):
     L = P.FIELD_LIMBS[field]
     B = 8 * L
     sc = P.ShardedCommit(enc, n)
+    pipelined = bool(_cabi_tunable(P, "SHARD_PIPELINE", 1))
+    sc.transport += ("; consecutive commits pipelined: a commit's exchange wait, hashing and tree run on a second stream "
+                     "under the next commit's encode" if pipelined else "; commits strictly one after the other")
     # this rank's rows of a synthetic polynomial (uniform field elements, seeded per rank: only the slice a rank owns
     # is ever materialised, so 2^28 coefficients do not cost every rank 8 GiB of host memory)
     x = synthetic_coeffs(field, sc.n_elems, seed=1000 + rank)

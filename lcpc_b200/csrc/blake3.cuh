@@ -35,6 +35,8 @@ __device__ __forceinline__ uint32_t rotr(uint32_t x, int n) { return __funnelshi
 // pipe idles.  An add written as x * 1 + y with the 1 hidden in constant memory has to be an IMAD, which moves it
 // to the other pipe: LCPC_B3_FMA_ADDS of the two three-input adds of every G are done that way (0, 1 or 2).
 // Measured on the Ft255 leaf kernel at 2^24 (131072 columns x 129 compressions): 0.831 / 0.784 / 0.734 ms.
+// Levels 3 / 4 (round 2: also the two-input adds c += d) measured 0.752 / 0.752 ms against 0.746 for level 2 in the
+// same run (profiles/r02_ab_blake3_fma_adds.jsonl): the pipes are balanced at 2.
 #ifndef LCPC_B3_FMA_ADDS
 #define LCPC_B3_FMA_ADDS 2
 #endif
@@ -53,15 +55,25 @@ __device__ __forceinline__ uint32_t add3_second(uint32_t a, uint32_t b, uint32_t
   return a + b + m;
 }
 
+// levels 3 and 4 also move the first / both two-input adds (c += d): one ALU op becomes one multiplier-pipe op
+__device__ __forceinline__ uint32_t add2_first(uint32_t c, uint32_t d) {
+  if (LCPC_B3_FMA_ADDS >= 3) return add_on_fma(c, d);
+  return c + d;
+}
+__device__ __forceinline__ uint32_t add2_second(uint32_t c, uint32_t d) {
+  if (LCPC_B3_FMA_ADDS >= 4) return add_on_fma(c, d);
+  return c + d;
+}
+
 #define LCPC_B3_G(a, b, c, d, mx, my) \
   do {                                \
     a = add3_first(a, b, (mx));       \
     d = rotr(d ^ a, 16);              \
-    c = c + d;                        \
+    c = add2_first(c, d);             \
     b = rotr(b ^ c, 12);              \
     a = add3_second(a, b, (my));      \
     d = rotr(d ^ a, 8);               \
-    c = c + d;                        \
+    c = add2_second(c, d);            \
     b = rotr(b ^ c, 7);               \
   } while (0)
 

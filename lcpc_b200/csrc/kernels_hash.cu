@@ -40,7 +40,7 @@ __device__ __forceinline__ void gload_elem(uint32_t (&v)[N], const uint32_t *p) 
 // Chunk `k` of column `col`.  Works in "slots" of one element (B bytes): slot s of the leaf input is
 // zero for s < 32/B (the 32-byte zero prefix, lib.rs:722-723) and row s - 32/B after that.
 // Requires B | 64 (Ft63, Ft127, Ft255).
-template <int FID>
+template <int FID, bool SHORT_SOURCE = false>
 __global__ void __launch_bounds__(HASH_THREADS)
 leaf_chunk_kernel(const uint32_t *__restrict__ comm, size_t n_rows, size_t n_cols, size_t row_stride,
                   uint32_t *__restrict__ out, unsigned n_chunks, unsigned k_first, size_t out_cols, size_t col0,
@@ -63,7 +63,8 @@ leaf_chunk_kernel(const uint32_t *__restrict__ comm, size_t n_rows, size_t n_col
   const uint32_t *cp = comm + col * N;
   // rows of this column that exist in the source: all of them, unless the source ends inside the last row (element
   // (r, c) exists iff r * row_stride + c < src_total; beyond that the commit's zero padding is hashed)
-  const size_t rows_here = src_total == ~(size_t)0 ? n_rows
+  // (compiled in only for sources that can end early: the whole-commit path pays nothing for it)
+  const size_t rows_here = !SHORT_SOURCE ? n_rows
                            : (src_total > col ? min(n_rows, (src_total - col + row_stride - 1) / row_stride) : 0);
   for (unsigned b = 0; b < n_blocks; b++) {
     uint32_t m[16];
@@ -237,10 +238,19 @@ cudaError_t launch_leaf_chunks_range(int field, const uint32_t *comm, size_t n_r
   // stream leaves registers for the kernels it runs beside (only applied to ranges, i.e. col0 or total_cols set)
   const size_t pad = (total_cols != n_cols) ? (size_t)std::min<long>(47, std::max<long>(0, tunable("LEAF_SMEM_PAD_KB", 0))) << 10 : 0;
   switch (field) {
-    case FT63: leaf_chunk_kernel<FT63><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total); break;
-    case FT127: leaf_chunk_kernel<FT127><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total); break;
+    case FT63:
+      if (src_total == ~(size_t)0) leaf_chunk_kernel<FT63, false><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total);
+      else leaf_chunk_kernel<FT63, true><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total);
+      break;
+    case FT127:
+      if (src_total == ~(size_t)0) leaf_chunk_kernel<FT127, false><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total);
+      else leaf_chunk_kernel<FT127, true><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total);
+      break;
     case FT191: leaf_chunk_kernel_generic<FT191><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total); break;
-    case FT255: leaf_chunk_kernel<FT255><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total); break;
+    case FT255:
+      if (src_total == ~(size_t)0) leaf_chunk_kernel<FT255, false><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total);
+      else leaf_chunk_kernel<FT255, true><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total);
+      break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

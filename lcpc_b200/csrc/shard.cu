@@ -546,7 +546,9 @@ int lcpc_b200_shard_new(lcpc_b200_enc *enc, size_t len, unsigned world, unsigned
   if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&s->enc_done, cudaEventDisableTiming);
   if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&s->hash_done, cudaEventDisableTiming);
   if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&s->hash_stream, cudaStreamNonBlocking);
-  s->pipelined = tunable("SHARD_PIPELINE", 0) != 0;
+  // 2 GPUs, 2^24 (profiles/r02_bench_g2_pipeline{0,1}.json): Brakedown 1.057 -> 0.968 ms per commit, Ligero unchanged
+  // (its leaf hashing is a full-GPU ALU-bound kernel at that share); on by default
+  s->pipelined = tunable("SHARD_PIPELINE", 1) != 0;
   if (ce == cudaSuccess) ce = cudaMemset(s->d_forest, 0, std::max<size_t>(s->forest_nodes * 32, 256));
   if (ce == cudaSuccess) ce = cudaMemset(s->d_top, 0, (2 * p.n_sub - 1) * 32);
   if (ce == cudaSuccess) ce = cudaMemset(s->d_coeffs, 0, std::max<size_t>(s->my_rows * n_per_row * B, 256));

@@ -249,8 +249,9 @@ def test_two_stream_chunked_encode_is_result_neutral(chunks):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("pipeline", [1, 0])
 @pytest.mark.parametrize("kind,field,length,world", [("ligero", P.FT255, 1 << 16, 2), ("sdig", P.FT127, 1 << 14, 3), ("ligero", P.FT127, 5000, 4)])
-def test_pipelined_hash_stream_is_result_neutral(kind, field, length, world):
+def test_pipelined_hash_stream_is_result_neutral(kind, field, length, world, pipeline):
     """SHARD_PIPELINE=1: exchange wait, hashing and the tree of commit k run on a second stream under the encode of
     commit k+1.  Several commits back to back with alternating inputs (so that a receive matrix overwritten too early,
     or a root read too early, would show), then prove pieces, then a whole prove()."""
@@ -260,7 +261,7 @@ def test_pipelined_hash_stream_is_result_neutral(kind, field, length, world):
     from lcpc_b200 import _cabi
     lib = _cabi.lib()
     try:
-        lib.lcpc_b200_set_tunable(b"SHARD_PIPELINE", 1)
+        lib.lcpc_b200_set_tunable(b"SHARD_PIPELINE", pipeline)
         encs = _encodings(kind, field, length, [0] * world)
         oenc = _oracle(kind, field, length)
         xs = [O.random_elems(field, length, seed=40 + i) for i in range(2)]
@@ -283,4 +284,4 @@ def test_pipelined_hash_stream_is_result_neutral(kind, field, length, world):
         assert mc.get_root().root == ocs[0]["root"]
         mc.close()
     finally:
-        lib.lcpc_b200_set_tunable(b"SHARD_PIPELINE", 0)
+        lib.lcpc_b200_set_tunable(b"SHARD_PIPELINE", 1)
