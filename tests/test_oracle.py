@@ -431,3 +431,32 @@ def test_seed_from_u64_value_of_rand_core_and_the_oracle_draw():
         want = [v & ((1 << 63) - 1) for v in u64s if (v & ((1 << 63) - 1)) < p][:100]  # ff_derive random: mask, reject >= p
         got = [int(v) for v in O.random_elems(O.FT63, 100, seed=seed, stream=stream)[:, 0]]
         assert got == want
+
+
+def test_commit_property_on_encoded_rows_at_the_headline_row_length():
+    """lcpc-2d/src/tests.rs:193-236 (ii) at config 4's row shape (Ft255, 65536 coefficients -> 2^17 points): the ENCODED
+    rows combined with the outer tensor (`eval_outer_fft`, lib.rs:1229-1249) and taken back through `ifft_oi` give the
+    combined coefficient row -- high half exactly zero, low half equal to collapse_columns of the coefficients -- and
+    the same evaluation as the direct sum.  This is everything the reference's own test pins about `fft_io_pc`: it is
+    linear and inverted by `ifft_oi` (which order / which root it uses stays a property of the fffft crate)."""
+    f = O.FT255
+    p = CONSTS[f]["p"]
+    n_rows, npr, nc = 4, 65536, 131072
+    enc = O.Encoding.ligero_from_dims(f, npr, nc)
+    x = O.random_elems(f, n_rows * npr, seed=17)
+    c = enc.commit(x)
+    pt = 0x1234567890abcdef1234567890abcdef % p
+    outer_int = [pow(pt, npr * r, p) for r in range(n_rows)]
+    outer = O.to_mont(f, outer_int)
+    comm = c["comm"].reshape(n_rows, nc, -1)
+    combined = np.zeros((nc, comm.shape[2]), np.uint64)
+    for r in range(n_rows):
+        t = np.repeat(outer[r:r + 1], nc, axis=0)
+        combined = O.field_op(f, "add", combined, O.field_op(f, "mul", np.ascontiguousarray(comm[r]), t))
+    back = O.ifft_oi(f, combined)
+    assert not back[npr:].any()                       # "high coefficients zero" (:226-231)
+    want = O.collapse(f, c["coeffs"], outer, n_rows, npr)
+    assert (back[:npr] == want).all()
+    # and the combination itself against big-int arithmetic on the first coefficients (collapse_columns' definition)
+    head = [sum(O.from_mont(f, x[r * npr + i:r * npr + i + 1])[0] * outer_int[r] for r in range(n_rows)) % p for i in range(8)]
+    assert O.from_mont(f, want[:8]) == head
