@@ -434,7 +434,7 @@ int encode_rows_from_host(lcpc_b200_enc *enc, const void *src, size_t len, uint3
   const size_t B = field_bytes(enc->field), N = B / 4;
   const size_t n_per_row = enc->n_per_row, padded = n_rows * n_per_row;
   const size_t row_bytes = n_per_row * B;
-  size_t n_chunks = std::min<size_t>(enc->kind == LCPC_B200_ENC_LIGERO ? 16 : 4, n_rows);
+  size_t n_chunks = std::min<size_t>(enc->kind == LCPC_B200_ENC_LIGERO ? 15 : 4, n_rows);  // + one short tail chunk, below
   while (n_chunks > 1 && (n_rows / n_chunks) * row_bytes < ((size_t)4 << 20)) n_chunks--;
   if (enc->kind == LCPC_B200_ENC_LIGERO) {
     // a row-chunk is one launch per transform pass, n_cols / 1024 CTAs per row: chunks of fewer rows than about two
@@ -456,8 +456,18 @@ int encode_rows_from_host(lcpc_b200_enc *enc, const void *src, size_t len, uint3
     CU(ctx, cudaEventRecord(ctx->begin_ev, st));  // earlier readers of d_coeffs on the engine stream
     CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->begin_ev, 0));
   }
+  // What is left to do once the last byte has crossed PCIe is pure latency on top of the copy: the last chunk is
+  // therefore a short one (a quarter of the others, H2D_TAIL_DIV), cut off the chunk before it -- its launches are
+  // small, but nothing runs beside them anyway
+  size_t tail_rows = 0;
+  if (enc->kind == LCPC_B200_ENC_LIGERO && n_chunks >= 2 && n_chunks < (size_t)lcpc_b200_ctx::MAX_CHUNKS) {
+    const long div = tunable("H2D_TAIL_DIV", 4);
+    if (div > 1 && n_rows / n_chunks >= 2 * (size_t)div) tail_rows = (n_rows / n_chunks) / (size_t)div, n_chunks += 1;
+  }
+  const size_t body_rows = n_rows - tail_rows, body_chunks = tail_rows ? n_chunks - 1 : n_chunks;
   for (size_t k = 0; k < n_chunks; k++) {
-    const size_t r0 = k * n_rows / n_chunks, r1 = (k + 1) * n_rows / n_chunks;
+    const size_t r0 = k < body_chunks ? k * body_rows / body_chunks : body_rows;
+    const size_t r1 = k < body_chunks ? (k + 1) * body_rows / body_chunks : n_rows;
     const size_t e0 = r0 * n_per_row, e1 = std::min(r1 * n_per_row, len);
     if (e1 > e0)
       CU(ctx, cudaMemcpyAsync((uint8_t *)d_coeffs + e0 * B, (const uint8_t *)src + e0 * B, (e1 - e0) * B,

@@ -25,6 +25,8 @@ def main():
     ap.add_argument("workload", choices=["ligero", "brakedown"])
     ap.add_argument("--lgl", type=int, default=24)
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--rows", type=int, default=0,
+                    help="commit only this many rows under the 2^lgl encoding (the share of one rank of a sharded commit)")
     ap.add_argument("knobs", nargs="*")
     args = ap.parse_args()
     import torch
@@ -38,6 +40,8 @@ def main():
     n = 1 << args.lgl
     ctx = P.Context(0)
     enc = P.LigeroEncoding(field, n, ctx=ctx) if args.workload == "ligero" else P.SdigEncoding(field, n, seed=0, ctx=ctx)
+    if args.rows:
+        n = args.rows * enc.n_per_row
     x = B.synthetic_coeffs(field, n, seed=0)
     dev = torch.from_numpy(x.view(np.int64)).cuda()
     names, values = [], []
