@@ -141,7 +141,9 @@ int expander_assemble(ExpanderCode *c, size_t t, std::string *err) {
   for (auto &m : c->mats) c->nnz += m.nnz;
   // innermost levels: grow the window outwards from the base code while it fits the shared-memory budget
   {
-    const size_t cap_elems = FUSED_SMEM_BYTES / field_bytes(c->field);
+    // FUSED_SMEM_KB: the shared-memory budget of the fused window (A/B knob, read when the code is assembled)
+    const size_t fused_bytes = (size_t)std::min<long>(200, std::max<long>(8, tunable("FUSED_SMEM_KB", (long)(FUSED_SMEM_BYTES >> 10)))) << 10;
+    const size_t cap_elems = fused_bytes / field_bytes(c->field);
     const size_t q = t;  // index of the Reed-Solomon op: ops = pre_0..pre_{t-1}, RS, post_{t-1}..post_0
     size_t lo = q, hi = q;
     size_t wlo = c->ops[q].out_off, wend = c->ops[q].out_off + c->ops[q].out_len;
@@ -851,7 +853,7 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
       bool &attr_set = attr_set_dev[dev_id & 63];
       if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(fused_levels_kernel<FID>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)FUSED_SMEM_BYTES);
+                                             200 << 10);
         if (e != cudaSuccess) return e;
         attr_set = true;
       }
