@@ -82,6 +82,10 @@ struct lcpc_b200_commit {
   uint8_t *d_hashes = nullptr;
   void *d_hash_scratch = nullptr;
   void *d_enc_scratch = nullptr;
+  // Brakedown, device-resident route: the codewords are left in the encoder's work buffer (d_enc_scratch,
+  // column-major W[position][row]) -- column hashing and column openings read columns, which are contiguous there --
+  // and the row-major d_comm is only made when somebody asks for it (ensure_comm)
+  bool comm_in_w = false;
   // prove-side staging
   uint32_t *d_tensor = nullptr, *d_poly = nullptr, *d_key = nullptr, *d_repr = nullptr;
   void *h_poly = nullptr;  // page-locked landing buffer for collapse results (pageable destinations copy from it)
@@ -664,6 +668,17 @@ static int commit_alloc(lcpc_b200_enc *enc, size_t len, lcpc_b200_commit **out) 
   return LCPC_B200_OK;
 }
 
+// make c->d_comm (row-major) valid; enqueue only
+static int ensure_comm(lcpc_b200_commit *c) {
+  if (!c->comm_in_w) return LCPC_B200_OK;
+  lcpc_b200_ctx *ctx = c->enc->ctx;
+  cudaError_t ce = expander_untranspose(c->enc->code, c->d_enc_scratch, c->d_comm, c->n_cols, c->n_rows, ctx->stream);
+  ctx->launches += 1;
+  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "comm from the work buffer");
+  c->comm_in_w = false;
+  return LCPC_B200_OK;
+}
+
 // enqueue the whole commit pipeline; src is host or device memory holding `len` elements
 static int commit_run(lcpc_b200_commit *c, const void *src, size_t len, cudaMemcpyKind kind,
                       const HostOut *host_out = nullptr) {
@@ -678,6 +693,7 @@ static int commit_run(lcpc_b200_commit *c, const void *src, size_t len, cudaMemc
   uint64_t l0 = ctx->launches;
   HashTrail trail{c->d_hashes, c->d_hash_scratch, 0, leaf_chunk_count(enc->field, c->n_rows), 0};
   size_t early_cols = 0;  // leading columns whose leaf chunks were hashed on the side stream already
+  c->comm_in_w = false;
   if (kind == cudaMemcpyHostToDevice && c->n_rows > 1) {
     if (int rc = encode_rows_from_host(enc, src, len, c->d_coeffs, c->d_comm, c->n_rows, c->d_enc_scratch, c->ev[1], nullptr,
                                        &trail, host_out))
@@ -745,11 +761,14 @@ static int commit_run(lcpc_b200_commit *c, const void *src, size_t len, cudaMemc
       ctx->launches += 1, trail.launches += 1;
       early_cols = c->n_per_row;
     }
+    // SDIG_LAZY_COMM (default on): no final transpose; the columns are hashed (and later opened) from the work buffer
+    const bool lazy = !host_out && early_cols == 0 && tunable("SDIG_LAZY_COMM", 1) != 0;
     int nl = 0;
-    cudaError_t ce = expander_encode_rows(enc->code, (const uint32_t *)src, c->n_per_row, c->n_per_row, c->d_comm, c->n_cols,
-                                          c->n_rows, c->d_enc_scratch, st, &nl, nullptr, c->d_coeffs, c->n_per_row, len);
+    cudaError_t ce = expander_encode_rows(enc->code, (const uint32_t *)src, c->n_per_row, c->n_per_row, lazy ? nullptr : c->d_comm,
+                                          c->n_cols, c->n_rows, c->d_enc_scratch, st, &nl, nullptr, c->d_coeffs, c->n_per_row, len);
     ctx->launches += nl;
     if (ce != cudaSuccess) return cuda_fail(ctx, ce, "encode");
+    c->comm_in_w = lazy;
   } else {
     // pad + copy (lcpc-2d/src/lib.rs:636-645): coeffs = coeffs_in || zeros
     CU(ctx, cudaMemcpyAsync(c->d_coeffs, src, len * B, kind, st));
@@ -764,9 +783,14 @@ static int commit_run(lcpc_b200_commit *c, const void *src, size_t len, cudaMemc
   if (c->np2 > c->n_cols) CU(ctx, cudaMemsetAsync(c->d_hashes + c->n_cols * 32, 0, (c->np2 - c->n_cols) * 32, st));
   // column leaves (:706-745): whatever chunks did not already trail the encode, then the per-column chunk merge
   int nl = 0;
-  cudaError_t ce = launch_leaf_chunks_range(enc->field, c->d_comm + early_cols * (B / 4), c->n_rows, c->n_cols - early_cols, c->n_cols,
-                                            c->d_hashes, c->d_hash_scratch, trail.next_chunk, trail.n_chunks - trail.next_chunk,
-                                            c->n_cols, early_cols, st);
+  cudaError_t ce =
+      c->comm_in_w
+          ? launch_leaf_chunks_range(enc->field, (const uint32_t *)c->d_enc_scratch, c->n_rows, c->n_cols, /*row_stride=*/1, c->d_hashes,
+                                     c->d_hash_scratch, trail.next_chunk, trail.n_chunks - trail.next_chunk, c->n_cols, 0, st,
+                                     ~(size_t)0, /*col_stride=*/c->n_rows)
+          : launch_leaf_chunks_range(enc->field, c->d_comm + early_cols * (B / 4), c->n_rows, c->n_cols - early_cols, c->n_cols,
+                                     c->d_hashes, c->d_hash_scratch, trail.next_chunk, trail.n_chunks - trail.next_chunk,
+                                     c->n_cols, early_cols, st);
   if (early_cols) CU(ctx, cudaStreamWaitEvent(st, ctx->side_done, 0));
   if (ce == cudaSuccess) ce = launch_leaf_merge(enc->field, c->n_rows, c->n_cols, c->d_hashes, c->d_hash_scratch, st, &nl);
   nl += 1;
@@ -904,7 +928,10 @@ int lcpc_b200_commit_download(lcpc_b200_commit *c, uint64_t *comm, uint64_t *coe
   std::lock_guard<std::mutex> g(ctx->mu);
   if (int rc = bind_device(ctx)) return rc;
   const size_t B = field_bytes(c->enc->field);
-  if (comm) CU(ctx, cudaMemcpyAsync(comm, c->d_comm, c->n_rows * c->n_cols * B, cudaMemcpyDeviceToHost, ctx->stream));
+  if (comm) {
+    if (int rc = ensure_comm(c)) return rc;
+    CU(ctx, cudaMemcpyAsync(comm, c->d_comm, c->n_rows * c->n_cols * B, cudaMemcpyDeviceToHost, ctx->stream));
+  }
   if (coeffs) CU(ctx, cudaMemcpyAsync(coeffs, c->d_coeffs, c->n_rows * c->n_per_row * B, cudaMemcpyDeviceToHost, ctx->stream));
   if (hashes) CU(ctx, cudaMemcpyAsync(hashes, c->d_hashes, (2 * c->np2 - 1) * 32, cudaMemcpyDeviceToHost, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -924,7 +951,13 @@ int lcpc_b200_commit_phase_times(lcpc_b200_commit *c, float ms[4], int launches[
 
 int lcpc_b200_commit_device_ptrs(lcpc_b200_commit *c, uint64_t **d_comm, uint64_t **d_coeffs, uint8_t **d_hashes) {
   if (!c) return LCPC_B200_ERR_BAD_ARG;
-  if (d_comm) *d_comm = (uint64_t *)c->d_comm;
+  if (d_comm) {
+    lcpc_b200_ctx *ctx = c->enc->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (int rc = bind_device(ctx)) return rc;
+    if (int rc = ensure_comm(c)) return rc;
+    *d_comm = (uint64_t *)c->d_comm;
+  }
   if (d_coeffs) *d_coeffs = (uint64_t *)c->d_coeffs;
   if (d_hashes) *d_hashes = c->d_hashes;
   return LCPC_B200_OK;
@@ -1099,8 +1132,11 @@ static int open_columns_locked(lcpc_b200_commit *c, const uint64_t *cols, size_t
   if (int rc = ensure_scratch(ctx, total)) return rc;
   uint8_t *base = (uint8_t *)ctx->scratch;
   CU(ctx, cudaMemcpyAsync(base, cols, n * 8, cudaMemcpyHostToDevice, ctx->stream));
-  cudaError_t ce = launch_gather_columns(field, c->d_comm, c->n_rows, c->n_cols, (const uint64_t *)base, n,
-                                         (uint32_t *)(base + off_vals), ctx->stream);
+  // open_column reads whole columns: contiguous in the work buffer when the codewords were left there
+  cudaError_t ce = c->comm_in_w ? launch_gather_columns(field, (const uint32_t *)c->d_enc_scratch, c->n_rows, 1, (const uint64_t *)base, n,
+                                                        (uint32_t *)(base + off_vals), ctx->stream, c->n_rows)
+                                : launch_gather_columns(field, c->d_comm, c->n_rows, c->n_cols, (const uint64_t *)base, n,
+                                                        (uint32_t *)(base + off_vals), ctx->stream);
   if (ce == cudaSuccess && path_len)
     ce = launch_gather_paths(c->d_hashes, c->np2, (const uint64_t *)base, n, path_len, base + off_paths, ctx->stream);
   ctx->launches += path_len ? 2 : 1;

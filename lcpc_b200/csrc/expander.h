@@ -42,4 +42,10 @@ cudaError_t expander_encode_rows(const ExpanderCode *code, const uint32_t *src, 
                                  int *n_launches, const Scatter *scatter = nullptr, uint32_t *copy_dst = nullptr,
                                  size_t copy_stride = 0, size_t src_total = ~(size_t)0, const SideLane *side = nullptr);
 
+// dst == nullptr in expander_encode_rows (no scatter): the codewords stay in the work buffer, column-major
+// (`scratch` = W[n_cols][n_rows], element (row r, position j) at (j * n_rows + r)); this produces the row-major matrix
+// from it on demand
+cudaError_t expander_untranspose(const ExpanderCode *code, const void *scratch, uint32_t *dst, size_t dst_stride, size_t n_rows,
+                                 cudaStream_t stream);
+
 }  // namespace lcpc

@@ -66,7 +66,9 @@ cudaError_t launch_leaf_chunks(int field, const uint32_t *comm, size_t n_rows, s
 // the padding of a short last row)
 cudaError_t launch_leaf_chunks_range(int field, const uint32_t *comm, size_t n_rows, size_t n_cols, size_t row_stride,
                                      uint8_t *leaves, void *scratch, unsigned k_first, unsigned k_count, size_t total_cols,
-                                     size_t col0, cudaStream_t stream, size_t src_total = ~(size_t)0);
+                                     size_t col0, cudaStream_t stream, size_t src_total = ~(size_t)0, size_t col_stride = 1);
+// (col_stride: elements between consecutive columns -- 1 for a row-major matrix; a column-major matrix, like the
+// expander's work buffer W[position][row], is row_stride = 1, col_stride = n_rows: every column is contiguous)
 cudaError_t launch_leaf_merge(int field, size_t n_rows, size_t n_cols, uint8_t *leaves, void *scratch, cudaStream_t stream,
                               int *n_launches);
 // hashes = [leaves(np2) | layer 1 | ... | root]; leaves given, upper layers computed
@@ -96,7 +98,8 @@ cudaError_t launch_expand_tensor(int field, const uint32_t *d_key, uint64_t stre
 
 // ---- open_column gather (lcpc-2d/src/lib.rs:802-808): out[i][r] = comm[r][cols[i]] ----
 cudaError_t launch_gather_columns(int field, const uint32_t *comm, size_t n_rows, size_t row_stride,
-                                  const uint64_t *cols, size_t n_open, uint32_t *out, cudaStream_t stream);
+                                  const uint64_t *cols, size_t n_open, uint32_t *out, cudaStream_t stream,
+                                  size_t col_stride = 1);
 
 // Merkle paths (lcpc-2d/src/lib.rs:811-821): out[i][l] = sibling of column cols[i]'s ancestor on layer l
 cudaError_t launch_gather_paths(const uint8_t *hashes, size_t np2, const uint64_t *cols, size_t n_open,

@@ -213,23 +213,24 @@ cudaError_t launch_expand_tensor(int field, const uint32_t *d_key, uint64_t stre
 // out[i * n_rows + r] = comm[r * row_stride + cols[i]]
 __global__ void gather_columns_kernel(const uint32_t *__restrict__ comm, size_t n_rows, size_t row_stride,
                                       const uint64_t *__restrict__ cols, size_t n_open, uint32_t *__restrict__ out,
-                                      int n_limbs) {
+                                      int n_limbs, size_t col_stride) {
   const size_t total = n_open * n_rows * (size_t)n_limbs;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const size_t l = idx % n_limbs, e = idx / n_limbs;
     const size_t r = e % n_rows, i = e / n_rows;
-    out[idx] = comm[(r * row_stride + cols[i]) * n_limbs + l];
+    out[idx] = comm[(r * row_stride + cols[i] * col_stride) * n_limbs + l];
   }
 }
 
 cudaError_t launch_gather_columns(int field, const uint32_t *comm, size_t n_rows, size_t row_stride,
-                                  const uint64_t *cols, size_t n_open, uint32_t *out, cudaStream_t stream) {
+                                  const uint64_t *cols, size_t n_open, uint32_t *out, cudaStream_t stream,
+                                  size_t col_stride) {
   int nl = field_limbs32(field);
   if (nl < 0) return cudaErrorInvalidValue;
   size_t total = n_open * n_rows * (size_t)nl;
   if (total == 0) return cudaSuccess;
   unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
-  gather_columns_kernel<<<grid, 256, 0, stream>>>(comm, n_rows, row_stride, cols, n_open, out, nl);
+  gather_columns_kernel<<<grid, 256, 0, stream>>>(comm, n_rows, row_stride, cols, n_open, out, nl, col_stride);
   return cudaGetLastError();
 }
 

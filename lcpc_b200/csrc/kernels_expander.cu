@@ -964,8 +964,11 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
-  // W -> row-major codewords (or per-column-block matrices); positions [0, n_in) are skipped if they already left
-  {
+  // W -> row-major codewords (or per-column-block matrices); positions [0, n_in) are skipped if they already left.
+  // dst == nullptr: the caller keeps the codewords in the work buffer (column-major: every column contiguous, which
+  // is what column hashing and column openings want) and calls expander_untranspose only if somebody asks for the
+  // row-major matrix
+  if (dst) {
     const size_t pos0 = early ? c->n_in : 0, n_pos = c->n_cols - pos0;
     dim3 grid((unsigned)((n_rows + TT - 1) / TT), (unsigned)((n_pos + TT - 1) / TT));
     Scatter sc;
@@ -981,6 +984,30 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
   }
   if (n_launches) *n_launches = launches;
   return cudaGetLastError();
+}
+
+template <int N>
+static cudaError_t untranspose_impl(const ExpanderCode *c, const void *scratch, uint32_t *dst, size_t dst_stride, size_t n_rows,
+                                    cudaStream_t st) {
+  const uint32_t *W = (const uint32_t *)scratch;
+  dim3 grid((unsigned)((n_rows + TT - 1) / TT), (unsigned)((c->n_cols + TT - 1) / TT));
+  Scatter none;
+  none.n_blocks = 0;
+  transpose_kernel<N><<<grid, 256, 0, st>>>(W, n_rows, dst, dst_stride, c->n_cols, n_rows, none, nullptr, 0, ~(size_t)0, 0);
+  return cudaGetLastError();
+}
+
+// the work buffer of the last encode (W[position][row]) -> row-major codewords dst[row][position]
+cudaError_t expander_untranspose(const ExpanderCode *c, const void *scratch, uint32_t *dst, size_t dst_stride, size_t n_rows,
+                                 cudaStream_t st) {
+  if (!scratch || !dst || n_rows == 0) return cudaErrorInvalidValue;
+  switch (c->field) {
+    case FT63: return untranspose_impl<2>(c, scratch, dst, dst_stride, n_rows, st);
+    case FT127: return untranspose_impl<4>(c, scratch, dst, dst_stride, n_rows, st);
+    case FT191: return untranspose_impl<6>(c, scratch, dst, dst_stride, n_rows, st);
+    case FT255: return untranspose_impl<8>(c, scratch, dst, dst_stride, n_rows, st);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 cudaError_t expander_encode_rows(const ExpanderCode *c, const uint32_t *src, size_t src_stride, size_t valid,

@@ -44,7 +44,7 @@ template <int FID, bool SHORT_SOURCE = false>
 __global__ void __launch_bounds__(HASH_THREADS)
 leaf_chunk_kernel(const uint32_t *__restrict__ comm, size_t n_rows, size_t n_cols, size_t row_stride,
                   uint32_t *__restrict__ out, unsigned n_chunks, unsigned k_first, size_t out_cols, size_t col0,
-                  size_t src_total) {
+                  size_t src_total, size_t col_stride) {
   using F = Field<FID>;
   constexpr int N = F::N;
   constexpr int B = F::BYTES;
@@ -60,7 +60,7 @@ leaf_chunk_kernel(const uint32_t *__restrict__ comm, size_t n_rows, size_t n_col
   const unsigned n_blocks = (unsigned)((chunk_len + 63) / 64);
   uint32_t cv[8];
   b3::set_iv(cv);
-  const uint32_t *cp = comm + col * N;
+  const uint32_t *cp = comm + col * col_stride * N;  // element (row r, column c) at (r * row_stride + c * col_stride)
   // rows of this column that exist in the source: all of them, unless the source ends inside the last row (element
   // (r, c) exists iff r * row_stride + c < src_total; beyond that the commit's zero padding is hashed)
   // (compiled in only for sources that can end early: the whole-commit path pays nothing for it)
@@ -99,7 +99,7 @@ template <int FID>
 __global__ void __launch_bounds__(HASH_THREADS)
 leaf_chunk_kernel_generic(const uint32_t *__restrict__ comm, size_t n_rows, size_t n_cols, size_t row_stride,
                           uint32_t *__restrict__ out, unsigned n_chunks, unsigned k_first, size_t out_cols, size_t col0,
-                          size_t src_total) {
+                          size_t src_total, size_t col_stride) {
   using F = Field<FID>;
   constexpr int N = F::N;
   constexpr int B = F::BYTES;
@@ -112,7 +112,7 @@ leaf_chunk_kernel_generic(const uint32_t *__restrict__ comm, size_t n_rows, size
   const unsigned n_blocks = (unsigned)((chunk_len + 63) / 64);
   uint32_t cv[8];
   b3::set_iv(cv);
-  const uint32_t *cp = comm + col * N;
+  const uint32_t *cp = comm + col * col_stride * N;  // element (row r, column c) at (r * row_stride + c * col_stride)
   size_t cached_row = (size_t)-1;
   uint32_t canon[N];
   for (unsigned b = 0; b < n_blocks; b++) {
@@ -227,7 +227,7 @@ unsigned leaf_chunk_count(int field, size_t n_rows) { return leaf_chunks(field, 
 // sparse products have produced the rest.
 cudaError_t launch_leaf_chunks_range(int field, const uint32_t *comm, size_t n_rows, size_t n_cols, size_t row_stride,
                                      uint8_t *leaves, void *scratch, unsigned k_first, unsigned k_count, size_t total_cols,
-                                     size_t col0, cudaStream_t stream, size_t src_total) {
+                                     size_t col0, cudaStream_t stream, size_t src_total, size_t col_stride) {
   if (n_cols == 0 || k_count == 0) return cudaSuccess;
   const unsigned n_chunks = leaf_chunks(field, n_rows);
   if (n_chunks > 65535u || k_first + k_count > n_chunks || col0 + n_cols > total_cols) return cudaErrorInvalidValue;
@@ -239,17 +239,17 @@ cudaError_t launch_leaf_chunks_range(int field, const uint32_t *comm, size_t n_r
   const size_t pad = (total_cols != n_cols) ? (size_t)std::min<long>(47, std::max<long>(0, tunable("LEAF_SMEM_PAD_KB", 0))) << 10 : 0;
   switch (field) {
     case FT63:
-      if (src_total == ~(size_t)0) leaf_chunk_kernel<FT63, false><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total);
-      else leaf_chunk_kernel<FT63, true><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total);
+      if (src_total == ~(size_t)0) leaf_chunk_kernel<FT63, false><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total, col_stride);
+      else leaf_chunk_kernel<FT63, true><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total, col_stride);
       break;
     case FT127:
-      if (src_total == ~(size_t)0) leaf_chunk_kernel<FT127, false><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total);
-      else leaf_chunk_kernel<FT127, true><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total);
+      if (src_total == ~(size_t)0) leaf_chunk_kernel<FT127, false><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total, col_stride);
+      else leaf_chunk_kernel<FT127, true><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total, col_stride);
       break;
-    case FT191: leaf_chunk_kernel_generic<FT191><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total); break;
+    case FT191: leaf_chunk_kernel_generic<FT191><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total, col_stride); break;
     case FT255:
-      if (src_total == ~(size_t)0) leaf_chunk_kernel<FT255, false><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total);
-      else leaf_chunk_kernel<FT255, true><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total);
+      if (src_total == ~(size_t)0) leaf_chunk_kernel<FT255, false><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total, col_stride);
+      else leaf_chunk_kernel<FT255, true><<<grid, HASH_THREADS, pad, stream>>>(comm, n_rows, n_cols, row_stride, out, n_chunks, k_first, total_cols, col0, src_total, col_stride);
       break;
     default: return cudaErrorInvalidValue;
   }
@@ -258,7 +258,7 @@ cudaError_t launch_leaf_chunks_range(int field, const uint32_t *comm, size_t n_r
 
 cudaError_t launch_leaf_chunks(int field, const uint32_t *comm, size_t n_rows, size_t n_cols, size_t row_stride,
                                uint8_t *leaves, void *scratch, unsigned k_first, unsigned k_count, cudaStream_t stream) {
-  return launch_leaf_chunks_range(field, comm, n_rows, n_cols, row_stride, leaves, scratch, k_first, k_count, n_cols, 0, stream, ~(size_t)0);
+  return launch_leaf_chunks_range(field, comm, n_rows, n_cols, row_stride, leaves, scratch, k_first, k_count, n_cols, 0, stream, ~(size_t)0, 1);
 }
 
 // BLAKE3 tree over the chunk chaining values of every column (no-op for single-chunk leaves)

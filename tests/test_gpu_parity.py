@@ -650,3 +650,42 @@ def test_device_matgen_headline_shape_setup_time():
     for got, want in zip(pre + post, hpre + hpost):
         assert (got["idxs"] == want["idxs"]).all() and (got["data"] == want["data"]).all()
     enc2.close()
+
+
+@pytest.mark.parametrize("field,length,seed", [(P.FT127, 1 << 15, 0), (P.FT255, (1 << 13) - 77, 1), (P.FT63, 6000, 2), (P.FT191, 3000, 3)])
+def test_brakedown_device_commit_keeps_codewords_column_major_until_asked(field, length, seed):
+    """Device-resident Brakedown commit: the codewords stay in the encoder's work buffer (no final transpose), leaves
+    are hashed and columns opened from there; the row-major comm appears when it is downloaded -- all equal to the
+    oracle, before and after, and with the lazy route switched off."""
+    import torch
+    from lcpc_b200 import _cabi
+    oenc = O.Encoding.sdig(field, length, seed=seed)
+    x = O.random_elems(field, length, seed=seed + 70)
+    oc = oenc.commit(x)
+    dev = torch.from_numpy(x.view(np.int64)).cuda()
+    for lazy in (1, 0):
+        _cabi.lib().lcpc_b200_set_tunable(b"SDIG_LAZY_COMM", lazy)
+        try:
+            enc = P.SdigEncoding(field, length, seed=seed)
+            c = P.LcCommit.commit_device(dev.data_ptr(), length, enc)
+            assert c.get_root().root == oc["root"]
+            comm = oc["comm"].reshape(c.n_rows, c.n_cols, -1)
+            cols = np.array([0, c.n_cols - 1, c.n_per_row - 1, c.n_per_row, c.n_cols // 2], np.uint64)
+            vals, paths = c.open_columns(cols)          # before anything asked for the row-major matrix
+            for i, col in enumerate(cols):
+                assert (vals[i] == comm[:, int(col)]).all()
+                assert O.verify_column_path(field, vals[i], paths[i], int(col), oc["root"])
+            assert (c.hashes == oc["hashes"]).all()
+            assert (c.comm == oc["comm"]).all() and (c.coeffs == oc["coeffs"]).all()   # materialised on demand
+            vals2, _ = c.open_columns(cols)             # and afterwards
+            assert (vals2 == vals).all()
+            c.rerun_device(dev.data_ptr(), length)      # a second commit into the same object: lazy again
+            vals3, _ = c.open_columns(cols)
+            assert (vals3 == vals).all() and c.get_root().root == oc["root"]
+            outer = O.random_elems(field, c.n_rows, seed=5)
+            inner = O.random_elems(field, c.n_per_row, seed=6)
+            proof = c.prove(outer, enc, P.Transcript(b"lazy comm"))
+            ev = proof.verify(c.get_root(), outer, inner, enc, P.Transcript(b"lazy comm"))
+            assert (ev == O.dot(field, inner, O.collapse(field, oc["coeffs"], outer, c.n_rows, c.n_per_row))).all()
+        finally:
+            _cabi.lib().lcpc_b200_set_tunable(b"SDIG_LAZY_COMM", 1)
