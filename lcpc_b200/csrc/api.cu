@@ -463,15 +463,38 @@ int encode_rows_from_host(lcpc_b200_enc *enc, const void *src, size_t len, uint3
   // What is left to do once the last byte has crossed PCIe is pure latency on top of the copy: the last chunk is
   // therefore a short one (a quarter of the others, H2D_TAIL_DIV), cut off the chunk before it -- its launches are
   // small, but nothing runs beside them anyway
+  size_t cuts[lcpc_b200_ctx::MAX_CHUNKS + 1];  // row-chunk k = rows [cuts[k], cuts[k + 1])
   size_t tail_rows = 0;
   if (enc->kind == LCPC_B200_ENC_LIGERO && n_chunks >= 2 && n_chunks < (size_t)lcpc_b200_ctx::MAX_CHUNKS) {
     const long div = tunable("H2D_TAIL_DIV", 4);
     if (div > 1 && n_rows / n_chunks >= 2 * (size_t)div) tail_rows = (n_rows / n_chunks) / (size_t)div, n_chunks += 1;
   }
-  const size_t body_rows = n_rows - tail_rows, body_chunks = tail_rows ? n_chunks - 1 : n_chunks;
+  {
+    const size_t body_rows = n_rows - tail_rows, body_chunks = tail_rows ? n_chunks - 1 : n_chunks;
+    for (size_t k = 0; k <= body_chunks; k++) cuts[k] = k * body_rows / body_chunks;
+    cuts[n_chunks] = n_rows;
+  }
+  // Expander code with trailing leaf hashing: all leaf chunks but the last one read rows [0, boundary) only (BLAKE3
+  // chunks are 1024 bytes: 62 Ft127 rows after the 32-byte prefix), so the tail is cut exactly there -- those chunks
+  // (16 of the 19 compressions per column at 72 rows) are hashed while the tail rows cross PCIe -- and the chunk
+  // before the tail is as short as the tail, so that its chain and that hashing fit under the tail's copy
+  // (H2D_TAIL_SDIG=0: the equal chunks of before).  Measured at 2^24/Ft127: see DESIGN.md section 5.
+  if (enc->kind == LCPC_B200_ENC_SDIG && trail && trail->n_chunks >= 2 && n_chunks >= 2 && tunable("H2D_TAIL_SDIG", 1) != 0) {
+    const size_t boundary = leaf_chunk_rows_end(enc->field, n_rows, trail->n_chunks - 2);
+    const size_t tail = n_rows - boundary;
+    if (boundary >= 16 && tail >= 1 && tail * 3 <= n_rows) {
+      const size_t pre = std::min(tail, boundary / 4);
+      const size_t big_rows = boundary - pre;
+      size_t big = std::min<size_t>(3, std::max<size_t>(1, big_rows / (size_t)std::max<long>(1, tunable("H2D_MIN_CHUNK_ROWS_SDIG", 16))));
+      n_chunks = 0;
+      for (size_t k = 0; k < big; k++) cuts[n_chunks++] = k * big_rows / big;
+      cuts[n_chunks++] = big_rows;
+      cuts[n_chunks++] = boundary;
+      cuts[n_chunks] = n_rows;
+    }
+  }
   for (size_t k = 0; k < n_chunks; k++) {
-    const size_t r0 = k < body_chunks ? k * body_rows / body_chunks : body_rows;
-    const size_t r1 = k < body_chunks ? (k + 1) * body_rows / body_chunks : n_rows;
+    const size_t r0 = cuts[k], r1 = cuts[k + 1];
     const size_t e0 = r0 * n_per_row, e1 = std::min(r1 * n_per_row, len);
     if (e1 > e0)
       CU(ctx, cudaMemcpyAsync((uint8_t *)d_coeffs + e0 * B, (const uint8_t *)src + e0 * B, (e1 - e0) * B,

@@ -689,3 +689,28 @@ def test_brakedown_device_commit_keeps_codewords_column_major_until_asked(field,
             assert (ev == O.dot(field, inner, O.collapse(field, oc["coeffs"], outer, c.n_rows, c.n_per_row))).all()
         finally:
             _cabi.lib().lcpc_b200_set_tunable(b"SDIG_LAZY_COMM", 1)
+
+
+@pytest.mark.parametrize("field,n_per_row,n_rows,short", [(P.FT255, 8200, 40, 0), (P.FT127, 16400, 72, 0), (P.FT127, 16400, 70, 333),
+                                                          (P.FT127, 9000, 130, 1)])
+def test_brakedown_host_commit_tail_chunk_at_the_leaf_boundary(field, n_per_row, n_rows, short):
+    """Host-route Brakedown commit with several row-chunks: the last chunk is cut where the last BLAKE3 chunk of the
+    leaf inputs starts, the earlier leaf chunks are hashed while it is still crossing PCIe.  Same LcCommit as the
+    oracle with the tail schedule on and off, also for a short last row."""
+    length = n_rows * n_per_row - short
+    enc = P.SdigEncoding.new_from_dims(field, n_per_row, seed=3)
+    oenc = O.Encoding.sdig_from_dims(field, n_per_row, seed=3)
+    x = O.random_elems(field, length, seed=n_rows)
+    oc = oenc.commit(x)
+    for tail in (1, 0):
+        _cabi.lib().lcpc_b200_set_tunable(b"H2D_TAIL_SDIG", tail)
+        try:
+            c = P.LcCommit.commit(x, enc)
+            assert c.n_rows == n_rows
+            assert c.get_root().root == oc["root"]
+            assert (c.hashes == oc["hashes"]).all() and (c.comm == oc["comm"]).all() and (c.coeffs == oc["coeffs"]).all()
+            y = O.random_elems(field, length, seed=n_rows + 1)
+            c.rerun(y)
+            assert c.get_root().root == oenc.commit(y)["root"]
+        finally:
+            _cabi.lib().lcpc_b200_set_tunable(b"H2D_TAIL_SDIG", 1)
