@@ -85,7 +85,8 @@ struct lcpc_b200_commit {
   // Brakedown, device-resident route: the codewords are left in the encoder's work buffer (d_enc_scratch,
   // column-major W[position][row]) -- column hashing and column openings read columns, which are contiguous there --
   // and the row-major d_comm is only made when somebody asks for it (ensure_comm)
-  bool comm_in_w = false;
+  bool comm_in_w = false;    // Brakedown, device route: the codewords are in d_enc_scratch (column-major), d_comm is stale
+  bool coeffs_in_w = false;  // ... and so are the padded coefficient rows (the systematic positions), d_coeffs is stale
   // prove-side staging
   uint32_t *d_tensor = nullptr, *d_poly = nullptr, *d_key = nullptr, *d_repr = nullptr;
   void *h_poly = nullptr;  // page-locked landing buffer for collapse results (pageable destinations copy from it)
@@ -438,7 +439,8 @@ int encode_rows_from_host(lcpc_b200_enc *enc, const void *src, size_t len, uint3
   const size_t B = field_bytes(enc->field), N = B / 4;
   const size_t n_per_row = enc->n_per_row, padded = n_rows * n_per_row;
   const size_t row_bytes = n_per_row * B;
-  size_t n_chunks = std::min<size_t>(enc->kind == LCPC_B200_ENC_LIGERO ? 15 : 4, n_rows);  // + one short tail chunk, below
+  size_t n_chunks = std::min<size_t>(enc->kind == LCPC_B200_ENC_LIGERO ? (size_t)std::min<long>(std::max<long>(tunable("H2D_MAX_CHUNKS", 15), 1), 15) : 4,
+                                     n_rows);  // + one short tail chunk, below
   while (n_chunks > 1 && (n_rows / n_chunks) * row_bytes < ((size_t)4 << 20)) n_chunks--;
   if (enc->kind == LCPC_B200_ENC_LIGERO) {
     // a row-chunk is one launch per transform pass, n_cols / 1024 CTAs per row: chunks of fewer rows than about two
@@ -470,8 +472,18 @@ int encode_rows_from_host(lcpc_b200_enc *enc, const void *src, size_t len, uint3
     if (div > 1 && n_rows / n_chunks >= 2 * (size_t)div) tail_rows = (n_rows / n_chunks) / (size_t)div, n_chunks += 1;
   }
   {
-    const size_t body_rows = n_rows - tail_rows, body_chunks = tail_rows ? n_chunks - 1 : n_chunks;
+    // ... and the chunk before it is twice the tail (H2D_PRE_TAIL): a full-size chunk's transform takes about half
+    // of its own copy time, i.e. it would still be running when the short tail has landed
+    size_t pre_rows = 0;
+    if (tail_rows && tunable("H2D_PRE_TAIL", 1) != 0 && tail_rows * std::max<size_t>(1, enc->n_cols >> 10) >= (size_t)std::max<long>(1, tunable("H2D_PRE_TAIL_MIN_CTAS", 512)) &&
+        n_chunks >= 4 && n_rows >= 8 * tail_rows) {
+      pre_rows = 2 * tail_rows;
+      if (n_chunks < (size_t)lcpc_b200_ctx::MAX_CHUNKS) n_chunks += 1;  // else one body chunk fewer
+    }
+    const size_t special = (tail_rows ? 1 : 0) + (pre_rows ? 1 : 0);
+    const size_t body_rows = n_rows - tail_rows - pre_rows, body_chunks = n_chunks - special;
     for (size_t k = 0; k <= body_chunks; k++) cuts[k] = k * body_rows / body_chunks;
+    if (pre_rows) cuts[body_chunks + 1] = body_rows + pre_rows;
     cuts[n_chunks] = n_rows;
   }
   // Expander code with trailing leaf hashing: all leaf chunks but the last one read rows [0, boundary) only (BLAKE3
@@ -702,6 +714,26 @@ static int ensure_comm(lcpc_b200_commit *c) {
   return LCPC_B200_OK;
 }
 
+// make c->d_coeffs (row-major) valid; enqueue only
+static int ensure_coeffs(lcpc_b200_commit *c) {
+  if (!c->coeffs_in_w) return LCPC_B200_OK;
+  lcpc_b200_ctx *ctx = c->enc->ctx;
+  cudaError_t ce = expander_untranspose(c->enc->code, c->d_enc_scratch, c->d_coeffs, c->n_per_row, c->n_rows, ctx->stream, c->n_per_row);
+  ctx->launches += 1;
+  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "coefficients from the work buffer");
+  c->coeffs_in_w = false;
+  return LCPC_B200_OK;
+}
+
+// collapse_columns over the commit's coefficients wherever they are
+static cudaError_t collapse_commit(lcpc_b200_commit *c, int *nl) {
+  lcpc_b200_ctx *ctx = c->enc->ctx;
+  if (c->coeffs_in_w)
+    return launch_collapse(c->enc->field, (const uint32_t *)c->d_enc_scratch, 1, c->d_tensor, c->d_poly, c->n_rows, c->n_per_row, nullptr,
+                           ctx->stream, nl, c->n_rows);
+  return launch_collapse(c->enc->field, c->d_coeffs, c->n_per_row, c->d_tensor, c->d_poly, c->n_rows, c->n_per_row, nullptr, ctx->stream, nl);
+}
+
 // enqueue the whole commit pipeline; src is host or device memory holding `len` elements
 static int commit_run(lcpc_b200_commit *c, const void *src, size_t len, cudaMemcpyKind kind,
                       const HostOut *host_out = nullptr) {
@@ -716,7 +748,9 @@ static int commit_run(lcpc_b200_commit *c, const void *src, size_t len, cudaMemc
   uint64_t l0 = ctx->launches;
   HashTrail trail{c->d_hashes, c->d_hash_scratch, 0, leaf_chunk_count(enc->field, c->n_rows), 0};
   size_t early_cols = 0;  // leading columns whose leaf chunks were hashed on the side stream already
-  c->comm_in_w = false;
+  if ((const void *)c->d_coeffs == src)  // re-commit of the commit's own coefficient rows: they have to be there
+    if (int rc = ensure_coeffs(c)) return rc;
+  c->comm_in_w = c->coeffs_in_w = false;
   if (kind == cudaMemcpyHostToDevice && c->n_rows > 1) {
     if (int rc = encode_rows_from_host(enc, src, len, c->d_coeffs, c->d_comm, c->n_rows, c->d_enc_scratch, c->ev[1], nullptr,
                                        &trail, host_out))
@@ -788,10 +822,11 @@ static int commit_run(lcpc_b200_commit *c, const void *src, size_t len, cudaMemc
     const bool lazy = !host_out && early_cols == 0 && tunable("SDIG_LAZY_COMM", 1) != 0;
     int nl = 0;
     cudaError_t ce = expander_encode_rows(enc->code, (const uint32_t *)src, c->n_per_row, c->n_per_row, lazy ? nullptr : c->d_comm,
-                                          c->n_cols, c->n_rows, c->d_enc_scratch, st, &nl, nullptr, c->d_coeffs, c->n_per_row, len);
+                                          c->n_cols, c->n_rows, c->d_enc_scratch, st, &nl, nullptr, lazy ? nullptr : c->d_coeffs, c->n_per_row,
+                                          len);
     ctx->launches += nl;
     if (ce != cudaSuccess) return cuda_fail(ctx, ce, "encode");
-    c->comm_in_w = lazy;
+    c->comm_in_w = c->coeffs_in_w = lazy;
   } else {
     // pad + copy (lcpc-2d/src/lib.rs:636-645): coeffs = coeffs_in || zeros
     CU(ctx, cudaMemcpyAsync(c->d_coeffs, src, len * B, kind, st));
@@ -955,7 +990,10 @@ int lcpc_b200_commit_download(lcpc_b200_commit *c, uint64_t *comm, uint64_t *coe
     if (int rc = ensure_comm(c)) return rc;
     CU(ctx, cudaMemcpyAsync(comm, c->d_comm, c->n_rows * c->n_cols * B, cudaMemcpyDeviceToHost, ctx->stream));
   }
-  if (coeffs) CU(ctx, cudaMemcpyAsync(coeffs, c->d_coeffs, c->n_rows * c->n_per_row * B, cudaMemcpyDeviceToHost, ctx->stream));
+  if (coeffs) {
+    if (int rc = ensure_coeffs(c)) return rc;
+    CU(ctx, cudaMemcpyAsync(coeffs, c->d_coeffs, c->n_rows * c->n_per_row * B, cudaMemcpyDeviceToHost, ctx->stream));
+  }
   if (hashes) CU(ctx, cudaMemcpyAsync(hashes, c->d_hashes, (2 * c->np2 - 1) * 32, cudaMemcpyDeviceToHost, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   return LCPC_B200_OK;
@@ -974,13 +1012,16 @@ int lcpc_b200_commit_phase_times(lcpc_b200_commit *c, float ms[4], int launches[
 
 int lcpc_b200_commit_device_ptrs(lcpc_b200_commit *c, uint64_t **d_comm, uint64_t **d_coeffs, uint8_t **d_hashes) {
   if (!c) return LCPC_B200_ERR_BAD_ARG;
-  if (d_comm) {
+  if (d_comm || d_coeffs) {
     lcpc_b200_ctx *ctx = c->enc->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
     if (int rc = bind_device(ctx)) return rc;
-    if (int rc = ensure_comm(c)) return rc;
-    *d_comm = (uint64_t *)c->d_comm;
+    if (d_comm)
+      if (int rc = ensure_comm(c)) return rc;
+    if (d_coeffs)
+      if (int rc = ensure_coeffs(c)) return rc;
   }
+  if (d_comm) *d_comm = (uint64_t *)c->d_comm;
   if (d_coeffs) *d_coeffs = (uint64_t *)c->d_coeffs;
   if (d_hashes) *d_hashes = c->d_hashes;
   return LCPC_B200_OK;
@@ -1027,8 +1068,7 @@ int lcpc_b200_commit_collapse(lcpc_b200_commit *c, const uint64_t *tensor, uint6
   const size_t B = field_bytes(field);
   CU(ctx, cudaMemcpyAsync(c->d_tensor, tensor, c->n_rows * B, cudaMemcpyHostToDevice, ctx->stream));
   int nl = 0;
-  cudaError_t ce = launch_collapse(field, c->d_coeffs, c->n_per_row, c->d_tensor, c->d_poly, c->n_rows, c->n_per_row,
-                                   nullptr, ctx->stream, &nl);
+  cudaError_t ce = collapse_commit(c, &nl);
   ctx->launches += nl;
   if (ce != cudaSuccess) return cuda_fail(ctx, ce, "collapse");
   return return_poly(c, poly);
@@ -1072,8 +1112,7 @@ int lcpc_b200_commit_degree_test(lcpc_b200_commit *c, const uint8_t key[32], uin
   const size_t B = field_bytes(field);
   if (int rc = expand_tensor_into(c, key)) return rc;
   int nl = 0;
-  cudaError_t ce = launch_collapse(field, c->d_coeffs, c->n_per_row, c->d_tensor, c->d_poly, c->n_rows, c->n_per_row,
-                                   nullptr, ctx->stream, &nl);
+  cudaError_t ce = collapse_commit(c, &nl);
   ctx->launches += nl;
   if (ce != cudaSuccess) return cuda_fail(ctx, ce, "collapse");
   if (tensor_out) CU(ctx, cudaMemcpyAsync(tensor_out, c->d_tensor, c->n_rows * B, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1266,8 +1305,7 @@ int lcpc_b200_commit_prove(lcpc_b200_commit *c, lcpc_b200_transcript *tr, const 
   // one collapse against the tensor in c->d_tensor: Montgomery limbs to `dst`, canonical bytes into the transcript
   auto collapse_and_absorb = [&](uint64_t *dst, const uint8_t *label, size_t label_len) -> int {
     int nl = 0;
-    cudaError_t ce = launch_collapse(field, c->d_coeffs, c->n_per_row, c->d_tensor, c->d_poly, c->n_rows, c->n_per_row,
-                                     nullptr, ctx->stream, &nl);
+    cudaError_t ce = collapse_commit(c, &nl);
     if (ce == cudaSuccess) ce = launch_field_op(field, 4, d_repr, c->d_poly, nullptr, c->n_per_row, ctx->stream);
     ctx->launches += nl + 1;
     if (ce != cudaSuccess) return cuda_fail(ctx, ce, "prove: collapse");

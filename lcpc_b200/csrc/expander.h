@@ -46,6 +46,6 @@ cudaError_t expander_encode_rows(const ExpanderCode *code, const uint32_t *src, 
 // (`scratch` = W[n_cols][n_rows], element (row r, position j) at (j * n_rows + r)); this produces the row-major matrix
 // from it on demand
 cudaError_t expander_untranspose(const ExpanderCode *code, const void *scratch, uint32_t *dst, size_t dst_stride, size_t n_rows,
-                                 cudaStream_t stream);
+                                 cudaStream_t stream, size_t n_pos = 0);
 
 }  // namespace lcpc

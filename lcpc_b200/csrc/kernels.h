@@ -89,7 +89,7 @@ cudaError_t launch_pack_column_blocks(int field, const uint32_t *src, size_t n_r
 size_t collapse_scratch_bytes(int field, size_t n_rows, size_t n_per_row);
 cudaError_t launch_collapse(int field, const uint32_t *coeffs, size_t row_stride, const uint32_t *tensor,
                             uint32_t *poly, size_t n_rows, size_t n_per_row, void *scratch, cudaStream_t stream,
-                            int *n_launches);
+                            int *n_launches, size_t col_stride = 1);  // element (r, c) at coeffs[r * row_stride + c * col_stride]
 
 // ---- challenge tensor (lcpc-2d/src/lib.rs:1026-1032): out[0..n) = n x F::random from ChaCha20Rng::from_seed(key)
 // with stream id `stream_id` (0 for from_seed); d_key: the 32-byte key as 8 little-endian words in device memory

@@ -39,7 +39,7 @@ __device__ __forceinline__ void ld_elem(uint32_t (&v)[N], const uint32_t *p) {
 
 template <int FID>
 __global__ void __launch_bounds__(COL_TILE *ROW_GROUPS)
-collapse_kernel(const uint32_t *__restrict__ coeffs, size_t row_stride, const uint32_t *__restrict__ tensor,
+collapse_kernel(const uint32_t *__restrict__ coeffs, size_t row_stride, size_t col_stride, const uint32_t *__restrict__ tensor,
                 uint32_t *__restrict__ poly, size_t n_rows, size_t n_per_row) {
   using F = Field<FID>;
   constexpr int N = F::N;
@@ -50,7 +50,7 @@ collapse_kernel(const uint32_t *__restrict__ coeffs, size_t row_stride, const ui
   if (col < n_per_row) {
     for (size_t r = grp; r < n_rows; r += ROW_GROUPS) {
       typename F::Elem a, t;
-      ld_elem<N>(a.v, coeffs + (r * row_stride + col) * N);
+      ld_elem<N>(a.v, coeffs + (r * row_stride + col * col_stride) * N);
       ld_elem<N>(t.v, tensor + r * N);
       F::mac_wide(wide, a, t);
     }
@@ -76,16 +76,16 @@ size_t collapse_scratch_bytes(int, size_t, size_t) { return 0; }
 
 cudaError_t launch_collapse(int field, const uint32_t *coeffs, size_t row_stride, const uint32_t *tensor,
                             uint32_t *poly, size_t n_rows, size_t n_per_row, void *, cudaStream_t stream,
-                            int *n_launches) {
+                            int *n_launches, size_t col_stride) {
   if (n_launches) *n_launches = 0;
   if (n_per_row == 0) return cudaSuccess;
   unsigned grid = (unsigned)((n_per_row + COL_TILE - 1) / COL_TILE);
   const int threads = COL_TILE * ROW_GROUPS;
   switch (field) {
-    case FT63: collapse_kernel<FT63><<<grid, threads, 0, stream>>>(coeffs, row_stride, tensor, poly, n_rows, n_per_row); break;
-    case FT127: collapse_kernel<FT127><<<grid, threads, 0, stream>>>(coeffs, row_stride, tensor, poly, n_rows, n_per_row); break;
-    case FT191: collapse_kernel<FT191><<<grid, threads, 0, stream>>>(coeffs, row_stride, tensor, poly, n_rows, n_per_row); break;
-    case FT255: collapse_kernel<FT255><<<grid, threads, 0, stream>>>(coeffs, row_stride, tensor, poly, n_rows, n_per_row); break;
+    case FT63: collapse_kernel<FT63><<<grid, threads, 0, stream>>>(coeffs, row_stride, col_stride, tensor, poly, n_rows, n_per_row); break;
+    case FT127: collapse_kernel<FT127><<<grid, threads, 0, stream>>>(coeffs, row_stride, col_stride, tensor, poly, n_rows, n_per_row); break;
+    case FT191: collapse_kernel<FT191><<<grid, threads, 0, stream>>>(coeffs, row_stride, col_stride, tensor, poly, n_rows, n_per_row); break;
+    case FT255: collapse_kernel<FT255><<<grid, threads, 0, stream>>>(coeffs, row_stride, col_stride, tensor, poly, n_rows, n_per_row); break;
     default: return cudaErrorInvalidValue;
   }
   cudaError_t e = cudaGetLastError();

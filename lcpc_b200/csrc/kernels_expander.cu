@@ -987,25 +987,27 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
 }
 
 template <int N>
-static cudaError_t untranspose_impl(const ExpanderCode *c, const void *scratch, uint32_t *dst, size_t dst_stride, size_t n_rows,
+static cudaError_t untranspose_impl(const void *scratch, uint32_t *dst, size_t dst_stride, size_t n_rows, size_t n_pos,
                                     cudaStream_t st) {
   const uint32_t *W = (const uint32_t *)scratch;
-  dim3 grid((unsigned)((n_rows + TT - 1) / TT), (unsigned)((c->n_cols + TT - 1) / TT));
+  dim3 grid((unsigned)((n_rows + TT - 1) / TT), (unsigned)((n_pos + TT - 1) / TT));
   Scatter none;
   none.n_blocks = 0;
-  transpose_kernel<N><<<grid, 256, 0, st>>>(W, n_rows, dst, dst_stride, c->n_cols, n_rows, none, nullptr, 0, ~(size_t)0, 0);
+  transpose_kernel<N><<<grid, 256, 0, st>>>(W, n_rows, dst, dst_stride, n_pos, n_rows, none, nullptr, 0, ~(size_t)0, 0);
   return cudaGetLastError();
 }
 
-// the work buffer of the last encode (W[position][row]) -> row-major codewords dst[row][position]
+// the work buffer of the last encode (W[position][row]) -> row-major dst[row][position] for positions [0, n_pos):
+// n_pos = n_cols gives the codewords, n_pos = n_in their systematic part, i.e. the (padded) coefficient rows
 cudaError_t expander_untranspose(const ExpanderCode *c, const void *scratch, uint32_t *dst, size_t dst_stride, size_t n_rows,
-                                 cudaStream_t st) {
-  if (!scratch || !dst || n_rows == 0) return cudaErrorInvalidValue;
+                                 cudaStream_t st, size_t n_pos) {
+  if (!scratch || !dst || n_rows == 0 || n_pos > c->n_cols) return cudaErrorInvalidValue;
+  if (n_pos == 0) n_pos = c->n_cols;
   switch (c->field) {
-    case FT63: return untranspose_impl<2>(c, scratch, dst, dst_stride, n_rows, st);
-    case FT127: return untranspose_impl<4>(c, scratch, dst, dst_stride, n_rows, st);
-    case FT191: return untranspose_impl<6>(c, scratch, dst, dst_stride, n_rows, st);
-    case FT255: return untranspose_impl<8>(c, scratch, dst, dst_stride, n_rows, st);
+    case FT63: return untranspose_impl<2>(scratch, dst, dst_stride, n_rows, n_pos, st);
+    case FT127: return untranspose_impl<4>(scratch, dst, dst_stride, n_rows, n_pos, st);
+    case FT191: return untranspose_impl<6>(scratch, dst, dst_stride, n_rows, n_pos, st);
+    case FT255: return untranspose_impl<8>(scratch, dst, dst_stride, n_rows, n_pos, st);
     default: return cudaErrorInvalidValue;
   }
 }

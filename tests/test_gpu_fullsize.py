@@ -187,3 +187,30 @@ def test_eager_commit_download_overlapped_with_upload():
         h_comm.fill_(-1)
         c.rerun_to_host(x, comm=h_comm.numpy().view(np.uint64), hashes=h_hash.numpy())
         assert (h_comm.numpy().view(np.uint64) == oc["comm"]).all() and c.get_root().root == oc["root"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pre_tail", [1, 0])
+def test_ligero_host_copy_chunk_schedule_with_short_last_chunks(pre_tail):
+    """The host->device copy of a Ligero commit ends with a half-size and a quarter-size row-chunk (what is left
+    after the last byte is pure latency).  Forced here at 2^20 by lowering the CTA thresholds: 8 body chunks + 4 + 2
+    rows, ragged last row; same LcCommit as the oracle."""
+    from lcpc_b200 import _cabi
+    field, length = P.FT255, (1 << 20) - 4321
+    enc = P.LigeroEncoding.new_from_dims(field, 16384, 32768)
+    oenc = O.Encoding.ligero_from_dims(field, 16384, 32768)
+    x = O.random_elems(field, length, seed=31)
+    knobs = {b"H2D_MIN_CHUNK_CTAS": (32, 1184), b"H2D_PRE_TAIL_MIN_CTAS": (1, 512), b"H2D_PRE_TAIL": (pre_tail, 1)}
+    for k, (v, _) in knobs.items():
+        _cabi.lib().lcpc_b200_set_tunable(k, v)
+    try:
+        c = P.LcCommit.commit(x, enc)
+        oc = oenc.commit(x)
+        assert oc["root"] == c.get_root().root and (oc["hashes"] == c.hashes).all() and (oc["comm"] == c.comm).all()
+        assert (oc["coeffs"] == c.coeffs).all()
+        y = O.random_elems(field, length, seed=32)
+        c.rerun(y)
+        assert oenc.commit(y)["root"] == c.get_root().root
+    finally:
+        for k, (_, d) in knobs.items():
+            _cabi.lib().lcpc_b200_set_tunable(k, d)

@@ -675,8 +675,11 @@ def test_brakedown_device_commit_keeps_codewords_column_major_until_asked(field,
             for i, col in enumerate(cols):
                 assert (vals[i] == comm[:, int(col)]).all()
                 assert O.verify_column_path(field, vals[i], paths[i], int(col), oc["root"])
+            t = O.random_elems(field, c.n_rows, seed=9)      # the row combination reads the coefficients there too
+            assert (c.collapse(t) == O.collapse(field, oc["coeffs"], t, c.n_rows, c.n_per_row)).all()
             assert (c.hashes == oc["hashes"]).all()
-            assert (c.comm == oc["comm"]).all() and (c.coeffs == oc["coeffs"]).all()   # materialised on demand
+            assert (c.coeffs == oc["coeffs"]).all() and (c.comm == oc["comm"]).all()   # materialised on demand
+            assert (c.collapse(t) == O.collapse(field, oc["coeffs"], t, c.n_rows, c.n_per_row)).all()
             vals2, _ = c.open_columns(cols)             # and afterwards
             assert (vals2 == vals).all()
             c.rerun_device(dev.data_ptr(), length)      # a second commit into the same object: lazy again
