@@ -11,7 +11,7 @@ BLAKE3 leaf -> Merkle tree, ending with the LcRoot.  Default workload: lcpc-lige
 `value`  : coefficients / device time, coefficients already resident in HBM (CUDA events).
 `e2e`    : same metric through the host-buffer C-ABI call: pinned host coefficients -> H2D -> commit
            -> D2H of the LcRoot, all inside the timed region.
-`roofline`: the dominant kernel (Ligero: ntt_pass_kernel; Brakedown: spmm_kernel phase) against the
+`roofline`: the dominant kernel (Ligero: ntt_pass_kernel; Brakedown: spmm_sum_kernel phase) against the
            measured HBM copy bandwidth of MEASURED_PEAKS.json.
 `cpu_baseline` / `--impl reference`: the CPU restatement of the reference's rayon path (oracle/, C +
            OpenMP; the Rust reference cannot be built in this image) on the box's host cores.
@@ -502,7 +502,7 @@ def bench_single(args, ctx, enc, field, n, torch, P, cpu_budget=0.0):
         nnz = sum(int(m["ptrs"][-1]) for mats in enc.matrices() for m in mats)
         code_bytes = nnz * (B + 4)
         # the expander phase = transposes + SpMM chain
-        dominant = dict(kernel=f"spmm_kernel chain + transposes (encode phase = {nl[0]} launches)",
+        dominant = dict(kernel=f"spmm_sum_kernel chain + transpose (encode phase = {nl[0]} launches)",
                         launches_per_step=max(1, nl[0]), phase_ms=phases[1],
                         moved_bytes_per_launch=None, traffic=None)
     # parity at the benchmarked size: the oracle (CPU restatement of the reference) commits the SAME coefficients --

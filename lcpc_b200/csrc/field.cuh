@@ -387,6 +387,89 @@ template <int FID> struct Field {
   }
   LCPC_DEV static void mac_wide(Wide &acc, const Elem &a, const Elem &b) { wide_add_fold(acc, mul_full(a, b)); }
 
+  // ---- sums of MANY products with no carry propagation per term ----
+  // mac_wide pays ~6N ALU operations per term on top of the N^2 wide multiply-adds (merging the product's two
+  // accumulator arrays, adding it to the running sum, folding).  Here the two arrays of the schoolbook rows PERSIST
+  // across terms -- E[k] at limb position k, O[k] at position k + 1, both 64-bit aligned for IMAD.WIDE -- every row
+  // of every term multiply-adds straight into them, and the one carry that leaves each chain (2N per term) is
+  // counted in C[q] (limb position N + q) instead of rippling upwards.  Nothing is merged or reduced until
+  // sum_reduce: per term N^2 wide multiply-adds + 2N carry adds.  Exact for up to 2^30 terms (C and the top limb
+  // count terms); the result is the canonical residue of sum_k a_k b_k / R, the same as reduce-every-product.
+  struct Sum { uint32_t E[2 * N], O[2 * N], C[N + 1]; };
+  LCPC_DEV static Sum sum_zero() {
+    Sum s;
+#pragma unroll
+    for (int i = 0; i < 2 * N; i++) s.E[i] = 0, s.O[i] = 0;
+#pragma unroll
+    for (int i = 0; i <= N; i++) s.C[i] = 0;
+    return s;
+  }
+  // d += carry, kept on the ALU pipe (the multiplier pipe is the one these loops saturate)
+  LCPC_DEV static void count_carry(uint32_t &d) {
+#ifdef __CUDA_ARCH__
+    asm volatile("addc.u32 %0, %0, %1;" : "+r"(d) : "r"(kZero32));
+#else
+    add_carry(d);
+#endif
+  }
+  LCPC_DEV static void sum_mac(Sum &s, const Elem &a, const Elem &b) {
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      uint32_t *Y = (i & 1) ? &s.O[i - 1] : &s.E[i];  // limb position i
+      uint32_t *X = (i & 1) ? &s.E[i + 1] : &s.O[i];  // limb position i + 1
+      const uint32_t bi = b.v[i];
+      mad_wide_cc(Y[0], Y[1], a.v[0], bi, Y[0], Y[1]);
+#pragma unroll
+      for (int j = 2; j < N; j += 2) madc_wide_cc(Y[j], Y[j + 1], a.v[j], bi, Y[j], Y[j + 1]);
+      count_carry(s.C[i]);  // out of position i + N - 1 into position i + N
+      mad_wide_cc(X[0], X[1], a.v[1], bi, X[0], X[1]);
+#pragma unroll
+      for (int j = 3; j < N; j += 2) madc_wide_cc(X[j - 1], X[j], a.v[j], bi, X[j - 1], X[j]);
+      count_carry(s.C[i + 1]);  // into position i + N + 1
+    }
+  }
+  // (sum / R) mod p in [0, p)
+  LCPC_DEV static Elem sum_reduce(const Sum &s) {
+    uint32_t T[2 * N + 1];
+    T[0] = s.E[0];
+    add_cc(T[1], s.E[1], s.O[0]);
+#pragma unroll
+    for (int k = 2; k < 2 * N; k++) addc_cc(T[k], s.E[k], s.O[k - 1]);
+    addc(T[2 * N], 0u, 0u);  // O[2N - 1] is never written
+    add_cc(T[N], T[N], s.C[0]);
+#pragma unroll
+    for (int q = 1; q < N; q++) addc_cc(T[N + q], T[N + q], s.C[q]);
+    addc(T[2 * N], T[2 * N], s.C[N]);
+    // REDC: (T + q p) / 2^(32N) = redc_low(low half) + high half, an (N+1)-limb value V whose top limb counts terms
+    Elem r = redc_low(T);
+    uint32_t V[N + 1];
+    add_cc(V[0], r.v[0], T[N]);
+#pragma unroll
+    for (int i = 1; i < N; i++) addc_cc(V[i], r.v[i], T[N + i]);
+    addc(V[N], T[2 * N], 0u);
+    // V mod p: quotient estimate from the top two limbs against the modulus' top limb + 1 (never too large, at most
+    // one too small: the top limb of every modulus here is >= 2^30 and V / p < 2^24), one conditional subtraction
+    const uint64_t top = ((uint64_t)V[N] << 32) | V[N - 1];
+    const uint32_t qhat = (uint32_t)(top / ((uint64_t)FP::P(N - 1) + 1u));
+    uint32_t Q[N + 1];
+    uint64_t carry = 0;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      const uint64_t pr = (uint64_t)qhat * FP::P(k) + carry;
+      Q[k] = (uint32_t)pr;
+      carry = pr >> 32;
+    }
+    Q[N] = (uint32_t)carry;
+    sub_cc(V[0], V[0], Q[0]);
+#pragma unroll
+    for (int k = 1; k < N; k++) subc_cc(V[k], V[k], Q[k]);
+    subc(V[N], V[N], Q[N]);  // 0 now: V < 2p < 2^(32N)
+    Elem t;
+#pragma unroll
+    for (int i = 0; i < N; i++) t.v[i] = V[i];
+    return cond_sub_p(t);
+  }
+
   // Montgomery reduction of the low half: (lo + q p) / 2^(32N) for the q that clears the low N limbs;
   // the result is <= p.  Rows of q*p are laid out as in mul_full_n (operand p, digits found on the fly);
   // `c` is the carry that the two arrays still owe to the position being cleared.

@@ -397,6 +397,68 @@ spmm_kernel(const uint32_t *__restrict__ seg_lo, const uint32_t *__restrict__ se
   stv<N>(yp, out.v);
 }
 
+// The same product with the carry-counting accumulator of field.cuh (Field::Sum): the rows of every term
+// multiply-add straight into two persistent accumulator arrays and only the 2N chain carries per term are counted,
+// instead of forming each product, merging its two arrays, adding it to the running sum and folding
+// (mac_wide: ~6N ALU operations per term, and ptxas turns a quarter of them into IMAD.X / IMAD.MOV on the multiplier
+// pipe -- the pipe that bounds this kernel: ncu sm__throughput 75-77 % with issue 52 %, ALU 50 %).
+// Same canonical result (sum_reduce brings the exact sum to [0, p)).  SPMM_MAC=0 selects spmm_kernel.
+// DEEP: twice as many gathers in flight per thread (8 for the 2- and 4-limb fields), the matrix values loaded just in
+// time (they are shared by all batch rows of an output: L1 hits), three CTAs per SM instead of four -- an A/B knob
+// (SPMM_SUM_DEEP) for the levels whose gathers miss in L2.
+template <int FID, bool DEEP>
+__global__ void __launch_bounds__(256, (Field<FID>::N <= 4 ? (DEEP ? 3 : 4) : 2))
+spmm_sum_kernel(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ colidx, const uint32_t *__restrict__ vals,
+                const uint32_t *__restrict__ x, uint32_t *__restrict__ y, size_t m, size_t n_rows) {
+  using F = Field<FID>;
+  constexpr int N = F::N;
+  constexpr int U = (N <= 4 ? 4 : 2) * (DEEP ? 2 : 1);
+  const size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= m * n_rows) return;
+  const size_t i = item / n_rows, r = item % n_rows;
+  const uint32_t k0 = __ldg(rowptr + i), k1 = __ldg(rowptr + i + 1);
+  typename F::Sum acc = F::sum_zero();
+  const uint32_t *xr = x + r * N;
+  const uint32_t pos_stride = (uint32_t)(n_rows * N);
+  const uint32_t *vp = vals + (size_t)k0 * N;
+  const uint32_t *cp = colidx + k0;
+  uint32_t left = k1 - k0;
+  for (; left >= U; left -= U, vp += U * N, cp += U) {
+    uint32_t j[U];
+    typename F::Elem xv[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) j[u] = __ldg(cp + u);
+    if constexpr (DEEP) {
+#pragma unroll
+      for (int u = 0; u < U; u++) ldv_early<N>(xv[u].v, xr + (size_t)j[u] * pos_stride);
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        typename F::Elem a;
+        ldv<N>(a.v, vp + u * N);
+        F::sum_mac(acc, xv[u], a);
+      }
+    } else {
+      typename F::Elem a[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        ldv_early<N>(xv[u].v, xr + (size_t)j[u] * pos_stride);
+        ldv_early<N>(a[u].v, vp + u * N);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) F::sum_mac(acc, xv[u], a[u]);
+    }
+  }
+  for (; left; left--, vp += N, cp++) {
+    const uint32_t j = __ldg(cp);
+    typename F::Elem a, xv;
+    ldv<N>(a.v, vp);
+    ldv<N>(xv.v, xr + (size_t)j * pos_stride);
+    F::sum_mac(acc, xv, a);
+  }
+  typename F::Elem out = F::sum_reduce(acc);
+  stv<N>(y + (i * n_rows + r) * N, out.v);
+}
+
 // The same product with the gathers SOFTWARE-PIPELINED one batch ahead: while a thread multiplies batch b, the
 // gathers of batch b+1 are already in flight and the column indices of batch b+2 are on their way, so a warp never
 // sits in front of an empty load queue between its multiply phases (spmm_kernel alternates "wait for 4 gathers" and
@@ -933,6 +995,17 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
           if (e != cudaSuccess) return e;
           continue;
         }
+      }
+      if (tunable("SPMM_MAC", 1) != 0 && Q == 1 && rg == n_rows && !hints && !pipe && M.m) {
+        const size_t items = M.m * n_rows;
+        if (tunable("SPMM_SUM_DEEP", 0) != 0)
+          spmm_sum_kernel<FID, true><<<(unsigned)((items + 255) / 256), 256, spmm_pad, st>>>(M.rowptr, M.colidx, M.vals, x, y, M.m, n_rows);
+        else
+          spmm_sum_kernel<FID, false><<<(unsigned)((items + 255) / 256), 256, spmm_pad, st>>>(M.rowptr, M.colidx, M.vals, x, y, M.m, n_rows);
+        launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        continue;
       }
       for (unsigned q = 0; q < Q; q++) {
         const uint32_t *lo = Q > 1 ? M.seg + (size_t)q * M.m : M.rowptr;

@@ -14,6 +14,8 @@ template <int FID>
 static int run(int op, uint64_t *r, const uint64_t *a, const uint64_t *b, size_t n) {
   using F = Field<FID>;
   typename F::Elem x, y, z;
+  const size_t terms = (size_t)op >> 8;
+  op &= 0xff;
   for (size_t i = 0; i < n; i++) {
     memcpy(x.v, a + i * (F::N / 2), F::BYTES);
     if (b) memcpy(y.v, b + i * (F::N / 2), F::BYTES);
@@ -32,6 +34,17 @@ static int run(int op, uint64_t *r, const uint64_t *a, const uint64_t *b, size_t
           F::mac_wide(acc, u, v);
         }
         z = F::template redc<2>(acc);
+        break;
+      }
+      case 8: {  // the same sum through the carry-counting accumulator (sum_mac / sum_reduce), n_terms in op >> 8
+        typename F::Sum acc = F::sum_zero();
+        for (size_t k = 0; k < terms; k++) {
+          typename F::Elem u, v;
+          memcpy(u.v, a + ((i + k) % n) * (F::N / 2), F::BYTES);
+          memcpy(v.v, b + ((i * 7 + k) % n) * (F::N / 2), F::BYTES);
+          F::sum_mac(acc, u, v);
+        }
+        z = F::sum_reduce(acc);
         break;
       }
       case 7:  // Karatsuba product (fields with a multiple of 4 limbs; others fall back to mul)

@@ -167,6 +167,23 @@ def test_field_carry_chains_on_host_emulation(hostcheck, field):
     for k in range(37):
         want = O.field_op(field, "add", want, O.field_op(field, "mul", a[:m][(idx + k) % m], b[:m][(idx * 7 + k) % m]))
     assert (r == want).all()
+    # the same sums through the carry-counting accumulator (Field::Sum: sum_mac / sum_reduce), 1..300 terms
+    for terms in (1, 2, 37, 300):
+        r = np.empty_like(a[:m])
+        assert hostcheck.hostcheck_field_op(field, 8 | (terms << 8), r.ctypes.data_as(C.c_void_p), a[:m].ctypes.data_as(C.c_void_p),
+                                            b[:m].ctypes.data_as(C.c_void_p), C.c_size_t(m)) == 0
+        want = O.ints_to_elems([0] * m, field)
+        for k in range(terms):
+            want = O.field_op(field, "add", want, O.field_op(field, "mul", a[:m][(idx + k) % m], b[:m][(idx * 7 + k) % m]))
+        assert (r == want).all(), terms
+    # ... and its worst case: 100 000 terms of (p-1)^2 (the carry counters and the quotient estimate of sum_reduce)
+    R = 1 << (64 * nl)
+    big = O.ints_to_elems([p - 1] * 8, field)
+    for terms in (1, 37, 100000):
+        r = np.empty_like(big)
+        assert hostcheck.hostcheck_field_op(field, 8 | (terms << 8), r.ctypes.data_as(C.c_void_p), big.ctypes.data_as(C.c_void_p),
+                                            big.ctypes.data_as(C.c_void_p), C.c_size_t(8)) == 0
+        assert (r == O.ints_to_elems([terms * (p - 1) * (p - 1) * pow(R, -1, p) % p] * 8, field)).all(), terms
     # worst case for the fold bound: every term is (p-1)^2
     big = O.ints_to_elems([p - 1] * 64, field)
     r = np.empty_like(big)

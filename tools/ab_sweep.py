@@ -27,6 +27,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--rows", type=int, default=0,
                     help="commit only this many rows under the 2^lgl encoding (the share of one rank of a sharded commit)")
+    ap.add_argument("--per-row", type=int, default=0,
+                    help="ligero: an encoding of this many coefficients per row (rho 1/2) instead of the 2^lgl one, with "
+                         "--rows rows: e.g. --per-row 8192 --rows 256 has the leaf-hash shape of one rank's column block at 8 GPUs")
     ap.add_argument("knobs", nargs="*")
     args = ap.parse_args()
     import torch
@@ -40,6 +43,8 @@ def main():
     n = 1 << args.lgl
     ctx = P.Context(0)
     enc = P.LigeroEncoding(field, n, ctx=ctx) if args.workload == "ligero" else P.SdigEncoding(field, n, seed=0, ctx=ctx)
+    if args.per_row:
+        enc = P.LigeroEncoding.new_from_dims(field, args.per_row, 2 * args.per_row, ctx=ctx)
     if args.rows:
         n = args.rows * enc.n_per_row
     x = B.synthetic_coeffs(field, n, seed=0)
