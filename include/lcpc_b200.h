@@ -184,7 +184,11 @@ int lcpc_b200_commit_download(lcpc_b200_commit *c, uint64_t *comm, uint64_t *coe
  * stream: ms[0] pad/copy, ms[1] row encode, ms[2] column leaf hashing, ms[3] Merkle layers; launches[]
  * (optional) = kernels launched by the encode / leaf-hash / Merkle phases.  Synchronises. */
 int lcpc_b200_commit_phase_times(lcpc_b200_commit *c, float ms[4], int launches[3]);
-/* device pointers of the same three arrays (owned by the commit) */
+/* device pointers of the same three arrays (owned by the commit).  A Brakedown commit made from device memory keeps
+ * its codewords and coefficient rows column-major in the encoder's work buffer (columns are hashed, opened and combined
+ * from there); the row-major `comm` / `coeffs` the reference's LcCommit holds are written when they are first asked
+ * for, here or in lcpc_b200_commit_download: ask only for what you need (pass NULL for the rest).  The pointers stay
+ * valid until the commit is freed, their CONTENTS until the next rerun on this object. */
 int lcpc_b200_commit_device_ptrs(lcpc_b200_commit *c, uint64_t **d_comm, uint64_t **d_coeffs, uint8_t **d_hashes);
 /* commit into an existing object AND copy the LcCommit fields out (any of comm / coeffs / hashes may be NULL):
  * row-chunks of comm and coeffs travel back on a second copy stream while later chunks are still being

@@ -685,6 +685,14 @@ def test_brakedown_device_commit_keeps_codewords_column_major_until_asked(field,
             c.rerun_device(dev.data_ptr(), length)      # a second commit into the same object: lazy again
             vals3, _ = c.open_columns(cols)
             assert (vals3 == vals).all() and c.get_root().root == oc["root"]
+            # the device pointers of the row-major matrices (written on this request when the commit was lazy)
+            from cuda.bindings import runtime as rt
+            d_comm, d_coeffs, d_hashes = c.device_ptrs()
+            enc.ctx.synchronize()
+            for ptr, want in ((d_comm, oc["comm"]), (d_coeffs, oc["coeffs"]), (d_hashes, oc["hashes"])):
+                got = np.empty_like(want)
+                err, = rt.cudaMemcpy(got.ctypes.data, ptr, got.nbytes, rt.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+                assert int(err) == 0 and (got == want).all()
             outer = O.random_elems(field, c.n_rows, seed=5)
             inner = O.random_elems(field, c.n_per_row, seed=6)
             proof = c.prove(outer, enc, P.Transcript(b"lazy comm"))
