@@ -428,9 +428,11 @@ template <int FID> struct Field {
       count_carry(s.C[i + 1]);  // into position i + N + 1
     }
   }
-  // (sum / R) mod p in [0, p)
-  LCPC_DEV static Elem sum_reduce(const Sum &s) {
-    uint32_t T[2 * N + 1];
+  // the sum as ONE integer of 2N+1 limbs (the top limb counts terms): what lanes that split a sum add up
+  struct Collected { uint32_t v[2 * N + 1]; };
+  LCPC_DEV static Collected sum_collect(const Sum &s) {
+    Collected t;
+    uint32_t *T = t.v;
     T[0] = s.E[0];
     add_cc(T[1], s.E[1], s.O[0]);
 #pragma unroll
@@ -440,6 +442,18 @@ template <int FID> struct Field {
 #pragma unroll
     for (int q = 1; q < N; q++) addc_cc(T[N + q], T[N + q], s.C[q]);
     addc(T[2 * N], T[2 * N], s.C[N]);
+    return t;
+  }
+  LCPC_DEV static void collected_add(Collected &a, const Collected &b) {
+    add_cc(a.v[0], a.v[0], b.v[0]);
+#pragma unroll
+    for (int k = 1; k < 2 * N; k++) addc_cc(a.v[k], a.v[k], b.v[k]);
+    addc(a.v[2 * N], a.v[2 * N], b.v[2 * N]);
+  }
+  // (sum / R) mod p in [0, p)
+  LCPC_DEV static Elem sum_reduce(const Sum &s) { return collected_reduce(sum_collect(s)); }
+  LCPC_DEV static Elem collected_reduce(const Collected &ct) {
+    const uint32_t *T = ct.v;
     // REDC: (T + q p) / 2^(32N) = redc_low(low half) + high half, an (N+1)-limb value V whose top limb counts terms
     Elem r = redc_low(T);
     uint32_t V[N + 1];

@@ -459,6 +459,64 @@ spmm_sum_kernel(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict_
   stv<N>(y + (i * n_rows + r) * N, out.v);
 }
 
+// Small levels (a few thousand outputs x the batch rows: fewer threads than the GPU has slots) are pure latency in
+// spmm_sum_kernel -- one thread walks its output's ~45 non-zeros in rounds of four dependent gathers.  Here G lanes
+// share an output: lane g takes non-zeros g, g + G, ..., the partial sums are collected (Field::Collected, one
+// 2N+1-limb integer each) and added across the G lanes with shuffles, lane 0 reduces and stores.  Lanes with the same
+// g hold consecutive batch rows, so a gather is still a run of 32 / G elements.  Same exact sum, same result.
+template <int FID, int G>
+__global__ void __launch_bounds__(256)
+spmm_sum_split_kernel(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ colidx, const uint32_t *__restrict__ vals,
+                      const uint32_t *__restrict__ x, uint32_t *__restrict__ y, size_t m, size_t n_rows) {
+  using F = Field<FID>;
+  constexpr int N = F::N;
+  constexpr int U = N <= 4 ? 4 : 2;
+  constexpr unsigned PER_WARP = 32 / G;  // (output, batch row) items per warp
+  const unsigned lane = threadIdx.x & 31u, g = lane / PER_WARP;
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t item = warp * PER_WARP + lane % PER_WARP, total = m * n_rows;
+  const bool live = item < total;
+  const size_t i = live ? item / n_rows : 0, r = live ? item % n_rows : 0;
+  typename F::Sum acc = F::sum_zero();
+  if (live) {
+    const uint32_t k0 = __ldg(rowptr + i), k1 = __ldg(rowptr + i + 1);
+    const uint32_t *xr = x + r * N;
+    const uint32_t pos_stride = (uint32_t)(n_rows * N);
+    for (uint32_t kb = k0 + g; kb < k1; kb += U * G) {
+      uint32_t j[U];
+      typename F::Elem a[U], xv[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) j[u] = __ldg(colidx + min(kb + u * G, k1 - 1));
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        ldv_early<N>(xv[u].v, xr + (size_t)j[u] * pos_stride);
+        ldv_early<N>(a[u].v, vals + (size_t)min(kb + u * G, k1 - 1) * N);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (kb + u * G >= k1) {  // past the row's end: a zero factor adds nothing
+#pragma unroll
+          for (int l = 0; l < N; l++) a[u].v[l] = 0;
+        }
+        F::sum_mac(acc, xv[u], a[u]);
+      }
+    }
+  }
+  typename F::Collected t = F::sum_collect(acc);
+  __syncwarp();
+#pragma unroll
+  for (unsigned off = PER_WARP; off < 32; off <<= 1) {
+    typename F::Collected o;
+#pragma unroll
+    for (int l = 0; l < 2 * N + 1; l++) o.v[l] = __shfl_xor_sync(0xffffffffu, t.v[l], off);
+    F::collected_add(t, o);
+  }
+  if (live && g == 0) {
+    typename F::Elem out = F::collected_reduce(t);
+    stv<N>(y + (i * n_rows + r) * N, out.v);
+  }
+}
+
 // The same product with the gathers SOFTWARE-PIPELINED one batch ahead: while a thread multiplies batch b, the
 // gathers of batch b+1 are already in flight and the column indices of batch b+2 are on their way, so a warp never
 // sits in front of an empty load queue between its multiply phases (spmm_kernel alternates "wait for 4 gathers" and
@@ -998,7 +1056,19 @@ static cudaError_t encode_impl(const ExpanderCode *c, const uint32_t *src, size_
       }
       if (tunable("SPMM_MAC", 1) != 0 && Q == 1 && rg == n_rows && !hints && !pipe && M.m) {
         const size_t items = M.m * n_rows;
-        if (tunable("SPMM_SUM_DEEP", 0) != 0)
+        // SPMM_SPLIT (default 1): levels with fewer (output, row) items than a quarter of the GPU's thread slots split
+        // every output's non-zeros over 4 lanes, those under an eighth over 8.  Measured (profiles/r02_ab_brakedown_split.jsonl):
+        // 2^20 (18 rows) encode 0.161 -> 0.145 ms, a 9-row share of 2^24 0.275 -> 0.256 ms; at 72 rows the 95 K- and
+        // 134 K-item levels gain nothing from it (one wave either way), hence the quarter.
+        const size_t slots = (size_t)148 * 2048;
+        const long split = tunable("SPMM_SPLIT", 1);
+        const unsigned G = split <= 0 ? 1 : (split > 1 ? (unsigned)split : (items * 8 <= slots ? 8 : (items * 4 <= slots ? 4 : 1)));
+        if (G == 4 || G == 8) {
+          const size_t threads = ((items + 32 / G - 1) / (32 / G)) * 32;
+          const unsigned grid = (unsigned)((threads + 255) / 256);
+          if (G == 4) spmm_sum_split_kernel<FID, 4><<<grid, 256, 0, st>>>(M.rowptr, M.colidx, M.vals, x, y, M.m, n_rows);
+          else spmm_sum_split_kernel<FID, 8><<<grid, 256, 0, st>>>(M.rowptr, M.colidx, M.vals, x, y, M.m, n_rows);
+        } else if (tunable("SPMM_SUM_DEEP", 0) != 0)
           spmm_sum_kernel<FID, true><<<(unsigned)((items + 255) / 256), 256, spmm_pad, st>>>(M.rowptr, M.colidx, M.vals, x, y, M.m, n_rows);
         else
           spmm_sum_kernel<FID, false><<<(unsigned)((items + 255) / 256), 256, spmm_pad, st>>>(M.rowptr, M.colidx, M.vals, x, y, M.m, n_rows);
