@@ -830,9 +830,7 @@ fused_levels_kernel(FusedOps ops, uint32_t *__restrict__ W, size_t n_rows, uint3
     stv<N>(win + (size_t)e * N, v);
   }
   __syncthreads();
-  typename F::Elem one = F::zero();
-  one.v[0] = 1;
-  for (int i = 0; i < 32 * N; i++) one = F::add(one, one);  // R mod p
+  const typename F::Elem one = F::one();  // R mod p
   for (int o = 0; o < ops.n; o++) {
     const FusedOp &op = ops.op[o];
     const uint32_t *in = (op.in_tmp ? tmp : win + (size_t)op.in_off * N);
@@ -905,9 +903,7 @@ fused_levels_kernel(FusedOps ops, uint32_t *__restrict__ W, size_t n_rows, uint3
 
 template <int FID> __global__ void one_mont_kernel(uint32_t *out) {
   using F = Field<FID>;
-  typename F::Elem one = F::zero();
-  one.v[0] = 1;
-  for (int i = 0; i < 32 * F::N; i++) one = F::add(one, one);  // 2^(32N) mod p
+  const typename F::Elem one = F::one();  // 2^(32N) mod p
   for (int l = 0; l < F::N; l++) out[l] = one.v[l];
 }
 

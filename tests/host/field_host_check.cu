@@ -47,6 +47,7 @@ static int run(int op, uint64_t *r, const uint64_t *a, const uint64_t *b, size_t
         z = F::sum_reduce(acc);
         break;
       }
+      case 9: z = F::one(); break;  // R mod p folded at compile time
       case 7:  // Karatsuba product (fields with a multiple of 4 limbs; others fall back to mul)
         if constexpr (F::N % 4 == 0) z = F::mul_karatsuba(x, y);
         else z = F::mul(x, y);

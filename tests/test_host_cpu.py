@@ -167,6 +167,14 @@ def test_field_carry_chains_on_host_emulation(hostcheck, field):
     for k in range(37):
         want = O.field_op(field, "add", want, O.field_op(field, "mul", a[:m][(idx + k) % m], b[:m][(idx * 7 + k) % m]))
     assert (r == want).all()
+    # R mod p folded at compile time (Field::one) == 2^(64 L) mod p, the value SURVEY.md's appendix A lists
+    r = np.empty_like(a[:1])
+    assert hostcheck.hostcheck_field_op(field, 9, r.ctypes.data_as(C.c_void_p), a[:1].ctypes.data_as(C.c_void_p),
+                                        b[:1].ctypes.data_as(C.c_void_p), C.c_size_t(1)) == 0
+    assert (r == O.ints_to_elems([(1 << (64 * nl)) % p], field)).all()
+    assert (r == O.ints_to_elems([{O.FT63: 0x2b8e9dfffffffffd, O.FT127: 0x23157ed08bbe3e8101a84dfffffffffe,
+                                   O.FT191: 0x305ae60140ca567045c6678ad9339c96892c79fffffffffd,
+                                   O.FT255: 0x33870cc92365adfe04ac41f68d514d2c211870def34d419ffab61bfffffffffe}[field]], field)).all()
     # the same sums through the carry-counting accumulator (Field::Sum: sum_mac / sum_reduce), 1..300 terms
     for terms in (1, 2, 37, 300):
         r = np.empty_like(a[:m])
