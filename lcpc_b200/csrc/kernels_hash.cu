@@ -19,6 +19,9 @@
 namespace lcpc {
 
 constexpr int HASH_THREADS = 128;
+#ifndef LCPC_LEAF_PREFETCH
+#define LCPC_LEAF_PREFETCH 0
+#endif
 
 template <int N>
 __device__ __forceinline__ void gload_elem(uint32_t (&v)[N], const uint32_t *p) {
@@ -66,6 +69,40 @@ leaf_chunk_kernel(const uint32_t *__restrict__ comm, size_t n_rows, size_t n_col
   // (compiled in only for sources that can end early: the whole-commit path pays nothing for it)
   const size_t rows_here = !SHORT_SOURCE ? n_rows
                            : (src_total > col ? min(n_rows, (src_total - col + row_stride - 1) / row_stride) : 0);
+#if LCPC_LEAF_PREFETCH
+  // The elements of block b + 1 are requested before block b is compressed (from_mont(0) = 0, so slots outside the
+  // column -- the zero prefix, the padding -- are just zero elements): without this every block starts by waiting for
+  // its own loads, which is where 60 % of the kernel's stall samples sat (profiles/r02_ncu_hot_leaf_chunk_ft255.txt).
+  // Measured (profiles/r02_ab_leaf_prefetch.jsonl): 0.748 against 0.734 ms (Ft255, 2^24), 0.285 against 0.277 ms
+  // (Ft127): the second element buffer costs 16-19 registers, i.e. two of the ten resident CTAs per SM, and the
+  // other warps were already covering those waits (ALU pipe 77-84 % busy).  Off.
+  typename F::Elem nxt[SPB];
+  auto request = [&](unsigned b) {
+    const size_t slot0 = (chunk_off + (size_t)b * 64) / B;
+#pragma unroll
+    for (int i = 0; i < SPB; i++) {
+      const size_t slot = slot0 + i;
+      nxt[i] = F::zero();
+      if (slot >= PRE && slot - PRE < rows_here) gload_elem<N>(nxt[i].v, cp + (slot - PRE) * row_stride * N);
+    }
+  };
+  request(0);
+  for (unsigned b = 0; b < n_blocks; b++) {
+    uint32_t m[16];
+#pragma unroll
+    for (int i = 0; i < SPB; i++) {
+      const typename F::Elem x = F::from_mont(nxt[i]);
+#pragma unroll
+      for (int l = 0; l < N; l++) m[i * N + l] = x.v[l];
+    }
+    if (b + 1 < n_blocks) request(b + 1);
+    const bool lastb = (b + 1 == n_blocks);
+    const uint32_t block_len = lastb ? (uint32_t)(chunk_len - (size_t)b * 64) : 64u;
+    uint32_t flags = (b == 0 ? b3::CHUNK_START : 0u) | (lastb ? b3::CHUNK_END : 0u);
+    if (lastb && n_chunks == 1) flags |= b3::ROOT;
+    b3::compress(cv, m, k, block_len, flags);
+  }
+#else
   for (unsigned b = 0; b < n_blocks; b++) {
     uint32_t m[16];
     const size_t slot0 = (chunk_off + (size_t)b * 64) / B;
@@ -87,6 +124,7 @@ leaf_chunk_kernel(const uint32_t *__restrict__ comm, size_t n_rows, size_t n_col
     if (lastb && n_chunks == 1) flags |= b3::ROOT;
     b3::compress(cv, m, k, block_len, flags);
   }
+#endif
   // single chunk: this is the digest; else the chunk chaining value for the merge kernel
   uint32_t *o = out + ((size_t)k * out_cols + col0 + col) * 8;
   reinterpret_cast<uint4 *>(o)[0] = make_uint4(cv[0], cv[1], cv[2], cv[3]);

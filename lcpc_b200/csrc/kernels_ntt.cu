@@ -14,6 +14,8 @@
 // (multi-GPU exchange fused into the transform).
 #include <algorithm>
 
+#include <type_traits>
+
 #include "field.cuh"
 #include "kernels.h"
 
@@ -324,6 +326,13 @@ __device__ __forceinline__ void ntt_round(uint32_t *smem, const uint32_t *__rest
   }
 }
 
+#ifndef LCPC_NTT_LOAD_BATCH
+#define LCPC_NTT_LOAD_BATCH 4
+#endif
+#ifndef LCPC_NTT_STORE_BATCH
+#define LCPC_NTT_STORE_BATCH 0
+#endif
+
 template <int FID>
 __global__ void __launch_bounds__(NTT_THREADS, LCPC_NTT_MIN_BLOCKS)
 ntt_pass_kernel(const uint32_t *__restrict__ src, uint32_t *dst, const uint32_t *__restrict__ roots, NttPass p) {
@@ -354,6 +363,40 @@ ntt_pass_kernel(const uint32_t *__restrict__ src, uint32_t *dst, const uint32_t 
   uint32_t *drow = dst + row * p.dst_stride * N;
   const unsigned granules = g.tile * NP;  // PW-limb pieces; consecutive lanes move consecutive pieces of HBM
 
+  // Staging: LCPC_NTT_LOAD_BATCH granules per thread are requested from HBM before the first one is stored to shared
+  // memory (a thread moves 16 granules of a 1024-element Ft255 tile; one at a time, or two as ptxas unrolled the plain
+  // loop, each round trip to HBM was exposed: the per-instruction stall samples of the --set full capture put 9 % of
+  // the kernel there).  0 = the plain loop.  Measured at 2^24 / Ft255 (profiles/r02_ab_ntt_load_batch.jsonl): encode 4.759 ms
+  // plain, 4.710 / 4.657 / 4.724 / 4.700 / 4.740 ms with 2 / 4 / 6 / 8 / 16 in flight (more registers held across the phase cost what the
+  // deeper queue gains); 4 is the default.
+#if LCPC_NTT_LOAD_BATCH > 0
+  for (unsigned g0 = threadIdx.x; g0 < granules; g0 += NTT_THREADS * LCPC_NTT_LOAD_BATCH) {
+    using V = typename std::conditional<PW == 4, uint4, uint2>::type;
+    V v[LCPC_NTT_LOAD_BATCH];
+#pragma unroll
+    for (int u = 0; u < LCPC_NTT_LOAD_BATCH; u++) {
+      const unsigned gi = g0 + u * NTT_THREADS;
+      const unsigned e = gi / NP, pl = gi % NP;
+      const unsigned t = (e >> g.tshift) & g.tmask, c = (e >> g.cshift) & g.cmask;
+      const size_t j = g.last ? g.base + e : g.base + ((size_t)t << g.log_stride) + c;
+      if constexpr (PW == 4) v[u] = make_uint4(0, 0, 0, 0);
+      else v[u] = make_uint2(0, 0);
+      if (gi < granules && j < p.src_valid) v[u] = __ldg(reinterpret_cast<const V *>(srow + j * N) + pl);
+    }
+#pragma unroll
+    for (int u = 0; u < LCPC_NTT_LOAD_BATCH; u++) {
+      const unsigned gi = g0 + u * NTT_THREADS;
+      if (gi >= granules) break;
+      const unsigned e = gi / NP, pl = gi % NP;
+      if (p.copy_dst) {
+        const unsigned t = (e >> g.tshift) & g.tmask, c = (e >> g.cshift) & g.cmask;
+        const size_t j = g.last ? g.base + e : g.base + ((size_t)t << g.log_stride) + c;
+        if (j < p.src_valid) reinterpret_cast<V *>(p.copy_dst + (row * p.copy_stride + j) * N)[pl] = v[u];
+      }
+      *reinterpret_cast<V *>(smem + ((size_t)pl * (g.tile + SmemLayout<N>::PLANE_PAD) + swz(e)) * PW) = v[u];
+    }
+  }
+#else
   for (unsigned gi = threadIdx.x; gi < granules; gi += NTT_THREADS) {
     const unsigned e = gi / NP, pl = gi % NP;
     const unsigned t = (e >> g.tshift) & g.tmask, c = (e >> g.cshift) & g.cmask;
@@ -375,6 +418,7 @@ ntt_pass_kernel(const uint32_t *__restrict__ src, uint32_t *dst, const uint32_t 
       *reinterpret_cast<uint2 *>(q) = v;
     }
   }
+#endif
   // last pass: its stages only ever use the 2^(S-1) twiddles w^(k n / 2^S); keep them in shared memory behind the
   // tile instead of paying an L2 round trip per butterfly
   uint32_t *tws = smem + SmemLayout<N>::bytes(g.tile) / 4;
@@ -410,6 +454,36 @@ ntt_pass_kernel(const uint32_t *__restrict__ src, uint32_t *dst, const uint32_t 
     __syncthreads();
   }
 
+  // (the store side the same way -- LCPC_NTT_STORE_BATCH granules read from shared memory before the first store --
+  // measured 4.680 / 4.682 ms for 4 / 8 against 4.657 ms for the plain loop: off)
+#if LCPC_NTT_STORE_BATCH > 0
+  for (unsigned g0 = threadIdx.x; g0 < granules; g0 += NTT_THREADS * LCPC_NTT_STORE_BATCH) {
+    using V = typename std::conditional<PW == 4, uint4, uint2>::type;
+    V v[LCPC_NTT_STORE_BATCH];
+#pragma unroll
+    for (int u = 0; u < LCPC_NTT_STORE_BATCH; u++) {
+      const unsigned gi = min(g0 + u * NTT_THREADS, granules - 1);
+      const unsigned e = gi / NP, pl = gi % NP;
+      v[u] = *reinterpret_cast<const V *>(smem + ((size_t)pl * (g.tile + SmemLayout<N>::PLANE_PAD) + swz(e)) * PW);
+    }
+#pragma unroll
+    for (int u = 0; u < LCPC_NTT_STORE_BATCH; u++) {
+      const unsigned gi = g0 + u * NTT_THREADS;
+      if (gi >= granules) break;
+      const unsigned e = gi / NP, pl = gi % NP;
+      const unsigned t = (e >> g.tshift) & g.tmask, c = (e >> g.cshift) & g.cmask;
+      const size_t j = g.last ? g.base + e : g.base + ((size_t)t << g.log_stride) + c;
+      uint32_t *out = drow + j * N;
+      if (p.sc.n_blocks) {
+        unsigned h = 0;
+        while (h + 1 < p.sc.n_blocks && j >= p.sc.starts[h + 1]) h++;
+        const size_t start = p.sc.starts[h], width = p.sc.starts[h + 1] - start;
+        out = p.sc.dst[h] + ((p.sc.row0 + row) * width + (j - start)) * N;
+      }
+      reinterpret_cast<V *>(out)[pl] = v[u];
+    }
+  }
+#else
   for (unsigned gi = threadIdx.x; gi < granules; gi += NTT_THREADS) {
     const unsigned e = gi / NP, pl = gi % NP;
     const unsigned t = (e >> g.tshift) & g.tmask, c = (e >> g.cshift) & g.cmask;
@@ -425,6 +499,7 @@ ntt_pass_kernel(const uint32_t *__restrict__ src, uint32_t *dst, const uint32_t 
     if constexpr (PW == 4) reinterpret_cast<uint4 *>(out)[pl] = *reinterpret_cast<const uint4 *>(q);
     else reinterpret_cast<uint2 *>(out)[pl] = *reinterpret_cast<const uint2 *>(q);
   }
+#endif
 }
 
 template <int FID>
