@@ -393,7 +393,10 @@ cudaError_t launch_merkle_layers(uint8_t *hashes, size_t n_leaves, unsigned n_la
   size_t off = 0, len = n_leaves;
   unsigned left = n_layers;
   while (left > 0) {
-    if (len >= 2 * HASH_THREADS * 148u) {
+    // MERKLE_WIDE_MIN: layers of at least this many nodes run one thread per output node, one launch per layer;
+    // below it a CTA reduces 256 nodes through 8 layers in shared memory (0 = subtrees only)
+    const size_t wide_min = (size_t)std::max<long>(0, tunable("MERKLE_WIDE_MIN", 2 * HASH_THREADS * 148));
+    if (wide_min && len >= wide_min) {
       // wide layer: one thread per node keeps every SM busy
       size_t n_out = len >> 1;
       merkle_layer_kernel<<<(unsigned)((n_out + HASH_THREADS - 1) / HASH_THREADS), HASH_THREADS, 0, stream>>>(
