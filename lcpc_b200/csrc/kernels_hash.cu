@@ -394,7 +394,9 @@ cudaError_t launch_merkle_layers(uint8_t *hashes, size_t n_leaves, unsigned n_la
   unsigned left = n_layers;
   while (left > 0) {
     // MERKLE_WIDE_MIN: layers of at least this many nodes run one thread per output node, one launch per layer;
-    // below it a CTA reduces 256 nodes through 8 layers in shared memory (0 = subtrees only)
+    // below it a CTA reduces 256 nodes through 8 layers in shared memory (0 = subtrees only).  Measured
+    // (profiles/r02_ab_merkle_wide.jsonl): subtrees only 0.0533 against 0.0503 ms at 2^19 leaves, 0.138 against
+    // 0.108 ms at 2^21; wide from 300 000 nodes up 0.0471 ms -- within noise of the default, which stays.
     const size_t wide_min = (size_t)std::max<long>(0, tunable("MERKLE_WIDE_MIN", 2 * HASH_THREADS * 148));
     if (wide_min && len >= wide_min) {
       // wide layer: one thread per node keeps every SM busy
