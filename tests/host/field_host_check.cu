@@ -47,6 +47,20 @@ static int run(int op, uint64_t *r, const uint64_t *a, const uint64_t *b, size_t
         z = F::sum_reduce(acc);
         break;
       }
+      case 10: {  // the same sum split over 4 accumulators (what spmm_sum_split_kernel's lanes do), collected and added
+        typename F::Sum part[4];
+        for (int g = 0; g < 4; g++) part[g] = F::sum_zero();
+        for (size_t k = 0; k < terms; k++) {
+          typename F::Elem u, v;
+          memcpy(u.v, a + ((i + k) % n) * (F::N / 2), F::BYTES);
+          memcpy(v.v, b + ((i * 7 + k) % n) * (F::N / 2), F::BYTES);
+          F::sum_mac(part[k % 4], u, v);
+        }
+        typename F::Collected t = F::sum_collect(part[0]);
+        for (int g = 1; g < 4; g++) F::collected_add(t, F::sum_collect(part[g]));
+        z = F::collected_reduce(t);
+        break;
+      }
       case 9: z = F::one(); break;  // R mod p folded at compile time
       case 7:  // Karatsuba product (fields with a multiple of 4 limbs; others fall back to mul)
         if constexpr (F::N % 4 == 0) z = F::mul_karatsuba(x, y);

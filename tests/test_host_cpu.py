@@ -184,6 +184,15 @@ def test_field_carry_chains_on_host_emulation(hostcheck, field):
         for k in range(terms):
             want = O.field_op(field, "add", want, O.field_op(field, "mul", a[:m][(idx + k) % m], b[:m][(idx * 7 + k) % m]))
         assert (r == want).all(), terms
+    # ... split over four accumulators whose collected sums are added (the lanes of spmm_sum_split_kernel)
+    for terms in (3, 45, 301):
+        r = np.empty_like(a[:m])
+        assert hostcheck.hostcheck_field_op(field, 10 | (terms << 8), r.ctypes.data_as(C.c_void_p), a[:m].ctypes.data_as(C.c_void_p),
+                                            b[:m].ctypes.data_as(C.c_void_p), C.c_size_t(m)) == 0
+        want = O.ints_to_elems([0] * m, field)
+        for k in range(terms):
+            want = O.field_op(field, "add", want, O.field_op(field, "mul", a[:m][(idx + k) % m], b[:m][(idx * 7 + k) % m]))
+        assert (r == want).all(), terms
     # ... and its worst case: 100 000 terms of (p-1)^2 (the carry counters and the quotient estimate of sum_reduce)
     R = 1 << (64 * nl)
     big = O.ints_to_elems([p - 1] * 8, field)
