@@ -1,6 +1,7 @@
 // lcpc_b200/csrc/host_transcript.cpp -- merlin 2.0 transcript (STROBE-128 over Keccak-f[1600]); see the header.
 #include "host_transcript.h"
 
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -53,8 +54,60 @@ static inline __attribute__((always_inline)) void keccak_rounds(uint64_t st[25])
   for (int i = 0; i < 25; i++) st[i] = a[i];
 }
 
+// The same permutation produced one output plane at a time, ping-ponging between two state arrays, with the next
+// round's column parities accumulated while the outputs are written (the order of the well-known 64-bit
+// implementations): every loop has a constant trip count and is unrolled, the arrays become registers.  With
+// andn / rorx this is the fastest single-state form on the hosts measured (tools/time_transcript.py); without BMI
+// the table-driven form above is.
+static inline __attribute__((always_inline)) uint64_t rol_or_id(uint64_t x, unsigned n) { return n ? rotl64(x, n) : x; }
+static inline __attribute__((always_inline)) void keccak_round_planes(const uint64_t *S, uint64_t *D, uint64_t *c, uint64_t rc) {
+  constexpr unsigned RHO[25] = {0,  1,  62, 28, 27, 36, 44, 6,  55, 20, 3,  10, 43,
+                                25, 39, 41, 45, 15, 21, 8,  18, 2,  61, 56, 14};  // r[x][y] at x + 5 y
+  uint64_t d[5], b[5];
+#pragma GCC unroll 5
+  for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rotl64(c[(x + 1) % 5], 1);
+#pragma GCC unroll 5
+  for (int Y = 0; Y < 5; Y++) {
+#pragma GCC unroll 5
+    for (int X = 0; X < 5; X++) {
+      // pi sends (x, y) to (X, Y) = (y, 2x + 3y): lane (X, Y) comes from y = X, x = 3 (Y - 3 X) mod 5
+      const int y = X, x = (3 * (Y + 15 - 3 * X)) % 5;
+      b[X] = rol_or_id(S[x + 5 * y] ^ d[x], RHO[x + 5 * y]);
+    }
+#pragma GCC unroll 5
+    for (int X = 0; X < 5; X++) {
+      uint64_t v = b[X] ^ (~b[(X + 1) % 5] & b[(X + 2) % 5]);
+      if (X == 0 && Y == 0) v ^= rc;
+      D[X + 5 * Y] = v;
+      c[X] = Y == 0 ? v : c[X] ^ v;
+    }
+  }
+}
+static inline __attribute__((always_inline)) void keccak_rounds_planes(uint64_t st[25]) {
+  static const uint64_t RC[24] = {
+      0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808aull, 0x8000000080008000ull,
+      0x000000000000808bull, 0x0000000080000001ull, 0x8000000080008081ull, 0x8000000000008009ull,
+      0x000000000000008aull, 0x0000000000000088ull, 0x0000000080008009ull, 0x000000008000000aull,
+      0x000000008000808bull, 0x800000000000008bull, 0x8000000000008089ull, 0x8000000000008003ull,
+      0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800aull, 0x800000008000000aull,
+      0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull};
+  uint64_t a[25], e[25], c[5];
+#pragma GCC unroll 25
+  for (int i = 0; i < 25; i++) a[i] = st[i];
+#pragma GCC unroll 5
+  for (int x = 0; x < 5; x++) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
+#pragma GCC unroll 12
+  for (int r = 0; r < 24; r += 2) {
+    keccak_round_planes(a, e, c, RC[r]);
+    keccak_round_planes(e, a, c, RC[r + 1]);
+  }
+#pragma GCC unroll 25
+  for (int i = 0; i < 25; i++) st[i] = a[i];
+}
+
 #if defined(__x86_64__) && defined(__GNUC__)
-__attribute__((target("bmi,bmi2"))) static void keccak_f1600_bmi(uint64_t st[25]) { keccak_rounds(st); }
+__attribute__((target("bmi,bmi2"))) static void keccak_f1600_bmi(uint64_t st[25]) { keccak_rounds_planes(st); }
+__attribute__((target("bmi,bmi2"))) static void keccak_f1600_bmi_table(uint64_t st[25]) { keccak_rounds(st); }
 #endif
 static void keccak_f1600_base(uint64_t st[25]) { keccak_rounds(st); }
 
@@ -129,46 +182,76 @@ __attribute__((target("avx512f,avx512vl"))) static void keccak_f1600_avx512(uint
 }
 #endif
 
-void keccak_f1600(uint64_t st[25]) {
 #if defined(__x86_64__) && defined(__GNUC__)
+static void (*keccak_pick())(uint64_t *) {
   static void (*const impl)(uint64_t *) = [] {
-    // LCPC_B200_KECCAK = base | bmi | avx512 forces a build the CPU supports (tests compare all of them)
+    // LCPC_B200_KECCAK = base | bmi | bmi_table | avx512 forces a build the CPU supports (tests compare all of them);
     const char *want = getenv("LCPC_B200_KECCAK");
     const std::string w = want ? want : "";
     const bool has_bmi = __builtin_cpu_supports("bmi") && __builtin_cpu_supports("bmi2");
     const bool has_512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512vl");
-    if (w == "base") return keccak_f1600_base;
-    if (w == "bmi" && has_bmi) return keccak_f1600_bmi;
-    if (has_512 && w != "bmi") return keccak_f1600_avx512;
-    return has_bmi ? keccak_f1600_bmi : keccak_f1600_base;
+    typedef void (*Fn)(uint64_t *);
+    if (w == "base") return (Fn)keccak_f1600_base;
+    if (w == "bmi" && has_bmi) return (Fn)keccak_f1600_bmi;
+    if (w == "bmi_table" && has_bmi) return (Fn)keccak_f1600_bmi_table;
+    if (w == "avx512" && has_512) return (Fn)keccak_f1600_avx512;
+    // Preference measured end to end (tools/time_transcript.py, ms per 65 536 absorbed Ft255 coefficients, this
+    // image's Xeon: plane-wise scalar with BMI 7.9, AVX-512 in place 8.7, portable 10.7; the bare permutations are
+    // within 2 % of each other -- the vector build pays for entering and leaving 512-bit code every 166 bytes).
+    // A timed selection at start-up was tried and dropped: on a shared host a 0.1 ms probe picks a different build
+    // from run to run.
+    if (has_bmi) return (Fn)keccak_f1600_bmi;
+    if (has_512) return (Fn)keccak_f1600_avx512;
+    return (Fn)keccak_f1600_base;
   }();
-  impl(st);
+  return impl;
+}
+#endif
+
+void keccak_f1600(uint64_t st[25]) {
+#if defined(__x86_64__) && defined(__GNUC__)
+  keccak_pick()(st);
 #else
   keccak_f1600_base(st);
 #endif
 }
 
+// The duplex state is written byte-wise by STROBE right before and read byte-wise right after every permutation.  The
+// vector build loads and stores it with five masked 512-bit moves and is fastest working on it in place; the scalar
+// builds' 25 64-bit loads would each wait for the narrower stores still in flight (store forwarding cannot merge
+// them: measured 16.2 against 8.0 ms per 65 536 absorbs), so they work on a copy, as memcpy's wide moves do not.
+bool keccak_in_place() {
+#if defined(__x86_64__) && defined(__GNUC__)
+  static const bool v = keccak_pick() == keccak_f1600_avx512;
+  return v;
+#else
+  return false;
+#endif
+}
+
 // ---- STROBE-128 as merlin instantiates it (merlin/src/strobe.rs) --------------------------------
 Strobe128::Strobe128(const uint8_t *protocol_label, size_t n) {
-  memset(st_, 0, sizeof st_);
+  memset(lanes_, 0, sizeof lanes_);
   const uint8_t head[6] = {1, (uint8_t)(R + 2), 1, 0, 1, 96};
-  memcpy(st_, head, 6);
-  memcpy(st_ + 6, "STROBEv1.0.2", 12);
-  uint64_t lanes[25];
-  memcpy(lanes, st_, 200);  // lanes are little-endian; so is every host this builds for
-  keccak_f1600(lanes);
-  memcpy(st_, lanes, 200);
+  memcpy(st(), head, 6);
+  memcpy(st() + 6, "STROBEv1.0.2", 12);
+  keccak_f1600(lanes_);  // lanes are little-endian; so is every host this builds for
   meta_ad(protocol_label, n, false);
 }
 
 void Strobe128::run_f() {
-  st_[pos_] ^= pos_begin_;
-  st_[pos_ + 1] ^= 0x04;
-  st_[R + 1] ^= 0x80;
-  uint64_t lanes[25];
-  memcpy(lanes, st_, 200);
-  keccak_f1600(lanes);
-  memcpy(st_, lanes, 200);
+  uint8_t *s = st();
+  s[pos_] ^= pos_begin_;
+  s[pos_ + 1] ^= 0x04;
+  s[R + 1] ^= 0x80;
+  if (keccak_in_place()) {
+    keccak_f1600(lanes_);  // the byte view and the lane view are the same storage
+  } else {
+    uint64_t lanes[25];
+    memcpy(lanes, lanes_, 200);
+    keccak_f1600(lanes);
+    memcpy(lanes_, lanes, 200);
+  }
   pos_ = 0, pos_begin_ = 0;
 }
 
@@ -178,12 +261,12 @@ void Strobe128::absorb(const uint8_t *data, size_t n) {
     size_t i = 0;
     for (; i + 8 <= run; i += 8) {  // eight bytes at a time (unaligned access through memcpy)
       uint64_t a, b;
-      memcpy(&a, st_ + pos_ + i, 8);
+      memcpy(&a, st() + pos_ + i, 8);
       memcpy(&b, data + i, 8);
       a ^= b;
-      memcpy(st_ + pos_ + i, &a, 8);
+      memcpy(st() + pos_ + i, &a, 8);
     }
-    for (; i < run; i++) st_[pos_ + i] ^= data[i];
+    for (; i < run; i++) st()[pos_ + i] ^= data[i];
     pos_ = (uint8_t)(pos_ + run), data += run, n -= run;
     if (pos_ == R) run_f();
   }
@@ -191,15 +274,15 @@ void Strobe128::absorb(const uint8_t *data, size_t n) {
 
 void Strobe128::overwrite(const uint8_t *data, size_t n) {
   for (size_t i = 0; i < n; i++) {
-    st_[pos_++] = data[i];
+    st()[pos_++] = data[i];
     if (pos_ == R) run_f();
   }
 }
 
 void Strobe128::squeeze(uint8_t *data, size_t n) {
   for (size_t i = 0; i < n; i++) {
-    data[i] = st_[pos_];
-    st_[pos_++] = 0;
+    data[i] = st()[pos_];
+    st()[pos_++] = 0;
     if (pos_ == R) run_f();
   }
 }
@@ -215,11 +298,37 @@ void Strobe128::begin_op(uint8_t flags, bool more) {
   if (force_f && pos_ != 0) run_f();
 }
 
+// meta_ad(label, false) followed by meta_ad(len, true), the pair every merlin message and challenge starts with: the
+// operation header, the label and the length are consecutive duplex input, so they are absorbed in ONE pass (the
+// prover appends 65 536 messages per vector; five small absorb calls per message were a third of the transcript time)
+void Strobe128::meta_ad_label_len(const uint8_t *label, size_t nl, const uint8_t len[4]) {
+  if (nl > 56) {
+    meta_ad(label, nl, false);
+    meta_ad(len, 4, true);
+    return;
+  }
+  uint8_t buf[64];
+  buf[0] = pos_begin_, buf[1] = FLAG_M | FLAG_A;  // begin_op: the header names where the previous operation began
+  pos_begin_ = (uint8_t)(pos_ + 1);
+  cur_flags_ = FLAG_M | FLAG_A;
+  memcpy(buf + 2, label, nl);
+  memcpy(buf + 2 + nl, len, 4);
+  absorb(buf, 2 + nl + 4);
+}
 void Strobe128::meta_ad(const uint8_t *data, size_t n, bool more) {
   begin_op(FLAG_M | FLAG_A, more);
   absorb(data, n);
 }
 void Strobe128::ad(const uint8_t *data, size_t n, bool more) {
+  if (!more && n <= 62) {  // header and a short message in one pass (a field element is 8..32 bytes)
+    uint8_t buf[64];
+    buf[0] = pos_begin_, buf[1] = FLAG_A;
+    pos_begin_ = (uint8_t)(pos_ + 1);
+    cur_flags_ = FLAG_A;
+    memcpy(buf + 2, data, n);
+    absorb(buf, 2 + n);
+    return;
+  }
   begin_op(FLAG_A, more);
   absorb(data, n);
 }
@@ -247,8 +356,7 @@ static inline void le32(uint8_t out[4], size_t n) {
 void Transcript::append_message(const uint8_t *label, size_t nl, const uint8_t *msg, size_t n) {
   uint8_t len[4];
   le32(len, n);
-  strobe_.meta_ad(label, nl, false);
-  strobe_.meta_ad(len, 4, true);
+  strobe_.meta_ad_label_len(label, nl, len);
   strobe_.ad(msg, n, false);
 }
 
@@ -261,8 +369,7 @@ void Transcript::append_u64(const uint8_t *label, size_t nl, uint64_t x) {
 void Transcript::challenge_bytes(const uint8_t *label, size_t nl, uint8_t *out, size_t n) {
   uint8_t len[4];
   le32(len, n);
-  strobe_.meta_ad(label, nl, false);
-  strobe_.meta_ad(len, 4, true);
+  strobe_.meta_ad_label_len(label, nl, len);
   strobe_.prf(out, n, false);
 }
 

@@ -15,11 +15,13 @@ namespace lcpc {
 namespace host {
 
 void keccak_f1600(uint64_t st[25]);
+bool keccak_in_place();  // whether the selected build is fastest on the caller's own state (no copy)
 
 class Strobe128 {
  public:
   explicit Strobe128(const uint8_t *protocol_label, size_t n);
   void meta_ad(const uint8_t *data, size_t n, bool more);
+  void meta_ad_label_len(const uint8_t *label, size_t nl, const uint8_t len[4]);  // meta_ad(label) + meta_ad(len, more)
   void ad(const uint8_t *data, size_t n, bool more);
   void prf(uint8_t *data, size_t n, bool more);
   void key(const uint8_t *data, size_t n, bool more);
@@ -32,7 +34,8 @@ class Strobe128 {
   void overwrite(const uint8_t *data, size_t n);
   void squeeze(uint8_t *data, size_t n);
   void begin_op(uint8_t flags, bool more);
-  uint8_t st_[200];
+  uint64_t lanes_[25];  // the duplex state; STROBE addresses it as 200 little-endian bytes (st_), Keccak as 25 lanes
+  uint8_t *st() { return reinterpret_cast<uint8_t *>(lanes_); }
   uint8_t pos_ = 0, pos_begin_ = 0, cur_flags_ = 0;
 };
 

@@ -39,9 +39,9 @@ def test_product_transcript_reproduces_merlin_vector():
     assert t.challenge_bytes(b"challenge", 32).hex() == MERLIN_VECTOR
 
 
-@pytest.mark.parametrize("impl", ["base", "bmi", "avx512"])
+@pytest.mark.parametrize("impl", ["base", "bmi", "bmi_table", "avx512"])
 def test_every_keccak_build_reproduces_merlin_vector_and_agrees(impl):
-    """The transcript's permutation has three builds (portable, BMI, AVX-512) chosen at run time; each one the CPU
+    """The transcript's permutation has four builds (portable, BMI plane-wise and table-driven, AVX-512) chosen at run time; each one the CPU
     supports is forced in a fresh process and must give the merlin vector and the same digest of a long absorb."""
     import subprocess
     import sys

@@ -13,7 +13,7 @@ for _ in range(7):
 print(round(best * 1e3, 3))
 """
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for which in ("base", "bmi", "avx512"):
+for which in ("base", "bmi_table", "bmi", "avx512"):
     env = dict(os.environ, LCPC_B200_KECCAK=which, PYTHONPATH=root)
     out = subprocess.run([sys.executable, "-c", CODE], env=env, capture_output=True, text=True)
     print(which, out.stdout.strip() or out.stderr.strip()[-200:], "ms per 65536 x 32-byte absorbs", flush=True)
